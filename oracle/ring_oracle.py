@@ -1,0 +1,249 @@
+"""CPU oracle for path E (SPDZ additive-shared fixed-precision forward) -- TEST INFRASTRUCTURE ONLY.
+
+This module is a torch-CPU int64 restatement of the reference's algorithm.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
+it; the product (``primia_b200``) never does.  All file:line citations are relative to
+``/root/reference``.
+
+Parity pin: the reference ships no golden vectors.  The pieces of
+the reference that are plain torch (``_pre_conv``, ``_post_conv``, ``triple_mat_mul``,
+``build_triple``'s ``c = a @ b``, ``reciprocal(method="newton")`` control flow) were
+executed *from the reference sources* in the build container by
+``tests/golden/make_golden.py`` and their outputs are committed under ``tests/golden/``;
+``tests/test_oracle_ring.py`` checks this restatement against them.  Two torch-1.4
+semantics cannot be executed on torch 2.11 and are pinned by hand here (SURVEY.md
+section 7 "Hard parts"): integer ``/`` == C truncation toward zero, and the fp32 scalar
+promotion in ``fix_precision``.
+
+Random streams (torch 1.4 ``random_``/``randint``) are not reproducible, so every share
+and triple is an explicit input: parity == identical outputs for identical inputs.
+"""
+from __future__ import annotations
+
+import torch
+
+I64 = torch.int64
+
+
+# --------------------------------------------------------------------------- E2 / E14
+def encode(x: torch.Tensor, base: int = 10, precision_fractional: int = 16) -> torch.Tensor:
+    """FixedPrecisionTensor.fix_precision -- precision.py:117-132.
+
+    ``(rational * base ** pf).long()``: a python-int scalar times an fp32 tensor is an
+    fp32 multiply (the scalar is rounded to fp32 first), then ``.long()`` truncates
+    toward zero.
+    """
+    assert x.dtype == torch.float32
+    scale = torch.tensor(float(base ** precision_fractional), dtype=torch.float32)
+    up = (x * scale).to(I64)
+    return up
+
+
+def decode(q: torch.Tensor, base: int = 10, precision_fractional: int = 16) -> torch.Tensor:
+    """FixedPrecisionTensor.float_precision -- precision.py:134-144 (gate arithmetic is the identity)."""
+    scale = torch.tensor(float(base ** precision_fractional), dtype=torch.float32)
+    return q.to(torch.float32) / scale
+
+
+# --------------------------------------------------------------------------- E3
+def share_from_random(secret: torch.Tensor, s0: torch.Tensor):
+    """AdditiveSharingTensor.generate_shares for n_workers == 2 -- additive_shared.py:336-365.
+
+    ``s0`` is the explicit random tensor (reference: ``random_(min_value, max_value)``);
+    shares = [s0, secret - s0] with native int64 wraparound.
+    """
+    return [s0.clone(), secret - s0]
+
+
+def reconstruct(shares) -> torch.Tensor:
+    """AdditiveSharingTensor.get -- additive_shared.py:287-301 (sum of shares, wraps mod 2**64)."""
+    out = shares[0].clone()
+    for s in shares[1:]:
+        out = out + s
+    return out
+
+
+# --------------------------------------------------------------------------- E5 / E10
+def pre_conv(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, dilation=1):
+    """_pre_conv -- nn/functional.py:79-166 (groups == 1), vectorised.
+
+    x: [B, C, H, W] int64, w: [Cout, C, kh, kw] int64.
+    Returns (im [B, M=Ho*Wo, K=C*kh*kw], w_r [K, Cout], B, Cout, Ho, Wo).
+    Column index k = ch*(kh*kw) + r*kw + c ; row index m = oh*Wo + ow (functional.py:129-149).
+    """
+    st = (stride, stride) if isinstance(stride, int) else tuple(stride)
+    pd = (padding, padding) if isinstance(padding, int) else tuple(padding)
+    dl = (dilation, dilation) if isinstance(dilation, int) else tuple(dilation)
+    B, C, H, W = x.shape
+    Co, Ck, kh, kw = w.shape
+    assert C == Ck
+    Ho = int(((H + 2 * pd[0] - dl[0] * (kh - 1) - 1) / st[0]) + 1)
+    Wo = int(((W + 2 * pd[1] - dl[1] * (kw - 1) - 1) / st[1]) + 1)
+    if pd != (0, 0):
+        x = torch.nn.functional.pad(x, (pd[1], pd[1], pd[0], pd[0]), "constant")
+        H += 2 * pd[0]
+        W += 2 * pd[1]
+    ch = torch.arange(C).view(C, 1, 1)
+    r = torch.arange(kh).view(1, kh, 1)
+    c = torch.arange(kw).view(1, 1, kw)
+    # NB the reference uses dilation[0] for the row term and dilation[1] for the column term
+    pattern = (r * W * dl[0] + c * dl[1] + ch * H * W).reshape(-1)  # [K]
+    oh = torch.arange(Ho).view(Ho, 1)
+    ow = torch.arange(Wo).view(1, Wo)
+    offset = (oh * st[0] * W + ow * st[1]).reshape(-1)  # [M]
+    idx = offset.view(-1, 1) + pattern.view(1, -1)  # [M, K]
+    im = x.reshape(B, -1)[:, idx]  # [B, M, K]
+    w_r = w.reshape(Co, -1).t()
+    return im, w_r, B, Co, Ho, Wo
+
+
+def post_conv(bias, res: torch.Tensor, B, Co, Ho, Wo):
+    """_post_conv -- nn/functional.py:170-201."""
+    if bias is not None:
+        res = res + bias
+    return res.permute(0, 2, 1).reshape(B, Co, Ho, Wo).contiguous()
+
+
+# --------------------------------------------------------------------------- E7 / E8
+def build_triple_c(a: torch.Tensor, b: torch.Tensor, op: str) -> torch.Tensor:
+    """c = a (op) b from build_triple -- beaver.py:32-52 (a, b are explicit inputs)."""
+    return torch.matmul(a, b) if op == "matmul" else a * b
+
+
+def spdz_mask(x_j, y_j, a_j, b_j):
+    """spdz_mask -- spdz.py:22-45: (x - a, y - b) on party j."""
+    return x_j - a_j, y_j - b_j
+
+
+def spdz_compute(j: int, delta, epsilon, a_j, b_j, c_j, op: str):
+    """spdz_compute -- spdz.py:64-122: delta(op)b + a(op)eps + c (+ delta(op)eps on party 0).
+
+    The reference evaluates ``delta_epsilon + delta_b + a_epsilon + c`` (j == 0) or
+    ``delta_b + a_epsilon + c``; int64 addition is associative mod 2**64 so order is moot.
+    """
+    f = torch.matmul if op == "matmul" else torch.mul
+    delta_b = f(delta, b_j)
+    a_eps = f(a_j, epsilon)
+    if j == 0:
+        return f(delta, epsilon) + delta_b + a_eps + c_j
+    return delta_b + a_eps + c_j
+
+
+def spdz_mul(op: str, x_sh, y_sh, triple_sh):
+    """spdz_mul -- spdz.py:125-197 for 2 parties.
+
+    x_sh, y_sh: [share0, share1]; triple_sh: [(a0,b0,c0), (a1,b1,c1)].
+    Returns the two output shares (before any truncation).
+    """
+    d, e = [], []
+    for j in range(2):
+        dj, ej = spdz_mask(x_sh[j], y_sh[j], triple_sh[j][0], triple_sh[j][1])
+        d.append(dj)
+        e.append(ej)
+    delta = d[0] + d[1]  # spdz.py:162
+    epsilon = e[0] + e[1]  # spdz.py:163
+    return [spdz_compute(j, delta, epsilon, *triple_sh[j], op) for j in range(2)]
+
+
+# --------------------------------------------------------------------------- E9
+def trunc_div(share: torch.Tensor, divisor: int) -> torch.Tensor:
+    """Per-share public division -- additive_shared.py:673-678 with torch-1.4 integer ``/``
+    (C truncation toward zero); reached from FixedPrecisionTensor.truncate precision.py:146-154."""
+    return torch.div(share, divisor, rounding_mode="trunc")
+
+
+def truncate(shares, base: int, precision_fractional: int):
+    return [trunc_div(s, base ** precision_fractional) for s in shares]
+
+
+# --------------------------------------------------------------------------- E4 / E6
+def conv2d_shared(x_sh, w_sh, triple_sh, stride, padding, base, pf, dilation=1):
+    """conv2d on shares -- nn/functional.py:204-308 followed by FPT.matmul's truncate
+    (precision.py:419-463).  Returns per-party NCHW output shares.
+    triple_sh[j] = (a_j [B,M,K], b_j [K,N], c_j [B,M,N])."""
+    pre = [pre_conv(x_sh[j], w_sh[j], stride, padding, dilation) for j in range(2)]
+    z = spdz_mul("matmul", [pre[0][0], pre[1][0]], [pre[0][1], pre[1][1]], triple_sh)
+    z = truncate(z, base, pf)
+    return [post_conv(None, z[j], *pre[j][2:]) for j in range(2)]
+
+
+def mul_shared(x_sh, y_sh, triple_sh, base, pf):
+    """FPT.mul for FPT>AST operands -- precision.py:264-366 (private mul then truncate)."""
+    z = spdz_mul("mul", x_sh, y_sh, triple_sh)
+    return truncate(z, base, pf)
+
+
+# --------------------------------------------------------------------------- E11
+def public_sub_shared(x_sh, const_sh):
+    """AST.sub(int) -- additive_shared.py:455-487: the public operand is *secret-shared*
+    (fresh randomness => explicit ``const_sh`` input) and subtracted share-wise."""
+    return [x_sh[j] - const_sh[j] for j in range(2)]
+
+
+def rsub_const(x_sh, const_sh):
+    """FPT.__rsub__ -- precision.py:240-241: ``(self - other) * -1``; the ``* -1`` is a public
+    mul per share (additive_shared.py:561-588)."""
+    return [(x_sh[j] - const_sh[j]) * -1 for j in range(2)]
+
+
+def newton_inv_sqrt_like(v_sh, consts_sh, triples, base, pf, iters=80):
+    """reciprocal(method="newton") -- precision.py:507-518, literally.
+
+    x0 = (C+1 - v)/C ; then 79x:  y = C+1 - v*(x*x) ; x = y*x/C   with C = 20.
+    consts_sh[i]  : explicit 2-party sharing of encode(21) used at iteration i.
+    triples[i]    : for i >= 1, three elementwise triples (for x*x, v*(x*x), y*x).
+    ``/ C`` is FPT.__truediv__ by a python int -> per-share trunc_div (precision.py:264-366
+    cmd == "div" with int other: no rescale, no truncate; additive_shared.py:673-678).
+    """
+    C = 20
+    x = None
+    for i in range(iters):
+        if x is not None:
+            xx = mul_shared(x, x, triples[i][0], base, pf)
+            vxx = mul_shared(v_sh, xx, triples[i][1], base, pf)
+            y = rsub_const(vxx, consts_sh[i])
+            yx = mul_shared(y, x, triples[i][2], base, pf)
+            x = [trunc_div(s, C) for s in yx]
+        else:
+            y = rsub_const(v_sh, consts_sh[i])
+            x = [trunc_div(s, C) for s in y]
+    return x
+
+
+def batch_norm_eval_shared(x_sh, mean_sh, var_sh, gamma_sh, beta_sh, consts_sh, triples, tri_norm,
+                           tri_affine, base, pf, iters=80):
+    """batch_norm (eval) -- nn/functional.py:44-75.  x_sh: per-party [B,C,H,W].
+
+    input -> [B*H*W (n-major within channel), C]; x = newton(var); normalized = x*(input-mean);
+    result = normalized*weight + bias; reshape back.  NB eps is ignored in eval (functional.py:62-64).
+    tri_norm / tri_affine: elementwise triples with broadcast shapes ([C] x [P,C]) and ([P,C] x [C]).
+    """
+    B, C, H, W = x_sh[0].shape
+    flat = [s.permute(1, 0, 2, 3).reshape(C, -1).t() for s in x_sh]  # [P, C]
+    inv = newton_inv_sqrt_like(var_sh, consts_sh, triples, base, pf, iters)
+    centered = [flat[j] - mean_sh[j] for j in range(2)]
+    normalized = mul_shared(inv, centered, tri_norm, base, pf)
+    res = mul_shared(normalized, gamma_sh, tri_affine, base, pf)
+    res = [res[j] + beta_sh[j] for j in range(2)]
+    return [r.t().reshape(C, B, H, W).permute(1, 0, 2, 3).contiguous() for r in res]
+
+
+# --------------------------------------------------------------------------- E13
+def avg_pool_shared(x_sh, k: int):
+    """avg_pool2d with kernel == stride == k, no padding -- nn/functional.py:460-525 mode "avg":
+    windows are summed per share and divided by k*k via AST.mean (additive_shared.py:720-729:
+    ``share.sum(dim) / m`` with integer trunc)."""
+    out = []
+    for s in x_sh:
+        B, C, H, W = s.shape
+        w = s.reshape(B, C, H // k, k, W // k, k).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // k, W // k, k * k)
+        out.append(trunc_div(w.sum(-1), k * k))
+    return out
+
+
+def linear_shared(x_sh, w_sh, b_sh, triple_sh, base, pf):
+    """linear -- nn/functional.py:10-14 -> native_linear: x.matmul(w.t()) + b  (Beaver matmul + truncate)."""
+    wt = [w.t() for w in w_sh]
+    z = spdz_mul("matmul", x_sh, wt, triple_sh)
+    z = truncate(z, base, pf)
+    return [z[j] + b_sh[j] for j in range(2)]

@@ -1,0 +1,111 @@
+"""Pin the path-E oracle against fixtures produced by executing the reference's own sources
+(tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import ring_oracle as R
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_pre_post_conv_matches_reference_output():
+    g = np.load(os.path.join(GOLDEN, "ring_preconv.npz"))
+    for i, (B, C, H, W, Co, k, s, p) in enumerate(g["cases"]):
+        x, w = T(g[f"x{i}"]), T(g[f"w{i}"])
+        im, wr, b_, co_, ho_, wo_ = R.pre_conv(x, w, int(s), int(p))
+        assert torch.equal(im, T(g[f"im{i}"]))
+        assert torch.equal(wr, T(g[f"wr{i}"]))
+        post = R.post_conv(None, torch.matmul(im, wr), b_, co_, ho_, wo_)
+        assert torch.equal(post, T(g[f"post{i}"]))
+
+
+def test_spdz_mask_compute_matches_reference_output():
+    g = np.load(os.path.join(GOLDEN, "ring_spdz.npz"))
+    for i in range(int(g["n"])):
+        op = str(g[f"op{i}"])
+        xs = [T(g[f"x{i}_{j}"]) for j in range(2)]
+        ys = [T(g[f"y{i}_{j}"]) for j in range(2)]
+        tri = [tuple(T(g[f"{n}{i}_{j}"]) for n in "abc") for j in range(2)]
+        d, e = zip(*[R.spdz_mask(xs[j], ys[j], tri[j][0], tri[j][1]) for j in range(2)])
+        for j in range(2):
+            assert torch.equal(d[j], T(g[f"d{i}_{j}"]))
+            assert torch.equal(e[j], T(g[f"e{i}_{j}"]))
+        z = R.spdz_mul(op, xs, ys, tri)
+        for j in range(2):
+            assert torch.equal(z[j], T(g[f"z{i}_{j}"]))
+
+
+def test_newton_control_flow_matches_reference_trace():
+    """oracle.newton_inv_sqrt_like must perform exactly the reference's op sequence."""
+    g = np.load(os.path.join(GOLDEN, "ring_newton.npz"))
+    trace = [t.split("|") for t in g["trace"]]
+    # iteration 0: rsub(21 - v), div 20 ; iterations 1..79: mul(x,x), mul(v,xx), rsub 21, mul(y,x), div 20
+    assert len(trace) == 2 + 79 * 5
+    assert [t[1] for t in trace[:2]] == ["rsub", "div"]
+    assert trace[0][3] == "21" and trace[1][3] == "20"
+    for it in range(79):
+        ops = trace[2 + it * 5: 7 + it * 5]
+        assert [o[1] for o in ops] == ["mul", "mul", "rsub", "mul", "div"]
+        x_prev = trace[1 + it * 5][0]
+        assert ops[0][2] == x_prev and ops[0][3] == x_prev  # x * x
+        assert ops[1][2] == "v" and ops[1][3] == ops[0][0]  # self * (x*x)
+        assert ops[2][2] == ops[1][0] and ops[2][3] == "21"  # C + 1 - ...
+        assert ops[3][2] == ops[2][0] and ops[3][3] == x_prev  # y * x
+        assert ops[4][2] == ops[3][0] and ops[4][3] == "20"  # / C
+
+
+def test_encode_fp32_promotion_and_trunc():
+    # probed 0.123456789 -> 1234567948140544 at (10,16)
+    x = torch.tensor([0.123456789, -0.123456789, 1.5, -2.75], dtype=torch.float32)
+    q = R.encode(x, 10, 16)
+    assert q[0].item() == 1234567948140544 and q[1].item() == -1234567948140544
+    q4 = R.encode(x, 10, 4)
+    assert q4.tolist() == [1234, -1234, 15000, -27500]
+    assert torch.allclose(R.decode(q4, 10, 4), torch.tensor([0.1234, -0.1234, 1.5, -2.75]))
+
+
+def test_trunc_div_is_c_truncation():
+    s = torch.tensor([7, -7, 19999, -19999, 0, -(2 ** 63)], dtype=torch.int64)
+    assert R.trunc_div(s, 10).tolist() == [0, 0, 1999, -1999, 0, -922337203685477580]
+
+
+def test_beaver_reconstructs_product_small_precision():
+    g = torch.Generator().manual_seed(1)
+    base, pf = 10, 4
+    x = torch.randn(1, 3, 8, 8, generator=g)
+    w = torch.randn(4, 3, 3, 3, generator=g) * 0.2
+    qx, qw = R.encode(x, base, pf), R.encode(w, base, pf)
+    r = lambda s: torch.randint(-(2 ** 63), 2 ** 63 - 1, s, dtype=torch.int64, generator=g)
+    xs = R.share_from_random(qx, r(qx.shape))
+    ws = R.share_from_random(qw, r(qw.shape))
+    M, K, N = 64, 27, 4
+    a, b = r((1, M, K)), r((K, N))
+    c = R.build_triple_c(a, b, "matmul")
+    a0, b0, c0 = r(a.shape), r(b.shape), r(c.shape)
+    tri = [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+    out = R.conv2d_shared(xs, ws, tri, 1, 1, base, pf)
+    got = R.decode(R.reconstruct(out), base, pf)
+    ref = torch.nn.functional.conv2d(x, w, padding=1)
+    # per-share truncation is off by at most 1 ulp of 10**-pf (+ wrap with prob ~ 2**-30)
+    assert (got - ref).abs().max() < 5e-3
+
+
+def test_avgpool_and_linear_shapes():
+    g = torch.Generator().manual_seed(2)
+    r = lambda s: torch.randint(-(2 ** 63), 2 ** 63 - 1, s, dtype=torch.int64, generator=g)
+    x = torch.randint(-1000, 1000, (1, 4, 14, 14), dtype=torch.int64, generator=g)
+    xs = R.share_from_random(x, r(x.shape))
+    out = R.avg_pool_shared(xs, 7)
+    assert out[0].shape == (1, 4, 2, 2)
+    exact = x.reshape(1, 4, 2, 7, 2, 7).permute(0, 1, 2, 4, 3, 5).reshape(1, 4, 2, 2, 49).sum(-1)
+    # share-wise truncation == exact/49 up to +-1 (and a 2**64/49 wrap term that reconstructs modulo)
+    rec = R.reconstruct(out)
+    wrap = (2 ** 64) // 49
+    diff = (rec - torch.div(exact, 49, rounding_mode="trunc"))
+    assert all(min(abs(int(d)), abs(abs(int(d)) - wrap)) <= 2 for d in diff.flatten())
