@@ -1,0 +1,183 @@
+/* primia_b200 -- C ABI of the B200-native hot paths of PriMIA.
+ *
+ * Every entry point takes raw DEVICE pointers (unless the name ends in _host), explicit sizes
+ * and a CUDA stream (cudaStream_t passed as void*), never allocates, and returns 0 on success
+ * or a PM_E* code (cudaGetLastError is folded into PM_ECUDA).  Callers own all buffers.
+ *
+ * The reference (gkaissis/PriMIA) has no FFI: its seam is Python operator overloading by dotted
+ * name.  Each group below cites the reference function(s) whose arithmetic it
+ * replaces (paths relative to the reference checkout).  The Python host side
+ * (primia_b200/ring, primia_b200/train, primia_b200/sy) mirrors those names on top of this ABI.
+ */
+#ifndef PRIMIA_B200_H
+#define PRIMIA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_EINVAL 1  /* bad shape / argument                      */
+#define PM_ECUDA 2   /* CUDA runtime error (see pm_last_error)    */
+#define PM_ERANGE 3  /* fixed-point encode overflow (precision.py:122-127 assert) */
+
+typedef void* pm_stream_t; /* cudaStream_t */
+
+const char* pm_last_error(void);
+int pm_version(void);
+int pm_device_sm_count(int* out);
+
+/* ===================================================================== path E : ring Z_2^64 */
+
+/* FixedPrecisionTensor.fix_precision  syft/frameworks/torch/tensors/interpreters/precision.py:117-132
+ * q = (int64) trunc( x * scale_f32 ); *overflow (device int, may be NULL) is set to 1 when |x*scale| >= 2^63. */
+int pm_encode_f32_i64(const float* x, float scale, int64_t* q, size_t n, int* overflow, pm_stream_t s);
+/* FixedPrecisionTensor.float_precision  precision.py:134-144 : x = (float) q / scale_f32 */
+int pm_decode_i64_f32(const int64_t* q, float scale, float* x, size_t n, pm_stream_t s);
+
+/* AdditiveSharingTensor.generate_shares (n_workers == 2)  additive_shared.py:336-365
+ * s0 ~ Philox4x32-10(seed, offset) over [-2^63, 2^63-2]; s1 = q - s0 (wraps). */
+int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, int64_t* s0, int64_t* s1, size_t n,
+                     pm_stream_t s);
+/* randint(-2^63, 2^63-1) of build_triple  syft/frameworks/torch/mpc/beaver.py:32-34 */
+int pm_random_i64(uint64_t seed, uint64_t offset, int64_t* out, size_t n, pm_stream_t s);
+
+/* _pre_conv im2col  syft/frameworks/torch/nn/functional.py:79-166 (groups==1)
+ * x [B,C,H,W] -> im [B, M=Ho*Wo, K=C*kh*kw], k = ch*kh*kw + r*kw + c, zero padding. */
+int pm_im2col_i64(const int64_t* x, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
+                  int64_t* im, pm_stream_t s);
+/* spdz_mask  syft/frameworks/torch/mpc/spdz.py:22-45 : delta_j = x_j - a_j (elementwise, same shape) */
+int pm_spdz_mask_i64(const int64_t* x, const int64_t* a, int64_t* delta, size_t n, pm_stream_t s);
+/* im2col-free fusion of _pre_conv + spdz_mask for the left operand: delta_j = im2col(x_j) - a_j */
+int pm_spdz_mask_im2col_i64(const int64_t* x, int B, int C, int H, int W, int kh, int kw, int stride, int pad,
+                            int dil, const int64_t* a, int64_t* delta, pm_stream_t s);
+/* right operand: weight_reshaped = w.reshape(Cout,-1).t() (functional.py:157) fused with spdz_mask:
+ * eps_j[k,n] = w_j[n*K + k] - b_j[k*N + n] */
+int pm_spdz_mask_wt_i64(const int64_t* w, int N, int K, const int64_t* b, int64_t* eps, pm_stream_t s);
+/* opening delta = delta_0 + delta_1  spdz.py:162-163.  `peer` may be a peer-mapped pointer of another GPU
+ * (NVLink P2P load) -- replaces the orchestrator hub. */
+int pm_open_add_i64(const int64_t* local, const int64_t* peer, int64_t* out, size_t n, pm_stream_t s);
+
+/* spdz_compute, op == "matmul"  spdz.py:64-122 (+ triple_mat_mul :54-59):
+ *   z_j = delta@b_j + a_j@eps + c_j (+ delta@eps if j == 0)   all mod 2^64
+ * delta,a_j [B,M,K]; eps,b_j [K,N]; c_j,z_j [B,M,N].  z_j must not alias inputs. `ws` is a [K,N] int64
+ * scratch (used when j == 0 for b_j + eps: delta@b + delta@eps == delta@(b+eps) exactly in the ring). */
+int pm_spdz_combine_matmul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a,
+                               const int64_t* b, const int64_t* c, int B, int M, int K, int N, int64_t* ws,
+                               int64_t* z, pm_stream_t s);
+/* spdz_compute, op == "mul" with torch broadcasting of a [C]-vector against [P,C]:
+ * mode 0: same shape n ; mode 1: left is [C], right is [P,C] ; mode 2: left is [P,C], right is [C]. */
+int pm_spdz_combine_mul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a, const int64_t* b,
+                            const int64_t* c, int mode, size_t P, size_t C, int64_t* z, pm_stream_t s);
+/* build_triple c = a @ b  beaver.py:36-52 ; also the plain ring matmul. C[B,M,N] = A[B,M,K] @ Bm[K,N] */
+int pm_matmul_i64(const int64_t* A, const int64_t* Bm, int B, int M, int K, int N, int64_t* C, pm_stream_t s);
+
+/* FixedPrecisionTensor.truncate -> AdditiveSharingTensor._public_div  precision.py:146-154,
+ * additive_shared.py:673-678: per-share C-style truncating divide. In place allowed. */
+int pm_trunc_div_i64(const int64_t* x, int64_t divisor, int64_t* out, size_t n, pm_stream_t s);
+/* truncate fused with _post_conv  functional.py:170-201: z [B,M,N] -> out [B,N,Ho*Wo] (= NCHW), (+bias[N]) */
+int pm_trunc_post_conv_i64(const int64_t* z, int64_t divisor, const int64_t* bias, int B, int M, int N,
+                           int64_t* out, pm_stream_t s);
+/* share-wise linear ops: out = alpha*x + beta*y (+gamma)  (AST add/sub/public mul, additive_shared.py:455-588).
+ * y may be NULL. ybcast: 0 same shape, 1 y is a length-C vector broadcast over rows of x [P,C], 2 y is a scalar[1]. */
+int pm_axpby_i64(int64_t alpha, const int64_t* x, int64_t beta, const int64_t* y, int ybcast, size_t P, size_t C,
+                 int64_t* out, pm_stream_t s);
+/* avg pool k x k, stride k on one share: sum / (k*k) with trunc  functional.py:460-525 + additive_shared.py:720-729 */
+int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t* out, pm_stream_t s);
+/* batch_norm layout shuffles functional.py:52-55,70-73: NCHW [B,C,H,W] <-> [P=B*H*W, C] */
+int pm_nchw_to_pc_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);
+int pm_pc_to_nchw_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);
+
+/* ===================================================================== path T : float training */
+/* Layout: activations NHWC; conv weights KRSC ([Cout][kh][kw][Cin]); fp32 ("_f32", parity mode) or
+ * bf16 activations with fp32 accumulation ("_bf16", throughput mode). Replaces the ATen CPU ops the
+ * worker executes for torchlib/models.py:466-482,268-284 via syft/workers/message_handler.py:105-118. */
+
+int pm_nchw_to_nhwc_f32(const float* x, int B, int C, int H, int W, float* out, pm_stream_t s);
+int pm_nchw_to_nhwc_f32_bf16(const float* x, int B, int C, int H, int W, int Cpad, void* out, pm_stream_t s);
+int pm_f32_to_bf16(const float* x, void* out, size_t n, pm_stream_t s);
+
+typedef struct {
+  int B, H, W, C;      /* input  NHWC */
+  int K, R, S;         /* filters: Cout, kh, kw */
+  int stride, pad;
+  int Ho, Wo;          /* output spatial */
+} pm_conv_t;
+
+/* conv2d forward: y[B,Ho,Wo,K] = x (*) w   (F.conv2d, models.py:219-235,379-381) */
+int pm_conv_fwd_f32(const pm_conv_t* p, const float* x, const float* w, float* y, pm_stream_t s);
+/* data gradient: dx[B,H,W,C] (= or +=) dy (*)^T w ; accumulate != 0 adds into dx */
+int pm_conv_dgrad_f32(const pm_conv_t* p, const float* dy, const float* w, float* dx, int accumulate, pm_stream_t s);
+/* weight gradient: dw[K,R,S,C] = sum_pix dy x ; ws: scratch of pm_conv_wgrad_ws_bytes() bytes */
+size_t pm_conv_wgrad_ws_bytes(const pm_conv_t* p);
+int pm_conv_wgrad_f32(const pm_conv_t* p, const float* x, const float* dy, float* dw, void* ws, pm_stream_t s);
+
+/* bf16 tensor-core (tcgen05 / TMEM) implicit-GEMM versions; x,w,y bf16; optional fused per-channel
+ * sum / sum-of-squares of the fp32 accumulators into stats[2*K] (doubles) for BatchNorm. */
+int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, pm_stream_t s);
+int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, pm_stream_t s);
+int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, void* ws, pm_stream_t s);
+
+/* BatchNorm2d (training) -- F.batch_norm, models.py:261,264,382 ; P = B*H*W rows of C channels.
+ * stats: [2*C] doubles (sum, sumsq), zeroed by the caller. */
+int pm_bn_stats_f32(const float* x, size_t P, int C, double* stats, pm_stream_t s);
+int pm_bn_stats_bf16(const void* x, size_t P, int C, double* stats, pm_stream_t s);
+/* mean/invstd from stats; running_mean/var momentum update (unbiased var), eps */
+int pm_bn_finalize(const double* stats, size_t P, int C, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, pm_stream_t s);
+/* y = act( (x-mean)*invstd*gamma + beta (+ residual) ) ; relu != 0 applies ReLU */
+int pm_bn_apply_f32(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    const float* residual, int relu, size_t P, int C, float* y, pm_stream_t s);
+int pm_bn_apply_bf16(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                     const void* residual, int relu, size_t P, int C, void* y, pm_stream_t s);
+/* backward: g = dy * (y_out > 0 if relu_mask) ; sums[0..C) = sum g , sums[C..2C) = sum g*xhat (doubles, zeroed by caller).
+ * If g_out != NULL the masked gradient is also written (used for the identity branch). */
+int pm_bn_bwd_reduce_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                         size_t P, int C, double* sums, float* g_out, pm_stream_t s);
+int pm_bn_bwd_reduce_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                          size_t P, int C, double* sums, void* g_out, pm_stream_t s);
+/* dx = gamma*invstd*( g - sum_g/P - xhat*sum_gxhat/P ) ; dgamma = sum_gxhat ; dbeta = sum_g (written into fp32 grads) */
+int pm_bn_bwd_apply_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                        const float* gamma, const double* sums, size_t P, int C, float* dx, float* dgamma,
+                        float* dbeta, pm_stream_t s);
+int pm_bn_bwd_apply_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                         const float* gamma, const double* sums, size_t P, int C, void* dx, float* dgamma,
+                         float* dbeta, pm_stream_t s);
+
+/* MaxPool2d(3,2,1) / AvgPool2d(3,2,1) (models.py:384-389) on NHWC; idx: uint8 argmax per output (first max wins) */
+int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s);
+int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s);
+int pm_maxpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, uint8_t* idx, pm_stream_t s);
+int pm_maxpool3s2_bwd_bf16(const void* dy, const uint8_t* idx, int B, int H, int W, int C, void* dx, pm_stream_t s);
+/* AvgPool2d(HW) -> [B,C] (models.py:400-404,477) and its backward (broadcast / HW) */
+int pm_gap_fwd_f32(const float* x, int B, int HW, int C, float* y, pm_stream_t s);
+int pm_gap_bwd_f32(const float* dy, int B, int HW, int C, float* dx, pm_stream_t s);
+int pm_gap_fwd_bf16(const void* x, int B, int HW, int C, float* y, pm_stream_t s);
+int pm_gap_bwd_bf16(const float* dy, int B, int HW, int C, void* dx, pm_stream_t s);
+
+/* Linear(512,ncls) + CrossEntropy (hard labels w/ optional class weights: nn.CrossEntropyLoss(weight,"mean");
+ * or soft targets: Cross_entropy_one_hot torchlib/utils.py:404-441), forward AND backward in one pass:
+ * logits[B,ncls]; loss[1]; dfeat[B,F]; dW[ncls,F]; db[ncls].  labels (int64) or soft (float [B,ncls]) -- one is NULL. */
+int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                     const float* class_w, int B, int F, int ncls, float* logits, float* loss, float* dfeat,
+                     float* dW, float* db, pm_stream_t s);
+
+/* torch.optim.Adam.step (train.py:280-303; L2 weight decay added to grad) on the flat parameter buffer */
+int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, pm_stream_t s);
+/* torch.optim.SGD.step (no momentum; weight decay) */
+int pm_sgd_step_f32(float* p, const float* g, size_t n, float lr, float weight_decay, pm_stream_t s);
+/* FedAvg tail (torchlib/utils.py:1078-1090): x *= scale (after the NCCL sum) ; and pre-scale for weighted averaging */
+int pm_scale_f32(float* x, float scale, size_t n, pm_stream_t s);
+/* KCRS (torch) <-> KRSC (ours) weight relayout, and the dgrad operand [C][R][S][K] in bf16 */
+int pm_kcrs_to_krsc_f32(const float* w, int K, int C, int R, int S, float* out, pm_stream_t s);
+int pm_krsc_to_kcrs_f32(const float* w, int K, int C, int R, int S, float* out, pm_stream_t s);
+int pm_krsc_to_bf16_fwd_dgrad(const float* w, int K, int C, int R, int S, int Cpad, void* w_fwd, void* w_dgrad,
+                              pm_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIMIA_B200_H */

@@ -1,0 +1,406 @@
+// Path T: BatchNorm2d (training) forward/backward, ReLU/residual fusion, max-pool and global average pool
+// on NHWC activations.  HBM-bound kernels: 16-byte vector accesses along the channel axis, per-thread
+// double accumulation for the statistics (the CPU reference accumulates in double too), grids sized as a
+// multiple of the SM count.  T = float (parity mode) or __nv_bfloat16 (throughput mode).
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  using raw = float4;
+  __device__ static void load(const float* p, float v[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float v[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float v[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float v[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+constexpr int BT = 256;
+
+// ---- per-channel sums: out[0..C) += sum f0 , out[C..2C) += sum f1   (f0,f1 produced by Functor per element)
+template <typename T, typename F>
+__global__ void __launch_bounds__(BT) chan_reduce_kernel(size_t P, int C, double* __restrict__ out, F f) {
+  constexpr int V = Vec<T>::N;
+  const int vr = C / V;                 // vectors per row (divides BT)
+  const int v = threadIdx.x % vr;
+  const int rpb = BT / vr;              // rows per block pass
+  const int r0 = threadIdx.x / vr;
+  double s0[V], s1[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0.0;
+  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += (size_t)gridDim.x * rpb) {
+    float a[V], b[V];
+    f(row, v * V, a, b);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s0[i] += (double)a[i]; s1[i] += (double)b[i]; }
+  }
+  // combine threads sharing a column group through shared memory
+  __shared__ double sh[2][BT][Vec<T>::N > 4 ? 1 : 1];
+  extern __shared__ double dyn[];       // [2][BT*V]
+  double* d0 = dyn;
+  double* d1 = dyn + BT * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { d0[threadIdx.x * V + i] = s0[i]; d1[threadIdx.x * V + i] = s1[i]; }
+  __syncthreads();
+  (void)sh;
+  for (int c = threadIdx.x; c < C; c += BT) {
+    const int vv = c / V, ii = c % V;
+    double t0 = 0.0, t1 = 0.0;
+    for (int r = 0; r < rpb; ++r) { t0 += d0[(r * vr + vv) * V + ii]; t1 += d1[(r * vr + vv) * V + ii]; }
+    atomicAdd(&out[c], t0);
+    atomicAdd(&out[C + c], t1);
+  }
+}
+
+template <typename T>
+struct StatsF {
+  const T* x; int C;
+  __device__ void operator()(size_t row, int c, float* a, float* b) const {
+    Vec<T>::load(x + row * C + c, a);
+#pragma unroll
+    for (int i = 0; i < Vec<T>::N; ++i) b[i] = a[i] * a[i];
+  }
+};
+
+// g = dy * (y_out > 0) ; a = g ; b = g * xhat ; optionally writes g
+template <typename T>
+struct BwdF {
+  const T* dy; const T* y_out; const T* x; const float* mean; const float* invstd; T* g_out; int C;
+  __device__ void operator()(size_t row, int c, float* a, float* b) const {
+    constexpr int V = Vec<T>::N;
+    float xv[V];
+    Vec<T>::load(dy + row * C + c, a);
+    Vec<T>::load(x + row * C + c, xv);
+    if (y_out) {
+      float yv[V];
+      Vec<T>::load(y_out + row * C + c, yv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] = yv[i] > 0.f ? a[i] : 0.f;
+    }
+    if (g_out) Vec<T>::store(g_out + row * C + c, a);
+#pragma unroll
+    for (int i = 0; i < V; ++i) b[i] = a[i] * ((xv[i] - mean[c + i]) * invstd[c + i]);
+  }
+};
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double P, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ rm,
+                                   float* __restrict__ rv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = stats[c] / P;
+  double var = stats[C + c] / P - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rm) {
+    const double unbiased = P > 1.0 ? var * P / (P - 1.0) : var;
+    rm[c] = (float)((1.0 - momentum) * (double)rm[c] + momentum * m);
+    rv[c] = (float)((1.0 - momentum) * (double)rv[c] + momentum * unbiased);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT)
+bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ res, int relu,
+                size_t nvec, int C, T* __restrict__ y) {
+  constexpr int V = Vec<T>::N;
+  for (size_t i = blockIdx.x * (size_t)BT + threadIdx.x; i < nvec; i += (size_t)gridDim.x * BT) {
+    const size_t e = i * V;
+    const int c = (int)(e % C);
+    float xv[V], rv[V];
+    Vec<T>::load(x + e, xv);
+    if (res) Vec<T>::load(res + e, rv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float v = (xv[k] - mean[c + k]) * invstd[c + k] * gamma[c + k] + beta[c + k];
+      if (res) v += rv[k];
+      if (relu) v = v > 0.f ? v : 0.f;
+      xv[k] = v;
+    }
+    Vec<T>::store(y + e, xv);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const T* __restrict__ x,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const double* __restrict__ sums, double invP, size_t nvec, int C, T* __restrict__ dx) {
+  constexpr int V = Vec<T>::N;
+  for (size_t i = blockIdx.x * (size_t)BT + threadIdx.x; i < nvec; i += (size_t)gridDim.x * BT) {
+    const size_t e = i * V;
+    const int c = (int)(e % C);
+    float g[V], xv[V], yv[V];
+    Vec<T>::load(dy + e, g);
+    Vec<T>::load(x + e, xv);
+    if (y_out) Vec<T>::load(y_out + e, yv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float gg = g[k];
+      if (y_out) gg = yv[k] > 0.f ? gg : 0.f;
+      const float is = invstd[c + k];
+      const float xhat = (xv[k] - mean[c + k]) * is;
+      const float mg = (float)(sums[c + k] * invP), mgx = (float)(sums[C + c + k] * invP);
+      g[k] = gamma[c + k] * is * (gg - mg - xhat * mgx);
+    }
+    Vec<T>::store(dx + e, g);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = (float)sums[c];
+  dgamma[c] = (float)sums[C + c];
+}
+
+// ---- max pool 3x3 s2 p1 (first max wins, like ATen's CPU kernel)
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, int H, int W, int C, int Ho, int Wo, size_t total,
+                                   T* __restrict__ y, uint8_t* __restrict__ idx) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t t = i / C;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const size_t b = t / Ho;
+    float best = -INFINITY;
+    int bi = 0;
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        const float v = to_f<T>(x[((b * H + ih) * W + iw) * C + c]);
+        if (first || v > best || v != v) { best = v; bi = r * 3 + s; first = false; }
+      }
+    }
+    y[i] = from_f<T>(best);
+    idx[i] = (uint8_t)bi;
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, int H, int W, int C,
+                                   int Ho, int Wo, size_t total, T* __restrict__ dx) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t t = i / C;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const size_t b = t / H;
+    float acc = 0.f;
+    for (int oh = h / 2; oh <= (h + 1) / 2; ++oh) {
+      if (oh >= Ho) continue;
+      const int r = h - (oh * 2 - 1);
+      if (r < 0 || r > 2) continue;
+      for (int ow = w / 2; ow <= (w + 1) / 2; ++ow) {
+        if (ow >= Wo) continue;
+        const int s = w - (ow * 2 - 1);
+        if (s < 0 || s > 2) continue;
+        const size_t o = ((b * Ho + oh) * Wo + ow) * C + c;
+        if (idx[o] == r * 3 + s) acc += to_f<T>(dy[o]);
+      }
+    }
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+template <typename T>
+__global__ void gap_fwd_kernel(const T* __restrict__ x, int HW, int C, size_t total, float* __restrict__ y) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t b = i / C;
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += to_f<T>(x[(b * HW + p) * C + c]);
+    y[i] = s / (float)HW;
+  }
+}
+
+template <typename T>
+__global__ void gap_bwd_kernel(const float* __restrict__ dy, int HW, int C, size_t total, T* __restrict__ dx) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t b = i / ((size_t)HW * C);
+    dx[i] = from_f<T>(dy[b * C + c] / (float)HW);
+  }
+}
+
+template <typename T>
+bool chan_ok(int C) { return C > 0 && C % Vec<T>::N == 0 && BT % (C / Vec<T>::N) == 0; }
+
+template <typename T, typename F>
+int launch_reduce(size_t P, int C, double* out, F f, cudaStream_t st) {
+  const int rpb = BT / (C / Vec<T>::N);
+  size_t blocks = (P + (size_t)rpb * 8 - 1) / ((size_t)rpb * 8);  // >= 8 rows per thread
+  const size_t cap = (size_t)pm_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
+  chan_reduce_kernel<T, F><<<(int)blocks, BT, smem, st>>>(P, C, out, f);
+  return 0;
+}
+
+template <typename T>
+int bn_stats_t(const T* x, size_t P, int C, double* stats, pm_stream_t s) {
+  PM_CHECK_ARG(x && stats && P > 0 && chan_ok<T>(C));
+  launch_reduce<T>(P, C, stats, StatsF<T>{x, C}, S(s));
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int bn_apply_t(const T* x, const float* mean, const float* invstd, const float* gamma, const float* beta, const T* res,
+               int relu, size_t P, int C, T* y, pm_stream_t s) {
+  PM_CHECK_ARG(x && mean && invstd && gamma && beta && y && C % Vec<T>::N == 0);
+  const size_t nvec = P * C / Vec<T>::N;
+  bn_apply_kernel<T><<<pm_grid(nvec, BT, 1, 16), BT, 0, S(s)>>>(x, mean, invstd, gamma, beta, res, relu, nvec, C, y);
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int bn_bwd_reduce_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, size_t P, int C,
+                    double* sums, T* g_out, pm_stream_t s) {
+  PM_CHECK_ARG(dy && x && mean && invstd && sums && P > 0 && chan_ok<T>(C));
+  launch_reduce<T>(P, C, sums, BwdF<T>{dy, y_out, x, mean, invstd, g_out, C}, S(s));
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int bn_bwd_apply_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma,
+                   const double* sums, size_t P, int C, T* dx, float* dgamma, float* dbeta, pm_stream_t s) {
+  PM_CHECK_ARG(dy && x && mean && invstd && gamma && sums && dx && C % Vec<T>::N == 0);
+  const size_t nvec = P * C / Vec<T>::N;
+  bn_bwd_apply_kernel<T><<<pm_grid(nvec, BT, 1, 16), BT, 0, S(s)>>>(dy, y_out, x, mean, invstd, gamma, sums,
+                                                                    1.0 / (double)P, nvec, C, dx);
+  if (dgamma && dbeta) bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, S(s)>>>(sums, C, dgamma, dbeta);
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int maxpool_fwd_t(const T* x, int B, int H, int W, int C, T* y, uint8_t* idx, pm_stream_t s) {
+  PM_CHECK_ARG(x && y && idx && B > 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * Ho * Wo * C;
+  maxpool_fwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(x, H, W, C, Ho, Wo, total, y, idx);
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int maxpool_bwd_t(const T* dy, const uint8_t* idx, int B, int H, int W, int C, T* dx, pm_stream_t s) {
+  PM_CHECK_ARG(dy && dx && idx && B > 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * H * W * C;
+  maxpool_bwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(dy, idx, H, W, C, Ho, Wo, total, dx);
+  PM_LAUNCH_OK();
+}
+
+}  // namespace
+
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int pm_bn_stats_f32(const float* x, size_t P, int C, double* stats, pm_stream_t s) { return bn_stats_t<float>(x, P, C, stats, s); }
+int pm_bn_stats_bf16(const void* x, size_t P, int C, double* stats, pm_stream_t s) { return bn_stats_t<bf16>((const bf16*)x, P, C, stats, s); }
+
+int pm_bn_finalize(const double* stats, size_t P, int C, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, pm_stream_t s) {
+  PM_CHECK_ARG(stats && mean && invstd && P > 0 && C > 0 && ((running_mean == nullptr) == (running_var == nullptr)));
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(s)>>>(stats, (double)P, C, eps, momentum, mean, invstd, running_mean,
+                                                        running_var);
+  PM_LAUNCH_OK();
+}
+
+int pm_bn_apply_f32(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    const float* residual, int relu, size_t P, int C, float* y, pm_stream_t s) {
+  return bn_apply_t<float>(x, mean, invstd, gamma, beta, residual, relu, P, C, y, s);
+}
+int pm_bn_apply_bf16(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                     const void* residual, int relu, size_t P, int C, void* y, pm_stream_t s) {
+  return bn_apply_t<bf16>((const bf16*)x, mean, invstd, gamma, beta, (const bf16*)residual, relu, P, C, (bf16*)y, s);
+}
+int pm_bn_bwd_reduce_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                         size_t P, int C, double* sums, float* g_out, pm_stream_t s) {
+  return bn_bwd_reduce_t<float>(dy, y_out, x, mean, invstd, P, C, sums, g_out, s);
+}
+int pm_bn_bwd_reduce_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                          size_t P, int C, double* sums, void* g_out, pm_stream_t s) {
+  return bn_bwd_reduce_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, P, C, sums, (bf16*)g_out, s);
+}
+int pm_bn_bwd_apply_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                        const float* gamma, const double* sums, size_t P, int C, float* dx, float* dgamma,
+                        float* dbeta, pm_stream_t s) {
+  return bn_bwd_apply_t<float>(dy, y_out, x, mean, invstd, gamma, sums, P, C, dx, dgamma, dbeta, s);
+}
+int pm_bn_bwd_apply_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                         const float* gamma, const double* sums, size_t P, int C, void* dx, float* dgamma,
+                         float* dbeta, pm_stream_t s) {
+  return bn_bwd_apply_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, sums, P, C, (bf16*)dx,
+                              dgamma, dbeta, s);
+}
+
+int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s) {
+  return maxpool_fwd_t<float>(x, B, H, W, C, y, idx, s);
+}
+int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s) {
+  return maxpool_bwd_t<float>(dy, idx, B, H, W, C, dx, s);
+}
+int pm_maxpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, uint8_t* idx, pm_stream_t s) {
+  return maxpool_fwd_t<bf16>((const bf16*)x, B, H, W, C, (bf16*)y, idx, s);
+}
+int pm_maxpool3s2_bwd_bf16(const void* dy, const uint8_t* idx, int B, int H, int W, int C, void* dx, pm_stream_t s) {
+  return maxpool_bwd_t<bf16>((const bf16*)dy, idx, B, H, W, C, (bf16*)dx, s);
+}
+
+int pm_gap_fwd_f32(const float* x, int B, int HW, int C, float* y, pm_stream_t s) {
+  PM_CHECK_ARG(x && y);
+  const size_t total = (size_t)B * C;
+  gap_fwd_kernel<float><<<pm_grid(total, 128), 128, 0, S(s)>>>(x, HW, C, total, y);
+  PM_LAUNCH_OK();
+}
+int pm_gap_fwd_bf16(const void* x, int B, int HW, int C, float* y, pm_stream_t s) {
+  PM_CHECK_ARG(x && y);
+  const size_t total = (size_t)B * C;
+  gap_fwd_kernel<bf16><<<pm_grid(total, 128), 128, 0, S(s)>>>((const bf16*)x, HW, C, total, y);
+  PM_LAUNCH_OK();
+}
+int pm_gap_bwd_f32(const float* dy, int B, int HW, int C, float* dx, pm_stream_t s) {
+  PM_CHECK_ARG(dy && dx);
+  const size_t total = (size_t)B * HW * C;
+  gap_bwd_kernel<float><<<pm_grid(total, 256), 256, 0, S(s)>>>(dy, HW, C, total, dx);
+  PM_LAUNCH_OK();
+}
+int pm_gap_bwd_bf16(const float* dy, int B, int HW, int C, void* dx, pm_stream_t s) {
+  PM_CHECK_ARG(dy && dx);
+  const size_t total = (size_t)B * HW * C;
+  gap_bwd_kernel<bf16><<<pm_grid(total, 256), 256, 0, S(s)>>>(dy, HW, C, total, (bf16*)dx);
+  PM_LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -1,0 +1,532 @@
+// Path E: SPDZ additive-secret-shared fixed-precision arithmetic in the ring Z_2^64 (two's-complement
+// int64 wraparound == the reference's native torch.int64 behaviour).  All kernels are exact integer
+// arithmetic: results are bit-identical to the CPU oracle for identical inputs.
+//
+// The dominant kernel is ring_gemm2_kernel: C (+)= A1@B1 + A2@B2 over int64 on the integer pipe
+// (no int64 MMA exists; 64-bit MAC = IMAD.WIDE.U32 + 2 IMAD).  Integer addition is associative, so
+// split-K with 64-bit atomics stays bit-exact.
+#include "common.cuh"
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void encode_kernel(const float* __restrict__ x, float scale, int64_t* __restrict__ q, size_t n,
+                              int* __restrict__ overflow) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < n; i += stride) {
+    float v = x[i] * scale;  // fp32 multiply, as torch does for float_tensor * python_scalar (precision.py:121)
+    // .long(): truncation toward zero; out-of-range is what the reference's assert rejects
+    if (!(fabsf(v) < 9223372036854775808.0f)) bad = true;
+    q[i] = (int64_t)v;
+  }
+  if (bad && overflow) atomicExch(overflow, 1);
+}
+
+__global__ void decode_kernel(const int64_t* __restrict__ q, float scale, float* __restrict__ x, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = (float)q[i] / scale;  // .float() is round-to-nearest-even like __ll2float_rn
+}
+
+// Philox4x32-10 (Salmon et al. 2011) written out; counter = (idx, offset), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ int64_t clamp_share_range(u64 r) {
+  // reference range is [-2^63, 2^63-2] (random_(min_value, max_value) / randint(low, high) exclude the top value)
+  int64_t v = (int64_t)r;
+  return v == INT64_MAX ? (int64_t)0 : v;
+}
+
+template <bool SHARE>
+__global__ void philox_kernel(const int64_t* __restrict__ q, u64 seed, u64 offset, int64_t* __restrict__ s0,
+                              int64_t* __restrict__ s1, size_t n) {
+  size_t pairs = (n + 1) / 2;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < pairs; i += stride) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), o);
+    int64_t r0 = clamp_share_range(((u64)o[1] << 32) | o[0]);
+    int64_t r1 = clamp_share_range(((u64)o[3] << 32) | o[2]);
+    size_t e = 2 * i;
+    s0[e] = r0;
+    if (SHARE) s1[e] = (int64_t)((u64)q[e] - (u64)r0);
+    if (e + 1 < n) {
+      s0[e + 1] = r1;
+      if (SHARE) s1[e + 1] = (int64_t)((u64)q[e + 1] - (u64)r1);
+    }
+  }
+}
+
+__global__ void sub_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ a, int64_t* __restrict__ d,
+                           size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = (int64_t)((u64)x[i] - (u64)a[i]);
+}
+
+__global__ void add_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ y, int64_t* __restrict__ d,
+                           size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = (int64_t)((u64)x[i] + (u64)y[i]);
+}
+
+__global__ void axpby_kernel(int64_t alpha, const int64_t* __restrict__ x, int64_t beta,
+                             const int64_t* __restrict__ y, int ybcast, size_t n, size_t C,
+                             int64_t* __restrict__ out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    u64 v = (u64)alpha * (u64)x[i];
+    if (y) {
+      size_t yi = ybcast == 0 ? i : (ybcast == 1 ? i % C : 0);
+      v += (u64)beta * (u64)y[yi];
+    }
+    out[i] = (int64_t)v;
+  }
+}
+
+__global__ void trunc_div_kernel(const int64_t* __restrict__ x, int64_t div, int64_t* __restrict__ out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = x[i] / div;  // C++ '/' on signed ints truncates toward zero
+}
+
+// z [B,M,N] -> out [B,N,M] with truncation (+bias[n])
+__global__ void trunc_post_conv_kernel(const int64_t* __restrict__ z, int64_t div, const int64_t* __restrict__ bias,
+                                       int M, int N, int64_t* __restrict__ out) {
+  __shared__ int64_t tile[32][33];
+  int b = blockIdx.z;
+  int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int64_t* zb = z + (size_t)b * M * N;
+  int64_t* ob = out + (size_t)b * M * N;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int m = m0 + r, n = n0 + threadIdx.x;
+    if (m < M && n < N) {
+      int64_t v = zb[(size_t)m * N + n];
+      if (div != 1) v = v / div;
+      if (bias) v = (int64_t)((u64)v + (u64)bias[n]);
+      tile[r][threadIdx.x] = v;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, m = m0 + threadIdx.x;
+    if (m < M && n < N) ob[(size_t)n * M + m] = tile[threadIdx.x][r];
+  }
+}
+
+// generic [B, R, Ccols] -> [B, Ccols, R] transpose of int64 (used for NCHW <-> [P,C] shuffles)
+__global__ void transpose_i64_kernel(const int64_t* __restrict__ x, int R, int Cc, int64_t* __restrict__ out) {
+  __shared__ int64_t tile[32][33];
+  int b = blockIdx.z;
+  int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int64_t* xb = x + (size_t)b * R * Cc;
+  int64_t* ob = out + (size_t)b * R * Cc;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int rr = r0 + r, cc = c0 + threadIdx.x;
+    if (rr < R && cc < Cc) tile[r][threadIdx.x] = xb[(size_t)rr * Cc + cc];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int cc = c0 + r, rr = r0 + threadIdx.x;
+    if (rr < R && cc < Cc) ob[(size_t)cc * R + rr] = tile[threadIdx.x][r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col (reference order k = ch*kh*kw + r*kw + c ; functional.py:129-149), optionally fused with "- a"
+// ------------------------------------------------------------------------------------------------
+template <bool MASK>
+__global__ void im2col_kernel(const int64_t* __restrict__ x, int C, int H, int W, int kh, int kw, int stride,
+                              int pad, int dil, int Ho, int Wo, const int64_t* __restrict__ a,
+                              int64_t* __restrict__ out, size_t total) {
+  const int K = C * kh * kw;
+  const int M = Ho * Wo;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t gstride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += gstride) {
+    int k = (int)(i % K);
+    size_t bm = i / K;
+    int m = (int)(bm % M);
+    int b = (int)(bm / M);
+    int cc = k % kw;
+    int r = (k / kw) % kh;
+    int ch = k / (kw * kh);
+    int oh = m / Wo, ow = m % Wo;
+    int ih = oh * stride - pad + r * dil;
+    int iw = ow * stride - pad + cc * dil;
+    int64_t v = 0;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)b * C + ch) * H + ih) * W + iw];
+    if (MASK) v = (int64_t)((u64)v - (u64)a[i]);
+    out[i] = v;
+  }
+}
+
+// eps[k,n] = w[n*K+k] - b[k*N+n]
+__global__ void mask_wt_kernel(const int64_t* __restrict__ w, int N, int K, const int64_t* __restrict__ b,
+                               int64_t* __restrict__ eps) {
+  __shared__ int64_t tile[32][33];
+  int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < K) tile[r][threadIdx.x] = w[(size_t)n * K + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, n = n0 + threadIdx.x;
+    if (n < N && k < K) {
+      size_t o = (size_t)k * N + n;
+      eps[o] = (int64_t)((u64)tile[threadIdx.x][r] - (u64)b[o]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// int64 GEMM with two (A,B) segments:  C[b] (+)= Cinit[b] + A1[b]@B1 + A2[b]@B2
+// ------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16, GTHREADS = 256;
+constexpr int GPAD = 2;
+
+__global__ void __launch_bounds__(GTHREADS, 2)
+ring_gemm2_kernel(const u64* __restrict__ A1, const u64* __restrict__ B1, const u64* __restrict__ A2,
+                  const u64* __restrict__ B2, const u64* __restrict__ Cinit, u64* __restrict__ Cout, int M, int K,
+                  int N, int splitK) {
+  __shared__ __align__(16) u64 As[2][GBK][GBM + GPAD];
+  __shared__ __align__(16) u64 Bs[2][GBK][GBN + GPAD];
+
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM;
+  const int batch = blockIdx.z / splitK, split = blockIdx.z % splitK;
+  const size_t a_off = (size_t)batch * M * K, c_off = (size_t)batch * M * N;
+
+  const int nk = (K + GBK - 1) / GBK;             // chunks per segment
+  const int nseg = A2 ? 2 : 1;
+  const int total = nk * nseg;
+  const int per = (total + splitK - 1) / splitK;
+  const int c_begin = split * per;
+  const int c_end = min(total, c_begin + per);
+
+  // loader mapping
+  const int a_k = tid & 15, a_m = tid >> 4;       // A: 16 k x 16 m per pass, 4 passes
+  const int b_n = tid & 63, b_k = tid >> 6;       // B: 64 n x 4 k per pass, 4 passes
+  // compute mapping
+  const int tx = tid & 15, ty = tid >> 4;
+
+  u64 acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+  u64 ra[4], rb[4];
+  auto gload = [&](int chunk) {
+    const int seg = chunk / nk, kc = chunk - seg * nk;
+    const u64* A = (seg == 0 ? A1 : A2) + a_off;
+    const u64* Bm = seg == 0 ? B1 : B2;
+    const int k = kc * GBK + a_k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + a_m + 16 * i;
+      ra[i] = (m < M && k < K) ? A[(size_t)m * K + k] : 0ull;
+    }
+    const int n = n0 + b_n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = kc * GBK + b_k + 4 * i;
+      rb[i] = (n < N && kk < K) ? Bm[(size_t)kk * N + n] : 0ull;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[buf][a_k][a_m + 16 * i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[buf][b_k + 4 * i][b_n] = rb[i];
+  };
+
+  if (c_begin < c_end) {
+    gload(c_begin);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int chunk = c_begin; chunk < c_end; ++chunk) {
+      const bool has_next = chunk + 1 < c_end;
+      if (has_next) gload(chunk + 1);
+#pragma unroll
+      for (int k = 0; k < GBK; ++k) {
+        u64 a[4], b[4];
+        const ulonglong2 a01 = *reinterpret_cast<const ulonglong2*>(&As[buf][k][ty * 4]);
+        const ulonglong2 a23 = *reinterpret_cast<const ulonglong2*>(&As[buf][k][ty * 4 + 2]);
+        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][tx * 4]);
+        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][tx * 4 + 2]);
+        a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+        b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+      }
+      if (has_next) {
+        sstore(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+      }
+    }
+  }
+
+  const bool atomic = splitK > 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const size_t o = c_off + (size_t)m * N + n;
+      u64 v = acc[i][j];
+      if (split == 0 && Cinit) v += Cinit[o];
+      if (atomic) atomicAdd(&Cout[o], v);
+      else Cout[o] = v;
+    }
+  }
+}
+
+static int launch_gemm2(const int64_t* A1, const int64_t* B1, const int64_t* A2, const int64_t* B2,
+                        const int64_t* Cinit, int64_t* C, int B, int M, int K, int N, cudaStream_t st) {
+  const int tm = (M + GBM - 1) / GBM, tn = (N + GBN - 1) / GBN;
+  const int nk = (K + GBK - 1) / GBK;
+  const int total = nk * (A2 ? 2 : 1);
+  const long tiles = (long)tm * tn * B;
+  int splitK = 1;
+  const long target = 2L * pm_num_sms() * 2;  // 2 CTAs/SM resident, aim for >= 2 waves
+  if (tiles < target) {
+    splitK = (int)((target + tiles - 1) / tiles);
+    int max_split = total / 4;  // keep >= 4 chunks (64 k-steps) per split
+    if (max_split < 1) max_split = 1;
+    if (splitK > max_split) splitK = max_split;
+  }
+  if ((long)B * splitK > 65535) return PM_EINVAL;
+  if (splitK > 1) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)B * M * N * sizeof(int64_t), st);
+    if (e != cudaSuccess) return pm_set_err(__FILE__, __LINE__, cudaGetErrorString(e));
+  }
+  dim3 grid(tn, tm, B * splitK);
+  ring_gemm2_kernel<<<grid, GTHREADS, 0, st>>>((const u64*)A1, (const u64*)B1, (const u64*)A2, (const u64*)B2,
+                                               (const u64*)Cinit, (u64*)C, M, K, N, splitK);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pm_set_err(__FILE__, __LINE__, cudaGetErrorString(e));
+  return PM_OK;
+}
+
+int pm_set_err(const char* file, int line, const char* msg) {
+  snprintf(g_pm_err, sizeof(g_pm_err), "%s:%d: %s", file, line, msg);
+  return PM_ECUDA;
+}
+
+// elementwise Beaver combine with broadcasting
+//   mode 0: all [n] ; mode 1: delta,a [C] vs eps,b,c,z [P,C] ; mode 2: delta,a,c,z [P,C] vs eps,b [C]
+__global__ void combine_mul_kernel(int j, const u64* __restrict__ delta, const u64* __restrict__ eps,
+                                   const u64* __restrict__ a, const u64* __restrict__ b, const u64* __restrict__ c,
+                                   int mode, size_t n, size_t C, u64* __restrict__ z) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const size_t il = mode == 1 ? i % C : i;
+    const size_t ir = mode == 2 ? i % C : i;
+    const u64 d = delta[il], e = eps[ir];
+    u64 v = d * b[ir] + a[il] * e + c[i];
+    if (j == 0) v += d * e;
+    z[i] = v;
+  }
+}
+
+__global__ void avgpool_kernel(const int64_t* __restrict__ x, int H, int W, int k, int64_t* __restrict__ out,
+                               size_t total) {
+  const int Ho = H / k, Wo = W / k;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int ow = (int)(i % Wo);
+    int oh = (int)((i / Wo) % Ho);
+    size_t bc = i / ((size_t)Wo * Ho);
+    const int64_t* p = x + (bc * H + (size_t)oh * k) * W + (size_t)ow * k;
+    u64 sacc = 0;
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) sacc += (u64)p[(size_t)r * W + c];
+    out[i] = (int64_t)sacc / (int64_t)(k * k);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pm_encode_f32_i64(const float* x, float scale, int64_t* q, size_t n, int* overflow, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(x && q);
+  encode_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(x, scale, q, n, overflow);
+  PM_LAUNCH_OK();
+}
+
+int pm_decode_i64_f32(const int64_t* q, float scale, float* x, size_t n, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(x && q);
+  decode_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(q, scale, x, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, int64_t* s0, int64_t* s1, size_t n,
+                     pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(q && s0 && s1);
+  philox_kernel<true><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(q, seed, offset, s0, s1, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_random_i64(uint64_t seed, uint64_t offset, int64_t* out, size_t n, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(out);
+  philox_kernel<false><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(nullptr, seed, offset, out, nullptr, n);
+  PM_LAUNCH_OK();
+}
+
+static int conv_out(int H, int k, int stride, int pad, int dil) { return (H + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
+
+int pm_im2col_i64(const int64_t* x, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
+                  int64_t* im, pm_stream_t s) {
+  PM_CHECK_ARG(x && im && B > 0 && C > 0 && stride > 0 && dil > 0 && pad >= 0);
+  const int Ho = conv_out(H, kh, stride, pad, dil), Wo = conv_out(W, kw, stride, pad, dil);
+  PM_CHECK_ARG(Ho > 0 && Wo > 0);
+  const size_t total = (size_t)B * Ho * Wo * C * kh * kw;
+  im2col_kernel<false><<<pm_grid(total, 256), 256, 0, S(s)>>>(x, C, H, W, kh, kw, stride, pad, dil, Ho, Wo, nullptr,
+                                                               im, total);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_mask_im2col_i64(const int64_t* x, int B, int C, int H, int W, int kh, int kw, int stride, int pad,
+                            int dil, const int64_t* a, int64_t* delta, pm_stream_t s) {
+  PM_CHECK_ARG(x && a && delta && B > 0 && C > 0 && stride > 0 && dil > 0 && pad >= 0);
+  const int Ho = conv_out(H, kh, stride, pad, dil), Wo = conv_out(W, kw, stride, pad, dil);
+  PM_CHECK_ARG(Ho > 0 && Wo > 0);
+  const size_t total = (size_t)B * Ho * Wo * C * kh * kw;
+  im2col_kernel<true><<<pm_grid(total, 256), 256, 0, S(s)>>>(x, C, H, W, kh, kw, stride, pad, dil, Ho, Wo, a, delta,
+                                                              total);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_mask_i64(const int64_t* x, const int64_t* a, int64_t* delta, size_t n, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(x && a && delta);
+  sub_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(x, a, delta, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_mask_wt_i64(const int64_t* w, int N, int K, const int64_t* b, int64_t* eps, pm_stream_t s) {
+  PM_CHECK_ARG(w && b && eps && N > 0 && K > 0);
+  dim3 grid((N + 31) / 32, (K + 31) / 32), block(32, 8);
+  mask_wt_kernel<<<grid, block, 0, S(s)>>>(w, N, K, b, eps);
+  PM_LAUNCH_OK();
+}
+
+int pm_open_add_i64(const int64_t* local, const int64_t* peer, int64_t* out, size_t n, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(local && peer && out);
+  add_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(local, peer, out, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_combine_matmul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a,
+                               const int64_t* b, const int64_t* c, int B, int M, int K, int N, int64_t* ws,
+                               int64_t* z, pm_stream_t s) {
+  PM_CHECK_ARG(delta && eps && a && b && c && z && B > 0 && M > 0 && K > 0 && N > 0 && (j == 0 || j == 1));
+  const int64_t* b_eff = b;
+  if (j == 0) {
+    PM_CHECK_ARG(ws != nullptr);
+    const size_t n = (size_t)K * N;
+    add_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(b, eps, ws, n);  // delta@b + delta@eps == delta@(b+eps) in Z_2^64
+    b_eff = ws;
+  }
+  return launch_gemm2(delta, b_eff, a, eps, c, z, B, M, K, N, S(s));
+}
+
+int pm_matmul_i64(const int64_t* A, const int64_t* Bm, int B, int M, int K, int N, int64_t* C, pm_stream_t s) {
+  PM_CHECK_ARG(A && Bm && C && B > 0 && M > 0 && K > 0 && N > 0);
+  return launch_gemm2(A, Bm, nullptr, nullptr, nullptr, C, B, M, K, N, S(s));
+}
+
+int pm_spdz_combine_mul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a, const int64_t* b,
+                            const int64_t* c, int mode, size_t P, size_t C, int64_t* z, pm_stream_t s) {
+  PM_CHECK_ARG(delta && eps && a && b && c && z && mode >= 0 && mode <= 2 && (j == 0 || j == 1));
+  const size_t n = P * C;
+  if (n == 0) return PM_OK;
+  combine_mul_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(j, (const u64*)delta, (const u64*)eps, (const u64*)a,
+                                                         (const u64*)b, (const u64*)c, mode, n, C, (u64*)z);
+  PM_LAUNCH_OK();
+}
+
+int pm_trunc_div_i64(const int64_t* x, int64_t divisor, int64_t* out, size_t n, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(x && out && divisor != 0);
+  trunc_div_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(x, divisor, out, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_trunc_post_conv_i64(const int64_t* z, int64_t divisor, const int64_t* bias, int B, int M, int N,
+                           int64_t* out, pm_stream_t s) {
+  PM_CHECK_ARG(z && out && divisor != 0 && B > 0 && M > 0 && N > 0 && B <= 65535);
+  dim3 grid((M + 31) / 32, (N + 31) / 32, B), block(32, 8);
+  trunc_post_conv_kernel<<<grid, block, 0, S(s)>>>(z, divisor, bias, M, N, out);
+  PM_LAUNCH_OK();
+}
+
+int pm_axpby_i64(int64_t alpha, const int64_t* x, int64_t beta, const int64_t* y, int ybcast, size_t P, size_t C,
+                 int64_t* out, pm_stream_t s) {
+  PM_CHECK_ARG(x && out && ybcast >= 0 && ybcast <= 2);
+  const size_t n = P * C;
+  if (n == 0) return PM_OK;
+  axpby_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(alpha, x, beta, y, ybcast, n, C, out);
+  PM_LAUNCH_OK();
+}
+
+int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t* out, pm_stream_t s) {
+  PM_CHECK_ARG(x && out && k > 0 && H % k == 0 && W % k == 0);
+  const size_t total = (size_t)B * C * (H / k) * (W / k);
+  avgpool_kernel<<<pm_grid(total, 128), 128, 0, S(s)>>>(x, H, W, k, out, total);
+  PM_LAUNCH_OK();
+}
+
+int pm_nchw_to_pc_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s) {
+  // functional.py:52-55: permute(1,0,2,3).reshape(C,-1).t() -> row p = b*HW + hw, col c
+  PM_CHECK_ARG(x && out && B > 0 && C > 0 && HW > 0 && B <= 65535);
+  dim3 grid((C + 31) / 32, (HW + 31) / 32, B), block(32, 8);
+  transpose_i64_kernel<<<grid, block, 0, S(s)>>>(x, C, HW, out);  // per b: [C,HW] -> [HW,C]
+  PM_LAUNCH_OK();
+}
+
+int pm_pc_to_nchw_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s) {
+  PM_CHECK_ARG(x && out && B > 0 && C > 0 && HW > 0 && B <= 65535);
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_i64_kernel<<<grid, block, 0, S(s)>>>(x, HW, C, out);  // per b: [HW,C] -> [C,HW]
+  PM_LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""MPC versions of torch.nn.functional ops on FixedPrecisionTensor > AdditiveSharingTensor.
+
+Mirrors syft/frameworks/torch/nn/functional.py: conv2d :204-308 (_pre_conv :79-166, _post_conv :170-201),
+batch_norm :44-75, avg_pool2d :460-525, linear :10-14."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .spdz import EmptyCryptoPrimitiveStoreError, open_shares, spdz_compute
+from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
+
+
+def _pre_conv(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """Party-local im2col (functional.py:79-166); kept for API parity -- conv2d itself never materialises it."""
+    assert groups == 1 and input.dim() == 4 and weight.dim() == 4
+    B, C, H, W = input.shape
+    Co, Ck, kh, kw = weight.shape
+    assert C == Ck
+    im = ops.im2col(input, kh, kw, stride, padding, dilation)
+    Ho = ops.conv_out_size(H, kh, stride, padding, dilation)
+    Wo = ops.conv_out_size(W, kw, stride, padding, dilation)
+    w_r = weight.reshape(Co, -1).t()
+    return im, w_r, B, Co, Ho, Wo
+
+
+def _post_conv(bias, res, batch_size, nb_channels_out, nb_rows_out, nb_cols_out):
+    """functional.py:170-201 (no truncation: divisor 1)"""
+    return ops.trunc_post_conv(res, 1, bias, nb_rows_out, nb_cols_out)
+
+
+def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None, stride=1, padding=0, dilation=1,
+           groups=1):
+    """functional.py:204-308 + FPT.matmul truncation (precision.py:419-463), fused per party:
+
+      delta_j = im2col(x_j) - a_j      (pm_spdz_mask_im2col_i64: no im2col tensor is materialised)
+      eps_j   = w_j^T - b_j            (pm_spdz_mask_wt_i64)
+      open    delta, eps               (peer read over NVLink)
+      z_j     = [delta | a_j] @ [b_j (+eps) ; eps] + c_j   (pm_spdz_combine_matmul_i64)
+      out_j   = NCHW( z_j / base**pf ) (pm_trunc_post_conv_i64)
+    """
+    assert groups == 1
+    x, w = input.child, weight.child
+    parties, provider = x.parties, x.provider
+    B, C, H, W = x.shape
+    Co, Ck, kh, kw = w.shape
+    assert C == Ck
+    Ho = ops.conv_out_size(H, kh, stride, padding, dilation)
+    Wo = ops.conv_out_size(W, kw, stride, padding, dilation)
+    M, K, N = Ho * Wo, C * kh * kw, Co
+    shapes = ((B, M, K), (K, N))
+    while True:
+        try:
+            tri = [p.crypto_store.get_keys(op="matmul", shapes=shapes, remove=False) for p in parties]
+            break
+        except EmptyCryptoPrimitiveStoreError as e:  # spdz.py:156-160
+            if provider is None or any(p.crypto_store.force_preprocessing for p in parties):
+                raise
+            provider.provide_primitives(parties=parties, **e.kwargs_)
+    d_sh = [ops.mask_im2col(x.child[j], tri[j][0], kh, kw, stride, padding, dilation) for j in range(2)]
+    e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
+    delta = open_shares(parties, d_sh)
+    eps = open_shares(parties, e_sh)
+    z = [spdz_compute(p, j, delta[j], eps[j], "matmul") for j, p in enumerate(parties)]
+    bsh = bias.child.child if bias is not None else [None, None]
+    div = weight.base ** weight.precision_fractional
+    out = [ops.trunc_post_conv(z[j], div, None, Ho, Wo) for j in range(2)]
+    if bias is not None:  # bias is added after truncation (functional.py:185-192 runs on the truncated matmul result)
+        out = [ops.axpby(1, out[j].permute(0, 2, 3, 1).contiguous(), 1, bsh[j]).permute(0, 3, 1, 2).contiguous()
+               for j in range(2)]
+    return FixedPrecisionTensor(x._new(out), input.base, input.precision_fractional)
+
+
+def batch_norm(input: FixedPrecisionTensor, running_mean, running_var, weight, bias, training=False,
+               exponential_average_factor=0.0, eps=1e-5):
+    """functional.py:44-75 (eval branch: eps ignored, inverse sqrt by the 80-step Newton iteration)."""
+    assert not training, "encrypted inference uses model.eval() (inference.py:288)"
+    B, C, H, W = input.shape
+    flat = input._new(input.child.map(ops.nchw_to_pc))
+    x = running_var.reciprocal(method="newton")
+    normalized = x * (flat - running_mean)
+    result = normalized * weight + bias
+    return input._new(result.child.map(lambda s: ops.pc_to_nchw(s, B, C, H, W)))
+
+
+def avg_pool2d(input: FixedPrecisionTensor, kernel_size, stride=None, padding=0):
+    """functional.py:460-525 mode "avg" with kernel == stride, no padding (models.py:400-404)."""
+    assert padding == 0 and (stride is None or stride == kernel_size)
+    return input._new(input.child.map(lambda s: ops.avgpool(s, kernel_size)))
+
+
+def linear(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias: FixedPrecisionTensor = None):
+    """functional.py:10-14 -> native_linear: input.matmul(weight.t()) + bias"""
+    wt = weight._new(weight.child.map(lambda s: s.t().contiguous()))
+    out = input.matmul(wt)
+    if bias is not None:
+        out = out + bias
+    return out

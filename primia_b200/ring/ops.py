@@ -1,0 +1,229 @@
+"""Tensor-level wrappers of the ring (Z_2^64) entry points of the C ABI.
+
+Each function takes/returns contiguous CUDA int64 tensors and launches on the current
+stream of the tensor's device.  No CPU path exists."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .._lib import PrimiaError, call, ptr, stream
+
+I64 = torch.int64
+
+__all__ = [
+    "encode", "decode", "share_gen", "random_i64", "im2col", "mask", "mask_im2col", "mask_wt", "open_add",
+    "combine_matmul", "combine_mul", "matmul", "trunc_div", "trunc_post_conv", "axpby", "avgpool",
+    "nchw_to_pc", "pc_to_nchw", "conv_out_size",
+]
+
+
+def _chk(t, dtype=I64):
+    if t.dtype != dtype:
+        raise PrimiaError(f"expected {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def conv_out_size(H, k, stride, pad, dil=1):
+    return (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def encode(x: torch.Tensor, base: int = 10, precision_fractional: int = 16, check_range: bool = True):
+    """precision.py:117-132"""
+    x = _chk(x, torch.float32)
+    q = torch.empty(x.shape, dtype=I64, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        call("pm_encode_f32_i64", ptr(x), ctypes.c_float(float(base ** precision_fractional)), ptr(q), x.numel(),
+             ptr(flag), stream())
+    if check_range and int(flag.item()):
+        raise AssertionError("tensor cannot be correctly embedded: choose bigger field or a lower precision")
+    return q
+
+
+def decode(q: torch.Tensor, base: int = 10, precision_fractional: int = 16):
+    """precision.py:134-144"""
+    q = _chk(q)
+    x = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        call("pm_decode_i64_f32", ptr(q), ctypes.c_float(float(base ** precision_fractional)), ptr(x), q.numel(), stream())
+    return x
+
+
+def share_gen(q: torch.Tensor, seed: int, offset: int):
+    """additive_shared.py:336-365 (2 parties)"""
+    q = _chk(q)
+    s0, s1 = torch.empty_like(q), torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        call("pm_share_gen_i64", ptr(q), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(s0), ptr(s1), q.numel(), stream())
+    return s0, s1
+
+
+def random_i64(shape, seed: int, offset: int, device):
+    out = torch.empty(shape, dtype=I64, device=device)
+    with torch.cuda.device(out.device):
+        call("pm_random_i64", seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(out), out.numel(), stream())
+    return out
+
+
+def im2col(x, kh, kw, stride, pad, dil=1):
+    x = _chk(x)
+    B, C, H, W = x.shape
+    Ho, Wo = conv_out_size(H, kh, stride, pad, dil), conv_out_size(W, kw, stride, pad, dil)
+    out = torch.empty((B, Ho * Wo, C * kh * kw), dtype=I64, device=x.device)
+    with torch.cuda.device(x.device):
+        call("pm_im2col_i64", ptr(x), B, C, H, W, kh, kw, stride, pad, dil, ptr(out), stream())
+    return out
+
+
+def mask(x, a):
+    x, a = _chk(x), _chk(a)
+    assert x.shape == a.shape, (x.shape, a.shape)
+    d = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        call("pm_spdz_mask_i64", ptr(x), ptr(a), ptr(d), x.numel(), stream())
+    return d
+
+
+def mask_im2col(x, a, kh, kw, stride, pad, dil=1):
+    x, a = _chk(x), _chk(a)
+    B, C, H, W = x.shape
+    Ho, Wo = conv_out_size(H, kh, stride, pad, dil), conv_out_size(W, kw, stride, pad, dil)
+    assert tuple(a.shape) == (B, Ho * Wo, C * kh * kw), (a.shape, (B, Ho * Wo, C * kh * kw))
+    d = torch.empty_like(a)
+    with torch.cuda.device(x.device):
+        call("pm_spdz_mask_im2col_i64", ptr(x), B, C, H, W, kh, kw, stride, pad, dil, ptr(a), ptr(d), stream())
+    return d
+
+
+def mask_wt(w2d, b):
+    """eps = w2d.t() - b with w2d [N,K] contiguous, b [K,N]"""
+    w2d, b = _chk(w2d), _chk(b)
+    N, K = w2d.shape
+    assert tuple(b.shape) == (K, N)
+    e = torch.empty_like(b)
+    with torch.cuda.device(b.device):
+        call("pm_spdz_mask_wt_i64", ptr(w2d), N, K, ptr(b), ptr(e), stream())
+    return e
+
+
+def open_add(local, peer):
+    local, peer = _chk(local), _chk(peer)
+    out = torch.empty_like(local)
+    with torch.cuda.device(local.device):
+        call("pm_open_add_i64", ptr(local), ptr(peer), ptr(out), local.numel(), stream())
+    return out
+
+
+def combine_matmul(j, delta, eps, a, b, c):
+    delta, eps, a, b, c = map(_chk, (delta, eps, a, b, c))
+    if delta.dim() == 2:  # plain [M,K] @ [K,N] (linear, functional.py:10-14)
+        Bt, (M, K) = 1, delta.shape
+        assert tuple(c.shape) == (M, eps.shape[1])
+    else:
+        Bt, M, K = delta.shape
+        assert tuple(c.shape) == (Bt, M, eps.shape[1])
+    K2, N = eps.shape
+    assert K == K2 and a.shape == delta.shape and b.shape == eps.shape
+    z = torch.empty_like(c)
+    ws = torch.empty_like(b) if j == 0 else None
+    with torch.cuda.device(delta.device):
+        call("pm_spdz_combine_matmul_i64", j, ptr(delta), ptr(eps), ptr(a), ptr(b), ptr(c), Bt, M, K, N, ptr(ws), ptr(z),
+             stream())
+    return z
+
+
+def combine_mul(j, delta, eps, a, b, c):
+    delta, eps, a, b, c = map(_chk, (delta, eps, a, b, c))
+    if delta.shape == eps.shape:
+        mode, P, C = 0, 1, delta.numel()
+    elif delta.dim() == 1 and eps.dim() == 2 and eps.shape[1] == delta.shape[0]:
+        mode, (P, C) = 1, eps.shape
+    elif eps.dim() == 1 and delta.dim() == 2 and delta.shape[1] == eps.shape[0]:
+        mode, (P, C) = 2, delta.shape
+    else:
+        raise PrimiaError(f"unsupported broadcast {tuple(delta.shape)} x {tuple(eps.shape)}")
+    z = torch.empty_like(c)
+    with torch.cuda.device(delta.device):
+        call("pm_spdz_combine_mul_i64", j, ptr(delta), ptr(eps), ptr(a), ptr(b), ptr(c), mode, P, C, ptr(z), stream())
+    return z
+
+
+def matmul(A, Bm):
+    A, Bm = _chk(A), _chk(Bm)
+    squeeze = A.dim() == 2
+    if squeeze:
+        A = A.unsqueeze(0)
+    Bt, M, K = A.shape
+    K2, N = Bm.shape
+    assert K == K2
+    C = torch.empty((Bt, M, N), dtype=I64, device=A.device)
+    with torch.cuda.device(A.device):
+        call("pm_matmul_i64", ptr(A), ptr(Bm), Bt, M, K, N, ptr(C), stream())
+    return C[0] if squeeze else C
+
+
+def trunc_div(x, divisor: int, out=None):
+    x = _chk(x)
+    out = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        call("pm_trunc_div_i64", ptr(x), int(divisor), ptr(out), x.numel(), stream())
+    return out
+
+
+def trunc_post_conv(z, divisor: int, bias, Ho, Wo):
+    z = _chk(z)
+    Bt, M, N = z.shape
+    out = torch.empty((Bt, N, Ho, Wo), dtype=I64, device=z.device)
+    with torch.cuda.device(z.device):
+        call("pm_trunc_post_conv_i64", ptr(z), int(divisor), ptr(bias) if bias is not None else None, Bt, M, N, ptr(out),
+             stream())
+    return out
+
+
+def axpby(alpha: int, x, beta: int = 0, y=None):
+    x = _chk(x)
+    if y is None:
+        ybcast, P, C = 0, 1, x.numel()
+    else:
+        y = _chk(y)
+        if y.shape == x.shape:
+            ybcast, P, C = 0, 1, x.numel()
+        elif y.numel() == 1:
+            ybcast, P, C = 2, 1, x.numel()
+        elif y.dim() == 1 and x.shape[-1] == y.shape[0]:
+            ybcast, C = 1, y.shape[0]
+            P = x.numel() // C
+        else:
+            raise PrimiaError(f"unsupported broadcast {tuple(x.shape)} , {tuple(y.shape)}")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        call("pm_axpby_i64", int(alpha), ptr(x), int(beta), ptr(y), ybcast, P, C, ptr(out), stream())
+    return out
+
+
+def avgpool(x, k: int):
+    x = _chk(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, H // k, W // k), dtype=I64, device=x.device)
+    with torch.cuda.device(x.device):
+        call("pm_avgpool_i64", ptr(x), B, C, H, W, k, ptr(out), stream())
+    return out
+
+
+def nchw_to_pc(x):
+    x = _chk(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B * H * W, C), dtype=I64, device=x.device)
+    with torch.cuda.device(x.device):
+        call("pm_nchw_to_pc_i64", ptr(x), B, C, H * W, ptr(out), stream())
+    return out
+
+
+def pc_to_nchw(x, B, C, H, W):
+    x = _chk(x)
+    out = torch.empty((B, C, H, W), dtype=I64, device=x.device)
+    with torch.cuda.device(x.device):
+        call("pm_pc_to_nchw_i64", ptr(x), B, C, H * W, ptr(out), stream())
+    return out

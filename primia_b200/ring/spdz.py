@@ -1,0 +1,175 @@
+"""SPDZ Beaver multiplication on GPU-resident shares.
+
+Mirrors syft/frameworks/torch/mpc/{spdz,beaver,primitives}.py:
+  spdz_mask     spdz.py:22-45      party-local  delta_j = x_j - a_j , eps_j = y_j - b_j
+  spdz_compute  spdz.py:64-122     party-local  z_j = delta(op)b_j + a_j(op)eps + c_j (+ delta(op)eps, j==0)
+  spdz_mul      spdz.py:125-197    the protocol round (mask -> open -> compute)
+  PrimitiveStorage primitives.py:52-102,161-213,255-286 ; build_triple beaver.py:7-63
+  EmptyCryptoPrimitiveStoreError syft/exceptions.py:343-356
+
+B200 mapping: a Party is a GPU (``torch.device``) + its crypto store.  Opening delta/eps is a
+symmetric peer read over NVLink (``pm_open_add_i64`` reads the other party's buffer through its
+peer-mapped pointer) instead of the reference's star through the orchestrator (spdz.py:162-163).
+Triples are produced on the crypto provider's GPU (Philox) and copied to the two parties.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import ops
+
+
+class EmptyCryptoPrimitiveStoreError(Exception):
+    """syft/exceptions.py:343-356: carries the kwargs needed to build the missing primitives."""
+
+    def __init__(self, crypto_store=None, available_instances=-1, n_instances=1, op="", **kwargs):
+        self.kwargs_ = {"op": op, "n_instances": n_instances, **kwargs}
+        super().__init__(
+            f"not enough '{op}' primitives in the store of {getattr(crypto_store, 'owner_id', '?')}: "
+            f"asked {n_instances}, available {available_instances}; shapes={kwargs.get('shapes')}"
+        )
+
+
+def _key(shapes):
+    return tuple(tuple(int(d) for d in s) for s in shapes)
+
+
+class PrimitiveStorage:
+    """Per-party store of Beaver triples keyed by (op, operand shapes) -- primitives.py:52-102.
+
+    ``get_keys(remove=False)`` peeks (spdz_mask), ``remove=True`` pops (spdz_compute)."""
+
+    def __init__(self, owner_id):
+        self.owner_id = owner_id
+        self.force_preprocessing = False
+        self._stacks: Dict[str, Dict[tuple, List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]]] = {
+            "mul": defaultdict(list),
+            "matmul": defaultdict(list),
+        }
+
+    def get_keys(self, op: str, shapes, n_instances: int = 1, remove: bool = True, **kwargs):
+        stack = self._stacks[op][_key(shapes)]
+        if len(stack) < n_instances:
+            raise EmptyCryptoPrimitiveStoreError(self, len(stack) if stack else -1, n_instances, op=op, shapes=_key(shapes))
+        assert n_instances == 1
+        return stack.pop(0) if remove else stack[0]
+
+    def add_primitives(self, op: str, shapes, triples):
+        """primitives.py:194-213"""
+        self._stacks[op][_key(shapes)].extend(triples)
+
+    def count(self, op, shapes):
+        return len(self._stacks[op][_key(shapes)])
+
+    def nbytes(self):
+        return sum(t.numel() * 8 for st in self._stacks.values() for lst in st.values() for tri in lst for t in tri)
+
+
+class Party:
+    """A share holder / crypto provider pinned to one GPU (the VirtualWorker of path E)."""
+
+    def __init__(self, id, device):
+        self.id = id
+        self.device = torch.device(device)
+        self.crypto_store = PrimitiveStorage(id)
+
+    def __repr__(self):
+        return f"<Party {self.id} on {self.device}>"
+
+
+class TripleProvider:
+    """provide_primitives / build_triples / build_triple -- primitives.py:161-192,255-286, beaver.py:7-63.
+
+    a, b ~ Philox over [-2^63, 2^63-2]; c = a (op) b computed with the ring GEMM on the provider's GPU;
+    each of a,b,c is split into 2 additive shares which are copied to the parties' GPUs."""
+
+    def __init__(self, provider: Party, seed: int = 0x5EED):
+        self.provider = provider
+        self.seed = seed
+        self.counter = 0
+        self.generated_bytes = 0
+
+    def _rand(self, shape):
+        self.counter += 1
+        return ops.random_i64(shape, self.seed, self.counter, self.provider.device)
+
+    def build_triple(self, op: str, shapes):
+        ls, rs = shapes
+        a, b = self._rand(ls), self._rand(rs)
+        if op == "matmul":
+            c = ops.matmul(a, b)
+        else:
+            c = _mul_bcast(a, b)
+        out = [[None] * 3, [None] * 3]
+        for i, t in enumerate((a, b, c)):
+            self.counter += 1
+            s0, s1 = ops.share_gen(t, self.seed, self.counter)
+            out[0][i], out[1][i] = s0, s1
+        return out
+
+    def provide_primitives(self, op: str, shapes, parties, n_instances: int = 1, **_):
+        for _i in range(n_instances):
+            tri = self.build_triple(op, shapes)
+            for j, p in enumerate(parties):
+                moved = tuple(t.to(p.device, non_blocking=True) for t in tri[j])
+                self.generated_bytes += sum(t.numel() * 8 for t in moved)
+                p.crypto_store.add_primitives(op, shapes, [moved])
+        if any(p.device != self.provider.device for p in parties):
+            torch.cuda.synchronize(self.provider.device)
+
+
+def _mul_bcast(a, b):
+    """elementwise ring product with the [C] x [P,C] broadcasts batch_norm needs (exact in int64)."""
+    # use the combine kernel with delta=a, eps=b, a=0, b=0, c=0 on "party 0": z = delta*eps
+    if a.shape == b.shape:
+        zl, zr, zc = torch.zeros_like(a), torch.zeros_like(b), torch.zeros_like(a)
+    elif a.dim() == 1:
+        zl, zr, zc = torch.zeros_like(a), torch.zeros_like(b), torch.zeros_like(b)
+    else:
+        zl, zr, zc = torch.zeros_like(a), torch.zeros_like(b), torch.zeros_like(a)
+    return ops.combine_mul(0, a, b, zl, zr, zc)
+
+
+# ------------------------------------------------------------------ share level (run on each party)
+def spdz_mask(party: Party, x, y, op: str):
+    """spdz.py:22-45"""
+    a, b, _c = party.crypto_store.get_keys(op=op, shapes=(x.shape, y.shape), n_instances=1, remove=False)
+    return ops.mask(x, a), ops.mask(y, b)
+
+
+def spdz_compute(party: Party, j: int, delta, epsilon, op: str):
+    """spdz.py:64-122"""
+    a, b, c = party.crypto_store.get_keys(op=op, shapes=(delta.shape, epsilon.shape), n_instances=1, remove=True)
+    if op == "matmul":
+        return ops.combine_matmul(j, delta, epsilon, a, b, c)
+    return ops.combine_mul(j, delta, epsilon, a, b, c)
+
+
+def open_shares(parties, shares):
+    """delta = sum(shares) made available on every party (spdz.py:162-163), via peer reads."""
+    outs = []
+    for j, p in enumerate(parties):
+        peer = shares[1 - j]
+        if peer.device != p.device:
+            # symmetric NVLink exchange: read the peer's share through its device pointer
+            if not torch.cuda.can_device_access_peer(p.device.index, peer.device.index):
+                peer = peer.to(p.device)  # staged copy when no P2P mapping exists
+        outs.append(ops.open_add(shares[j], peer))
+    return outs
+
+
+def spdz_mul(op: str, x_shares, y_shares, parties, provider: TripleProvider = None):
+    """spdz.py:125-197.  x_shares / y_shares: per-party tensors. Returns per-party output shares."""
+    try:
+        masked = [spdz_mask(p, x_shares[j], y_shares[j], op) for j, p in enumerate(parties)]
+    except EmptyCryptoPrimitiveStoreError as e:
+        if provider is None or any(p.crypto_store.force_preprocessing for p in parties):
+            raise
+        provider.provide_primitives(parties=parties, **e.kwargs_)
+        return spdz_mul(op, x_shares, y_shares, parties, provider)
+    deltas = open_shares(parties, [m[0] for m in masked])
+    epsilons = open_shares(parties, [m[1] for m in masked])
+    return [spdz_compute(p, j, deltas[j], epsilons[j], op) for j, p in enumerate(parties)]

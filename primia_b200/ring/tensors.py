@@ -1,0 +1,178 @@
+"""AdditiveSharingTensor / FixedPrecisionTensor on GPU shares.
+
+Mirrors the subset of syft/frameworks/torch/tensors/interpreters/{additive_shared,precision}.py that
+inference.py:279-321 exercises."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .spdz import Party, TripleProvider, spdz_mul
+
+
+class ShareRNG:
+    """Source of the fresh randomness the reference draws when it secret-shares a value
+    (additive_shared.py:336-365).  Tests subclass it to replay explicit shares."""
+
+    def __init__(self, seed=0xA11CE):
+        self.seed = seed
+        self.counter = 0
+
+    def share(self, q: torch.Tensor):
+        self.counter += 1
+        return ops.share_gen(q, self.seed, self.counter)
+
+
+class AdditiveSharingTensor:
+    """2-party additive sharing over Z_2^64; ``child[j]`` is party j's share on party j's GPU."""
+
+    def __init__(self, shares, parties, provider: TripleProvider = None, rng: ShareRNG = None):
+        self.child = list(shares)
+        self.parties = list(parties)
+        self.provider = provider
+        self.rng = rng or ShareRNG()
+
+    # -- construction / reconstruction
+    @classmethod
+    def share_secret(cls, q: torch.Tensor, parties, provider=None, rng=None):
+        """additive_shared.py:317-365"""
+        rng = rng or ShareRNG()
+        s0, s1 = rng.share(q)
+        shares = [s0.to(parties[0].device), s1.to(parties[1].device)]
+        return cls(shares, parties, provider, rng)
+
+    def get(self):
+        """additive_shared.py:287-301"""
+        a, b = self.child
+        return ops.open_add(a, b.to(a.device))
+
+    @property
+    def shape(self):
+        return self.child[0].shape
+
+    def _new(self, shares):
+        return AdditiveSharingTensor(shares, self.parties, self.provider, self.rng)
+
+    # -- linear ops (additive_shared.py:455-527)
+    def _shared_const(self, value: int):
+        q = torch.tensor([value], dtype=torch.int64, device=self.parties[0].device)
+        s0, s1 = self.rng.share(q)
+        return [s0, s1.to(self.parties[1].device)]
+
+    def add(self, other):
+        if isinstance(other, int):
+            other = self._new(self._shared_const(other))
+        return self._new([ops.axpby(1, s, 1, o) for s, o in zip(self.child, other.child)])
+
+    def sub(self, other):
+        if isinstance(other, int):
+            other = self._new(self._shared_const(other))
+        return self._new([ops.axpby(1, s, -1, o) for s, o in zip(self.child, other.child)])
+
+    __add__ = add
+    __sub__ = sub
+
+    def public_mul(self, k: int):
+        """_public_mul additive_shared.py:561-588 (k != 0)"""
+        assert k != 0, "multiplying by public 0 needs a zero-refresh (additive_shared.py:27-60); not on the hot path"
+        return self._new([ops.axpby(k, s) for s in self.child])
+
+    def public_div(self, d: int):
+        """_public_div additive_shared.py:673-678"""
+        return self._new([ops.trunc_div(s, d) for s in self.child])
+
+    # -- private multiplications (additive_shared.py:529-557,643-654)
+    def mul(self, other):
+        if isinstance(other, int):
+            return self.public_mul(other)
+        return self._new(spdz_mul("mul", self.child, other.child, self.parties, self.provider))
+
+    def matmul(self, other):
+        return self._new(spdz_mul("matmul", self.child, other.child, self.parties, self.provider))
+
+    def map(self, fn):
+        return self._new([fn(s) for s in self.child])
+
+
+class FixedPrecisionTensor:
+    """precision.py: value = child / base**precision_fractional ; child is an AST (private) or an int64 tensor (public)."""
+
+    def __init__(self, child, base=10, precision_fractional=16):
+        self.child = child
+        self.base = base
+        self.precision_fractional = precision_fractional
+
+    @property
+    def scale(self):
+        return self.base ** self.precision_fractional
+
+    @classmethod
+    def fix_precision(cls, x: torch.Tensor, base=10, precision_fractional=16):
+        return cls(ops.encode(x, base, precision_fractional), base, precision_fractional)
+
+    def share(self, *parties, crypto_provider=None, rng=None, **_):
+        """precision.py:910-957 -> native.share native.py:887-949"""
+        prov = crypto_provider if isinstance(crypto_provider, TripleProvider) or crypto_provider is None else TripleProvider(crypto_provider)
+        ast = AdditiveSharingTensor.share_secret(self.child, list(parties), prov, rng)
+        return FixedPrecisionTensor(ast, self.base, self.precision_fractional)
+
+    def get(self):
+        return FixedPrecisionTensor(self.child.get(), self.base, self.precision_fractional)
+
+    def float_precision(self):
+        return ops.decode(self.child, self.base, self.precision_fractional)
+
+    float_prec = float_precision
+
+    def _new(self, child):
+        return FixedPrecisionTensor(child, self.base, self.precision_fractional)
+
+    @property
+    def shape(self):
+        return self.child.shape
+
+    def truncate(self, pf):
+        """precision.py:146-160"""
+        return self._new(self.child.public_div(self.base ** pf))
+
+    # precision.py:180-254
+    def __add__(self, other):
+        if isinstance(other, int):
+            return self._new(self.child.add(int(other * self.scale)))
+        return self._new(self.child.add(other.child))
+
+    def __sub__(self, other):
+        if isinstance(other, int):
+            return self._new(self.child.sub(int(other * self.scale)))
+        return self._new(self.child.sub(other.child))
+
+    def __rsub__(self, other):
+        return (self - other) * -1
+
+    # precision.py:264-366
+    def __mul__(self, other):
+        if isinstance(other, int):
+            return self._new(self.child.mul(other))
+        return self._new(self.child.mul(other.child)).truncate(self.precision_fractional)
+
+    def __truediv__(self, other):
+        assert isinstance(other, int)
+        return self._new(self.child.public_div(other))
+
+    # precision.py:419-463
+    def matmul(self, other):
+        return self._new(self.child.matmul(other.child)).truncate(other.precision_fractional)
+
+    def reciprocal(self, method="newton"):
+        """precision.py:507-518 -- literally (80 iterations, C = 20)."""
+        assert method == "newton"
+        x = None
+        C = 20
+        for _ in range(80):
+            if x is not None:
+                y = C + 1 - self * (x * x)
+                x = y * x / C
+            else:
+                y = C + 1 - self
+                x = y / C
+        return x

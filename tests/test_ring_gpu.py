@@ -1,0 +1,261 @@
+"""Path E parity: CUDA ring kernels (through the C ABI) vs the CPU oracle -- bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ring_oracle as R
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def rnd(gen, shape):
+    return torch.randint(-(2 ** 63), 2 ** 63 - 1, tuple(shape), dtype=torch.int64, generator=gen)
+
+
+def cu(t):
+    return t.contiguous().to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ring():
+    import primia_b200.ring as ring
+
+    return ring
+
+
+def test_encode_decode_bit_exact(ring):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(100003, generator=g) * 3
+    x[:6] = torch.tensor([0.0, -0.0, 0.123456789, -0.123456789, 1e-9, -7.5])
+    for base, pf in [(10, 16), (10, 4), (10, 3), (2, 20)]:
+        q = ring.encode(cu(x), base, pf)
+        ref = R.encode(x, base, pf)
+        assert torch.equal(q.cpu(), ref)
+        assert torch.equal(ring.decode(q, base, pf).cpu(), R.decode(ref, base, pf))
+    with pytest.raises(AssertionError):
+        ring.encode(cu(torch.tensor([1e5])), 10, 16)  # 1e21 > 2^63: precision.py:122-127
+    assert ring.encode(cu(torch.zeros(0)), 10, 4).numel() == 0  # empty input
+
+
+def test_share_gen_reconstructs_and_is_deterministic(ring):
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 2, 7, 4097):
+        q = rnd(g, (n,))
+        s0, s1 = ring.share_gen(cu(q), 123, 5)
+        assert torch.equal((s0 + s1).cpu(), q)
+        t0, _ = ring.share_gen(cu(q), 123, 5)
+        assert torch.equal(s0, t0)
+        u0, _ = ring.share_gen(cu(q), 123, 6)
+        assert not torch.equal(s0, u0) or n == 0
+    r = ring.random_i64((1 << 16,), 9, 1, DEV).cpu()
+    bits = ((r.view(-1, 1) >> torch.arange(64)) & 1).float().mean(0)
+    assert (bits - 0.5).abs().max() < 0.02
+    assert (r == 2 ** 63 - 1).sum() == 0
+
+
+def test_im2col_and_post_conv_vs_reference_fixture(ring):
+    g = np.load(os.path.join(GOLDEN, "ring_preconv.npz"))
+    for i, (B, C, H, W, Co, k, s, p) in enumerate(g["cases"]):
+        x, w = torch.from_numpy(g[f"x{i}"]), torch.from_numpy(g[f"w{i}"])
+        im, wr, b_, co_, ho_, wo_ = ring.functional._pre_conv(cu(x), cu(w), None, int(s), int(p))
+        assert torch.equal(im.cpu(), torch.from_numpy(g[f"im{i}"]))
+        assert torch.equal(wr.cpu(), torch.from_numpy(g[f"wr{i}"]))
+        res = ring.matmul(im, wr.contiguous())
+        post = ring.functional._post_conv(None, res, b_, co_, ho_, wo_)
+        assert torch.equal(post.cpu(), torch.from_numpy(g[f"post{i}"]))
+
+
+def test_spdz_fixture_from_reference_sources(ring):
+    g = np.load(os.path.join(GOLDEN, "ring_spdz.npz"))
+    for i in range(int(g["n"])):
+        op = str(g[f"op{i}"])
+        parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+        xs = [cu(torch.from_numpy(g[f"x{i}_{j}"])) for j in range(2)]
+        ys = [cu(torch.from_numpy(g[f"y{i}_{j}"])) for j in range(2)]
+        for j, p in enumerate(parties):
+            tri = tuple(cu(torch.from_numpy(g[f"{n}{i}_{j}"])) for n in "abc")
+            p.crypto_store.add_primitives(op, (xs[j].shape, ys[j].shape), [tri])
+        for j, p in enumerate(parties):
+            d, e = ring.spdz_mask(p, xs[j], ys[j], op)
+            assert torch.equal(d.cpu(), torch.from_numpy(g[f"d{i}_{j}"]))
+            assert torch.equal(e.cpu(), torch.from_numpy(g[f"e{i}_{j}"]))
+        z = ring.spdz_mul(op, xs, ys, parties)
+        for j in range(2):
+            assert torch.equal(z[j].cpu(), torch.from_numpy(g[f"z{i}_{j}"]))
+        assert parties[0].crypto_store.count(op, (xs[0].shape, ys[0].shape)) == 0  # consumed (remove=True)
+        with pytest.raises(ring.EmptyCryptoPrimitiveStoreError):
+            ring.spdz_mul(op, xs, ys, parties)
+
+
+@pytest.mark.parametrize("B,M,K,N", [(1, 49, 147, 64), (2, 100, 64, 128), (1, 1, 512, 3), (1, 196, 2304, 256), (3, 65, 17, 65),
+                                     (1, 3136, 576, 64)])
+def test_combine_matmul_bit_exact(ring, B, M, K, N):
+    g = torch.Generator().manual_seed(B * 1000 + M)
+    delta, a, eps, b, c = rnd(g, (B, M, K)), rnd(g, (B, M, K)), rnd(g, (K, N)), rnd(g, (K, N)), rnd(g, (B, M, N))
+    for j in range(2):
+        z = ring.combine_matmul(j, cu(delta), cu(eps), cu(a), cu(b), cu(c))
+        ref = R.spdz_compute(j, delta, eps, a, b, c, "matmul")
+        assert torch.equal(z.cpu(), ref), (j, B, M, K, N)
+    assert torch.equal(ring.matmul(cu(a), cu(b)).cpu(), torch.matmul(a, b))
+
+
+def test_combine_mul_broadcast_modes(ring):
+    g = torch.Generator().manual_seed(5)
+    P, C = 37, 64
+    for ls, rs in [((P, C), (P, C)), ((C,), (P, C)), ((P, C), (C,)), ((C,), (C,))]:
+        delta, a, eps, b = rnd(g, ls), rnd(g, ls), rnd(g, rs), rnd(g, rs)
+        c = rnd(g, torch.broadcast_shapes(ls, rs))
+        for j in range(2):
+            z = ring.combine_mul(j, cu(delta), cu(eps), cu(a), cu(b), cu(c))
+            assert torch.equal(z.cpu(), R.spdz_compute(j, delta, eps, a, b, c, "mul"))
+
+
+def test_trunc_div_edge_cases(ring):
+    s = torch.tensor([7, -7, 19999, -19999, 0, -(2 ** 63), 2 ** 63 - 1, -1, 1], dtype=torch.int64)
+    for d in (10, 10 ** 4, 10 ** 16, 49, 20):
+        assert torch.equal(ring.trunc_div(cu(s), d).cpu(), R.trunc_div(s, d))
+
+
+CONV_SHAPES = [  # (C, H, Cout, k, stride, pad): every distinct ResNet-18 conv geometry at reduced spatial size
+    (3, 32, 64, 7, 2, 3), (64, 8, 64, 3, 1, 1), (64, 8, 128, 3, 2, 1), (64, 8, 128, 1, 2, 0), (128, 6, 128, 3, 1, 1),
+    (128, 6, 256, 3, 2, 1), (128, 6, 256, 1, 2, 0), (256, 4, 256, 3, 1, 1), (256, 4, 512, 3, 2, 1), (256, 4, 512, 1, 2, 0),
+    (512, 3, 512, 3, 1, 1),
+]
+
+
+def _shared_conv_case(ring, g, B, C, H, Co, k, s, p, base, pf):
+    x, w = rnd(g, (B, C, H, H)), rnd(g, (Co, C, k, k))
+    xs = R.share_from_random(x, rnd(g, x.shape))
+    ws = R.share_from_random(w, rnd(g, w.shape))
+    Ho = (H + 2 * p - k) // s + 1
+    M, K, N = Ho * Ho, C * k * k, Co
+    a, b = rnd(g, (B, M, K)), rnd(g, (K, N))
+    c = R.build_triple_c(a, b, "matmul")
+    a0, b0, c0 = rnd(g, a.shape), rnd(g, b.shape), rnd(g, c.shape)
+    tri = [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+    ref = R.conv2d_shared(xs, ws, tri, s, p, base, pf)
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    for j, pty in enumerate(parties):
+        pty.crypto_store.add_primitives("matmul", ((B, M, K), (K, N)), [tuple(cu(t) for t in tri[j])])
+    X = ring.FixedPrecisionTensor(ring.AdditiveSharingTensor([cu(t) for t in xs], parties), base, pf)
+    Wt = ring.FixedPrecisionTensor(ring.AdditiveSharingTensor([cu(t) for t in ws], parties), base, pf)
+    out = ring.functional.conv2d(X, Wt, None, s, p)
+    for j in range(2):
+        assert torch.equal(out.child.child[j].cpu(), ref[j]), (C, H, Co, k, s, p, j)
+
+
+@pytest.mark.parametrize("base,pf", [(10, 16), (10, 4)])
+def test_conv2d_on_shares_all_resnet18_geometries(ring, base, pf):
+    g = torch.Generator().manual_seed(42)
+    for (C, H, Co, k, s, p) in CONV_SHAPES:
+        _shared_conv_case(ring, g, 1, C, H, Co, k, s, p, base, pf)
+    _shared_conv_case(ring, g, 2, 16, 9, 24, 3, 2, 1, base, pf)  # batch > 1, ragged M
+
+
+def test_conv2d_full_size_layer1(ring):
+    """BASELINE config C4 geometry: layer1 conv, 64ch 56x56, M=3136 K=576 N=64, pf=16."""
+    g = torch.Generator().manual_seed(7)
+    _shared_conv_case(ring, g, 1, 64, 56, 64, 3, 1, 1, 10, 16)
+
+
+def test_provider_generated_triples_reconstruct_true_product(ring):
+    """full-size property: with provider-made triples, reconstruct(z0+z1) == im2col(x) @ w^T mod 2^64."""
+    g = torch.Generator().manual_seed(9)
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", DEV), seed=77)
+    x, w = rnd(g, (1, 64, 28, 28)), rnd(g, (128, 64, 3, 3))
+    X = ring.FixedPrecisionTensor(cu(x), 10, 16).share(*parties, crypto_provider=prov)
+    Wt = ring.FixedPrecisionTensor(cu(w), 10, 16).share(*parties, crypto_provider=prov)
+    x_sh = [s.cpu() for s in X.child.child]
+    assert torch.equal(x_sh[0] + x_sh[1], x)
+    # untruncated protocol output
+    from primia_b200.ring import ops
+    im, wr, *_ = R.pre_conv(x, w, 2, 1)
+    z = ring.spdz_mul("matmul", [ops.im2col(s, 3, 3, 2, 1) for s in X.child.child],
+                      [s.reshape(128, -1).t().contiguous() for s in Wt.child.child], parties, prov)
+    assert torch.equal((z[0] + z[1]).cpu(), torch.matmul(im, wr))
+
+
+class ReplayRNG:
+    def __init__(self, s0_list):
+        self.s0 = list(s0_list)
+
+    def share(self, q):
+        s0 = self.s0.pop(0).to(q.device)
+        return s0, q - s0
+
+
+def test_batch_norm_eval_newton_bit_exact(ring):
+    g = torch.Generator().manual_seed(11)
+    base, pf = 10, 4
+    B, C, H, W = 1, 8, 3, 2
+    P = B * H * W
+    enc = lambda t: R.encode(t, base, pf)
+    x = enc(torch.randn(B, C, H, W, generator=g))
+    mean, var = enc(torch.randn(C, generator=g) * 0.1), enc(torch.rand(C, generator=g) + 0.5)
+    gamma, beta = enc(torch.rand(C, generator=g) + 0.5), enc(torch.randn(C, generator=g) * 0.1)
+    sh = lambda q: R.share_from_random(q, rnd(g, q.shape))
+    x_sh, m_sh, v_sh, g_sh, b_sh = sh(x), sh(mean), sh(var), sh(gamma), sh(beta)
+
+    def tri(ls, rs):
+        a, b = rnd(g, ls), rnd(g, rs)
+        c = a * b
+        a0, b0, c0 = rnd(g, a.shape), rnd(g, b.shape), rnd(g, c.shape)
+        return [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+
+    iters = 80
+    q21 = torch.tensor([21 * base ** pf], dtype=torch.int64)
+    c_s0 = [rnd(g, (1,)) for _ in range(iters)]
+    consts = [[s0, q21 - s0] for s0 in c_s0]
+    triples = [None] + [[tri((C,), (C,)) for _ in range(3)] for _ in range(iters - 1)]
+    tri_norm, tri_aff = tri((C,), (P, C)), tri((P, C), (C,))
+    ref = R.batch_norm_eval_shared(x_sh, m_sh, v_sh, g_sh, b_sh, consts, triples, tri_norm, tri_aff, base, pf, iters)
+
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    for j, pty in enumerate(parties):
+        for it in range(1, iters):
+            for t in triples[it]:
+                pty.crypto_store.add_primitives("mul", ((C,), (C,)), [tuple(cu(u) for u in t[j])])
+        pty.crypto_store.add_primitives("mul", ((C,), (P, C)), [tuple(cu(u) for u in tri_norm[j])])
+        pty.crypto_store.add_primitives("mul", ((P, C), (C,)), [tuple(cu(u) for u in tri_aff[j])])
+    rng = ReplayRNG(c_s0)
+    mk = lambda s: ring.FixedPrecisionTensor(ring.AdditiveSharingTensor([cu(t) for t in s], parties, None, rng), base, pf)
+    out = ring.functional.batch_norm(mk(x_sh), mk(m_sh), mk(v_sh), mk(g_sh), mk(b_sh))
+    for j in range(2):
+        assert torch.equal(out.child.child[j].cpu(), ref[j])
+    # numerically sane at pf=4: decodes to the float batch norm (eps ignored) within fixed-point error
+    got = R.decode(ref[0] + ref[1], base, pf)
+    xf, mf, vf, gf, bf = (R.decode(t, base, pf) for t in (x, mean, var, gamma, beta))
+    want = (xf - mf.view(1, C, 1, 1)) / vf.view(1, C, 1, 1).sqrt() * gf.view(1, C, 1, 1) + bf.view(1, C, 1, 1)
+    assert (got - want).abs().max() < 0.05
+
+
+def test_avgpool_and_linear_bit_exact(ring):
+    g = torch.Generator().manual_seed(13)
+    base, pf = 10, 16
+    x = rnd(g, (1, 512, 7, 7))
+    xs = R.share_from_random(x, rnd(g, x.shape))
+    ref = R.avg_pool_shared(xs, 7)
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    X = ring.FixedPrecisionTensor(ring.AdditiveSharingTensor([cu(t) for t in xs], parties), base, pf)
+    out = ring.functional.avg_pool2d(X, 7)
+    for j in range(2):
+        assert torch.equal(out.child.child[j].cpu(), ref[j])
+    feat = [r.reshape(1, 512) for r in ref]
+    w, bias = rnd(g, (3, 512)), rnd(g, (3,))
+    ws, bs = R.share_from_random(w, rnd(g, w.shape)), R.share_from_random(bias, rnd(g, bias.shape))
+    a, b = rnd(g, (1, 512)), rnd(g, (512, 3))
+    c = a @ b
+    a0, b0, c0 = rnd(g, a.shape), rnd(g, b.shape), rnd(g, c.shape)
+    tri = [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+    ref_l = R.linear_shared(feat, ws, bs, tri, base, pf)
+    for j, pty in enumerate(parties):
+        pty.crypto_store.add_primitives("matmul", ((1, 512), (512, 3)), [tuple(cu(t) for t in tri[j])])
+    mk = lambda s: ring.FixedPrecisionTensor(ring.AdditiveSharingTensor([cu(t) for t in s], parties), base, pf)
+    out = ring.functional.linear(mk(feat), mk(ws), mk(bs))
+    for j in range(2):
+        assert torch.equal(out.child.child[j].cpu(), ref_l[j])
