@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- federated-round throughput (images/s, whole job) of the B200-native PriMIA hot path T, with the
+encrypted-inference (path E) latency reported beside it.
+
+    python bench.py --gpus N --steps K --warmup W                (N=1 directly; N>1 under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path, timed on host cores)
+
+Workload (BASELINE.json configs[1]): ResNet-18 3-class, 224x224x3 synthetic chest-X-ray-shaped batches, one hospital
+(PySyft VirtualWorker) per GPU, batch 64 per hospital, Adam(lr 1e-4, betas (0.5,0.99), wd 5e-4), FedAvg after every
+local step (sync_every_n_batch = 1) with optimizer reset, bf16 tensor-core throughput mode (fp32 master weights).
+A "step" = one federated round = local step on every hospital (concurrently, one per GPU) + FedAvg all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = 10.645  # fwd + bwd conv/fc work, SURVEY.md section 8d (5.3227 GMAC)
+METRIC = "federated_round_images_per_sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle restatement of torchlib/utils.py:1108-1233 +
+    torchlib/models.py; the PySyft stack itself cannot be imported on this Python/torch -- SURVEY.md section 8c)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import train_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_workers = args.gpus
+    # bounded sample: size the per-hospital batch so that (steps + warmup) rounds fit in ~150 s of host time
+    probe = O.resnet18(seed=42)
+    px, py = torch.randn(4, 3, 224, 224), torch.randint(0, 3, (4,))
+    popt = O.make_optimizer(probe)
+    O.local_step(probe, popt, O.make_loss(), px, py)
+    t0 = time.perf_counter()
+    O.local_step(probe, popt, O.make_loss(), px, py)
+    per_img = (time.perf_counter() - t0) / 4
+    budget = 150.0 / max(1, (args.steps + args.warmup) * n_workers)
+    sample = int(max(2, min(args.ref_batch, budget / max(per_img, 1e-6))))
+    del probe, popt
+    ids = [f"hospital{i}" for i in range(n_workers)]
+    base = O.resnet18(seed=42)
+    models = {w: O.clone_model(base) for w in ids}
+    local = O.clone_model(base)
+    loss_fn = O.make_loss()
+    g = torch.Generator().manual_seed(42)
+    data = {w: (torch.randn(sample, 3, 224, 224, generator=g), torch.randint(0, 3, (sample,), generator=g)) for w in ids}
+
+    def one_round():
+        opts = {w: O.make_optimizer(models[w]) for w in ids}  # re-created after every aggregation (utils.py:1209-1218)
+        for w in ids:  # hospitals sequentially, as utils.py:1160
+            O.local_step(models[w], opts[w], loss_fn, *data[w])
+        O.aggregation(local, models, ids)
+        O.send_new_models(local, models, ids)
+
+    for _ in range(args.warmup):
+        one_round()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_round()
+    dt = time.perf_counter() - t0
+    value = n_workers * sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: ResNet-18 federated round, 224x224x3, FedAvg every step, Adam", "workers": n_workers,
+                   "batch_per_worker": 64, "parallelism": f"{n_workers} hospitals sequential on host cores"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per hospital per step instead of 64 (bounded CPU sample); torch-CPU fp32 oracle, "
+                                   "omits PySyft per-op msgpack round-trips => lower bound on the reference's time"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def cpu_baseline_sample(seconds_cap=25.0):
+    """torch-CPU fp32 oracle local step on a bounded sample, rank 0 / N=1 only."""
+    import torch
+
+    from oracle import train_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = O.resnet18(seed=42)
+    opt = O.make_optimizer(m)
+    loss_fn = O.make_loss()
+    Bs = 16
+    g = torch.Generator().manual_seed(42)
+    x, y = torch.randn(Bs, 3, 224, 224, generator=g), torch.randint(0, 3, (Bs,), generator=g)
+    O.local_step(m, opt, loss_fn, x, y)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.local_step(m, opt, loss_fn, x, y)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_cap or n >= 6:
+            break
+    return {"value": Bs * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} local steps of {Bs} images (fwd+bwd+Adam) with the torch-CPU fp32 oracle, {torch.get_num_threads()} threads"}
+
+
+def encrypted_inference_block(steps=3):
+    """Path E beside the headline: online latency of all 21 linear layers' Beaver protocol for one 224x224 image
+    (2 parties + crypto provider time-sharing this GPU), offline triple generation reported separately."""
+    import torch
+
+    from primia_b200 import ring
+    from primia_b200.ring.resnet import SharedLinearLayers
+
+    dev = "cuda:%d" % torch.cuda.current_device()
+    parties = [ring.Party("model_owner", dev), ring.Party("data_owner", dev)]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", dev), seed=42)
+    net = SharedLinearLayers(parties, prov, 10, 16)
+    xs = net.make_inputs(1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    off, on = [], []
+    for it in range(steps + 1):
+        torch.cuda.synchronize()
+        ev[0].record()
+        net.preprocess(1, 1)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ev[2].record()
+        net.forward(xs)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it:  # first iteration is warm-up
+            off.append(ev[0].elapsed_time(ev[1]))
+            on.append(ev[2].elapsed_time(ev[3]))
+    on_ms, off_ms = sum(on) / len(on), sum(off) / len(off)
+    macs = 2 * 1.81356288e9  # per party: delta@(b[+eps]) and a@eps fused in one GEMM pass (3 GEMMs in the reference)
+    return {"metric": "encrypted_inference_linear_layers_ms_per_image", "online_ms": on_ms, "offline_triple_gen_ms": off_ms,
+            "unit": "ms/image", "dtype": "int64", "int64_gmac_per_s_per_party": macs / (on_ms * 1e-3) / 1e9 * 1.0,
+            "scope": "20 convs + fc Beaver protocol (mask, open, combine, truncate) on shares, base 10 pf 16, both parties on one "
+                     "GPU; BN/ReLU/pool on shares excluded (ReLU needs FSS: SURVEY 8f-1)",
+            "triple_bytes_per_party": 226733592}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from primia_b200.train import HospitalWorker, ResNet18Engine, aggregation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+        group = dist.group.WORLD
+    B = args.batch
+    eng = ResNet18Engine(B, 3, 3, 224, "max", dev, args.mode)
+    eng.init_random(seed=42)
+    worker = HospitalWorker(f"hospital{rank}", eng)
+    nbuf = 4  # rotate 4 input batches (154 MB fp32) > L2; the activation working set (~1 GB/step) is >> L2 anyway
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    xs = [torch.randn(B, 3, 224, 224, device=dev, generator=g) for _ in range(nbuf)]
+    ys = [torch.randint(0, 3, (B,), device=dev, generator=g) for _ in range(nbuf)]
+    hx = [x.cpu().pin_memory() for x in xs]
+    hy = [y.cpu().pin_memory() for y in ys]
+
+    def fed_round(i):
+        worker.local_step(xs[i % nbuf], ys[i % nbuf])
+        aggregation([worker], None, group)
+        eng.reset_optimizer()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(args.warmup, 3)):
+        fed_round(i)
+    if args.graph:
+        eng.capture_graph(xs[0], ys[0])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(fed_round, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # end to end through the public API with HOST (pinned) buffers: H2D of the batch + D2H of the loss every step
+    host_loss = torch.zeros(1).pin_memory()
+
+    def fed_round_host(i):
+        loss = worker.local_step_host(hx[i % nbuf], hy[i % nbuf])
+        host_loss.copy_(loss, non_blocking=False)
+        aggregation([worker], None, group)
+        eng.reset_optimizer()
+
+    for i in range(2):
+        fed_round_host(i)
+    ms_e2e = timed(fed_round_host, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel family (tensor-core implicit-GEMM convs), measured live with CUDA events
+    conv_ms, launches = eng.profile_conv_time(xs[0], ys[0], steps=2)
+    pk = peaks()
+    achieved = GFLOP_PER_IMAGE * B / conv_ms  # GFLOP / ms == TFLOP/s
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM: fwd+dgrad+wgrad, 60 launches/step)",
+            "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+            "traffic": None, "conv_ms_per_step": conv_ms, "step_share": conv_ms / (ms / args.steps),
+            "algorithmic": f"{GFLOP_PER_IMAGE} GFLOP/image x {B} images per step", "peak_source": pk["source"] + ", sustained bf16 GEMM"}
+    if args.mode != "bf16":
+        roof["note"] = "fp32 parity mode runs on the FP32 pipe; fraction is still quoted against the bf16 tensor peak"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "C2: ResNet-18 3-class federated round, 224x224x3, batch 64 per hospital, FedAvg (NCCL all-reduce of the "
+                               "44.75 MB flat state) + optimizer reset after every local step, Adam", "workers": world,
+                   "batch_per_worker": B, "global_batch": world * B, "parallelism": f"fed{world} (one hospital per GPU)",
+                   "l2": "4 rotating input batches (154 MB) and ~1 GB of activations per step: working set >> 126 MB L2",
+                   "cuda_graph": bool(args.graph)},
+        "clocks": clocks, "gpu_launches": launches * args.steps,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * (hx[0].numel() * 4 + hy[0].numel() * 8),
+                "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e / args.steps},
+        "roofline": roof,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_sample()
+            try:
+                line["encrypted_inference"] = encrypted_inference_block()
+            except Exception as exc:  # the headline must still print
+                line["encrypted_inference"] = {"error": repr(exc)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--ref-batch", type=int, default=64, help="images per hospital per step for the bounded CPU reference sample")
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -157,12 +157,16 @@ int pm_gap_bwd_f32(const float* dy, int B, int HW, int C, float* dx, pm_stream_t
 int pm_gap_fwd_bf16(const void* x, int B, int HW, int C, float* y, pm_stream_t s);
 int pm_gap_bwd_bf16(const float* dy, int B, int HW, int C, void* dx, pm_stream_t s);
 
-/* Linear(512,ncls) + CrossEntropy (hard labels w/ optional class weights: nn.CrossEntropyLoss(weight,"mean");
- * or soft targets: Cross_entropy_one_hot torchlib/utils.py:404-441), forward AND backward in one pass:
- * logits[B,ncls]; loss[1]; dfeat[B,F]; dW[ncls,F]; db[ncls].  labels (int64) or soft (float [B,ncls]) -- one is NULL. */
+/* Linear(F,ncls) + CrossEntropy (hard labels w/ optional class weights: nn.CrossEntropyLoss(weight,"mean");
+ * or soft targets: Cross_entropy_one_hot torchlib/utils.py:404-441), forward AND backward:
+ * logits[B,ncls]; loss[1]; dfeat[B,F]; dW[ncls,F]; db[ncls].  labels (int64) or soft (float [B,ncls]) -- one is NULL.
+ * ws: scratch of B*(ncls+1)+1 floats. */
 int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const int64_t* labels, const float* soft,
                      const float* class_w, int B, int F, int ncls, float* logits, float* loss, float* dfeat,
-                     float* dW, float* db, pm_stream_t s);
+                     float* dW, float* db, float* ws, pm_stream_t s);
+/* inference-only head: logits = feat @ W^T + bias */
+int pm_linear_fwd_f32(const float* feat, const float* W, const float* bias, int B, int F, int ncls, float* logits,
+                      pm_stream_t s);
 
 /* torch.optim.Adam.step (train.py:280-303; L2 weight decay added to grad) on the flat parameter buffer */
 int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,

@@ -164,10 +164,19 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
     for (int k = 0; k < V; ++k) {
       float gg = g[k];
       if (y_out) gg = yv[k] > 0.f ? gg : 0.f;
-      const float is = invstd[c + k];
-      const float xhat = (xv[k] - mean[c + k]) * is;
-      const float mg = (float)(sums[c + k] * invP), mgx = (float)(sums[C + c + k] * invP);
-      g[k] = gamma[c + k] * is * (gg - mg - xhat * mgx);
+      if (sizeof(T) == 4) {
+        // parity mode: ATen's CPU kernel evaluates dy - mean(dy) - xhat*mean(dy*xhat) in double (acc_type<float>);
+        // the per-channel common mode of dy can exceed its fluctuation by 1e3-1e4, so fp32 here costs 1e-4 relative.
+        const double is = (double)invstd[c + k];
+        const double xhat = ((double)xv[k] - (double)mean[c + k]) * is;
+        const double mg = sums[c + k] * invP, mgx = sums[C + c + k] * invP;
+        g[k] = (float)((double)gamma[c + k] * is * ((double)gg - mg - xhat * mgx));
+      } else {
+        const float is = invstd[c + k];
+        const float xhat = (xv[k] - mean[c + k]) * is;
+        const float mg = (float)(sums[c + k] * invP), mgx = (float)(sums[C + c + k] * invP);
+        g[k] = gamma[c + k] * is * (gg - mg - xhat * mgx);
+      }
     }
     Vec<T>::store(dx + e, g);
   }

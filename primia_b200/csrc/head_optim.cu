@@ -1,0 +1,228 @@
+// Path T: classifier head (Linear + cross-entropy, forward and backward), optimizers on the flat
+// parameter buffer, FedAvg scaling and dtype/layout helpers.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAXC = 16;  // max classes handled by the fused head
+
+// one block per sample: logits, log-softmax, per-sample loss weight & nll, dlogits (unnormalised)
+__global__ void head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ W,
+                                const float* __restrict__ bias, const int64_t* __restrict__ labels,
+                                const float* __restrict__ soft, const float* __restrict__ cw, int F, int ncls,
+                                float* __restrict__ logits, float* __restrict__ ws) {
+  const int b = blockIdx.x;
+  __shared__ float red[MAXC][32];
+  __shared__ float lg[MAXC];
+  const float* f = feat + (size_t)b * F;
+  float part[MAXC];
+  for (int j = 0; j < ncls; ++j) part[j] = 0.f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float v = f[i];
+    for (int j = 0; j < ncls; ++j) part[j] = fmaf(v, W[(size_t)j * F + i], part[j]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j = 0; j < ncls; ++j) {
+    const float v = warp_sum(part[j]);
+    if (lane == 0) red[j][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ncls) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+    v += bias[threadIdx.x];
+    lg[threadIdx.x] = v;
+    logits[(size_t)b * ncls + threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && ws) {
+    float mx = lg[0];
+    for (int j = 1; j < ncls; ++j) mx = fmaxf(mx, lg[j]);
+    float se = 0.f;
+    for (int j = 0; j < ncls; ++j) se += expf(lg[j] - mx);
+    const float lse = mx + logf(se);
+    float* dl = ws + (size_t)b * (ncls + 1);  // [ncls] dlogits (unnormalised) + [1] weighted nll
+    if (labels) {
+      const int y = (int)labels[b];
+      const float wgt = cw ? cw[y] : 1.f;
+      for (int j = 0; j < ncls; ++j) dl[j] = wgt * (expf(lg[j] - lse) - (j == y ? 1.f : 0.f));
+      dl[ncls] = wgt * (lse - lg[y]);
+      // denominators are accumulated by head_bwd_kernel (sum of wgt) -- stash wgt in the last slot of ws
+      atomicAdd(ws + (size_t)gridDim.x * (ncls + 1), wgt);
+    } else {
+      const float* t = soft + (size_t)b * ncls;
+      float wsum = 1.f, tsum = 0.f, nll = 0.f;
+      if (cw) { wsum = 0.f; for (int j = 0; j < ncls; ++j) wsum += cw[j] * t[j]; }
+      for (int j = 0; j < ncls; ++j) { tsum += t[j]; nll += -t[j] * (lg[j] - lse); }
+      for (int j = 0; j < ncls; ++j) dl[j] = wsum * (expf(lg[j] - lse) * tsum - t[j]);
+      dl[ncls] = wsum * nll;
+      atomicAdd(ws + (size_t)gridDim.x * (ncls + 1), 1.f);
+    }
+  }
+}
+
+// normalise, loss, dfeat, dW, db.  grid: (ceil(F/128)), block 128: each thread owns one feature column f.
+__global__ void head_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ W, int B, int F, int ncls,
+                                const float* __restrict__ ws, float* __restrict__ loss, float* __restrict__ dfeat,
+                                float* __restrict__ dW, float* __restrict__ db) {
+  const float inv = 1.f / ws[(size_t)B * (ncls + 1)];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) {
+    float dw[MAXC], wcol[MAXC];
+    for (int j = 0; j < ncls; ++j) { dw[j] = 0.f; wcol[j] = W[(size_t)j * F + f]; }
+    for (int b = 0; b < B; ++b) {
+      const float* dl = ws + (size_t)b * (ncls + 1);
+      const float x = feat[(size_t)b * F + f];
+      float df = 0.f;
+      for (int j = 0; j < ncls; ++j) {
+        const float g = dl[j] * inv;
+        dw[j] = fmaf(g, x, dw[j]);
+        df = fmaf(g, wcol[j], df);
+      }
+      dfeat[(size_t)b * F + f] = df;
+    }
+    for (int j = 0; j < ncls; ++j) dW[(size_t)j * F + f] = dw[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ncls) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += ws[(size_t)b * (ncls + 1) + threadIdx.x];
+    db[threadIdx.x] = s * inv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += ws[(size_t)b * (ncls + 1) + ncls];
+    loss[0] = s * inv;
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt) {
+  // torch.optim.Adam (single-tensor path): grad += wd*p ; m = b1*m + (1-b1)*grad ; v = b2*v + (1-b2)*grad^2 ;
+  // denom = sqrt(v)/sqrt(bias_correction2) + eps ; p -= (lr/bias_correction1) * m/denom
+  const float step = lr / bc1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i]);
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // lerp_(grad, 1-beta1)
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step * (mi / denom);
+  }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float lr, float wd) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    p[i] = pi - lr * fmaf(wd, pi, g[i]);
+  }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, float scale, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= scale;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(x[i]);
+}
+
+// NCHW fp32 -> NHWC bf16 with channel padding (Cpad >= C, zero filled)
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, int C, int HW, int Cpad, size_t total,
+                                         __nv_bfloat16* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const size_t t = i / Cpad;
+    const size_t hw = t % HW, b = t / HW;
+    out[i] = c < C ? __float2bfloat16_rn(x[(b * C + c) * HW + hw]) : __float2bfloat16_rn(0.f);
+  }
+}
+
+// fp32 KRSC master -> bf16 forward operand [K][R][S][Cpad] and dgrad operand [C][R][S][K]
+__global__ void krsc_to_bf16_kernel(const float* __restrict__ w, int K, int C, int RS, int Cpad,
+                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const size_t nf = (size_t)K * RS * Cpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nf; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const size_t t = i / Cpad;
+    const int rs = (int)(t % RS);
+    const size_t k = t / RS;
+    const float v = c < C ? w[(k * RS + rs) * C + c] : 0.f;
+    wf[i] = __float2bfloat16_rn(v);
+    if (wd && c < C) wd[((size_t)c * RS + rs) * K + k] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                     const float* class_w, int B, int F, int ncls, float* logits, float* loss, float* dfeat,
+                     float* dW, float* db, float* ws, pm_stream_t s) {
+  PM_CHECK_ARG(feat && W && bias && logits && loss && dfeat && dW && db && ws && B > 0 && F > 0 && ncls > 0 && ncls <= MAXC);
+  PM_CHECK_ARG((labels != nullptr) != (soft != nullptr));
+  PM_CUDA(cudaMemsetAsync(ws + (size_t)B * (ncls + 1), 0, sizeof(float), S(s)));
+  head_fwd_kernel<<<B, 128, 0, S(s)>>>(feat, W, bias, labels, soft, class_w, F, ncls, logits, ws);
+  head_bwd_kernel<<<(F + 127) / 128, 128, 0, S(s)>>>(feat, W, B, F, ncls, ws, loss, dfeat, dW, db);
+  PM_LAUNCH_OK();
+}
+
+int pm_linear_fwd_f32(const float* feat, const float* W, const float* bias, int B, int F, int ncls, float* logits,
+                      pm_stream_t s) {
+  PM_CHECK_ARG(feat && W && bias && logits && B > 0 && F > 0 && ncls > 0 && ncls <= MAXC);
+  head_fwd_kernel<<<B, 128, 0, S(s)>>>(feat, W, bias, nullptr, nullptr, nullptr, F, ncls, logits, nullptr);
+  PM_LAUNCH_OK();
+}
+
+int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, pm_stream_t s) {
+  PM_CHECK_ARG(p && g && m && v && step >= 1);
+  if (n == 0) return PM_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<pm_grid(n, 256, 1, 16), 256, 0, S(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                       (float)sqrt(bc2));
+  PM_LAUNCH_OK();
+}
+
+int pm_sgd_step_f32(float* p, const float* g, size_t n, float lr, float weight_decay, pm_stream_t s) {
+  PM_CHECK_ARG(p && g);
+  if (n == 0) return PM_OK;
+  sgd_kernel<<<pm_grid(n, 256, 1, 16), 256, 0, S(s)>>>(p, g, n, lr, weight_decay);
+  PM_LAUNCH_OK();
+}
+
+int pm_scale_f32(float* x, float scale, size_t n, pm_stream_t s) {
+  PM_CHECK_ARG(x);
+  if (n == 0) return PM_OK;
+  scale_kernel<<<pm_grid(n, 256, 1, 16), 256, 0, S(s)>>>(x, scale, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_f32_to_bf16(const float* x, void* out, size_t n, pm_stream_t s) {
+  PM_CHECK_ARG(x && out);
+  if (n == 0) return PM_OK;
+  f32_to_bf16_kernel<<<pm_grid(n, 256, 1, 16), 256, 0, S(s)>>>(x, (__nv_bfloat16*)out, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_nchw_to_nhwc_f32_bf16(const float* x, int B, int C, int H, int W, int Cpad, void* out, pm_stream_t s) {
+  PM_CHECK_ARG(x && out && Cpad >= C);
+  const size_t total = (size_t)B * H * W * Cpad;
+  nchw_to_nhwc_bf16_kernel<<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(x, C, H * W, Cpad, total, (__nv_bfloat16*)out);
+  PM_LAUNCH_OK();
+}
+
+int pm_krsc_to_bf16_fwd_dgrad(const float* w, int K, int C, int R, int S_, int Cpad, void* w_fwd, void* w_dgrad,
+                              pm_stream_t s) {
+  PM_CHECK_ARG(w && w_fwd && Cpad >= C);
+  const size_t total = (size_t)K * R * S_ * Cpad;
+  krsc_to_bf16_kernel<<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(w, K, C, R * S_, Cpad, (__nv_bfloat16*)w_fwd,
+                                                                    (__nv_bfloat16*)w_dgrad);
+  PM_LAUNCH_OK();
+}
+
+}  // extern "C"

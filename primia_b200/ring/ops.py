@@ -20,6 +20,8 @@ __all__ = [
 
 
 def _chk(t, dtype=I64):
+    if not t.is_cuda:
+        raise PrimiaError("primia_b200 ring ops take CUDA tensors only (there is no CPU fallback)")
     if t.dtype != dtype:
         raise PrimiaError(f"expected {dtype}, got {t.dtype}")
     return t.contiguous()

@@ -1,0 +1,84 @@
+"""Encrypted ResNet-18 forward on shares (inference.py:279-321): layer schedule and geometry.
+
+Round-1 scope: every *linear* layer of the encrypted forward (20 convs + fc: rows E4-E10, E13-linear of SURVEY.md
+section 8a) runs the full Beaver protocol on GPU shares at the reference's geometry and triple shapes; BatchNorm on
+shares (E11) is implemented and parity-tested (``functional.batch_norm``) and can be switched on; the comparison-based
+ops (ReLU / max-pool via FSS, E12 -- SURVEY.md section 8f "next") are not built yet, so ``linear_layers_forward`` feeds
+each layer a share tensor of the right shape rather than chaining activations."""
+from __future__ import annotations
+
+import torch
+
+from . import functional as F
+from . import ops
+from .spdz import Party, TripleProvider
+from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
+
+# (name, Cin, H_in, Cout, k, stride, pad) for a 224x224 input -- torchlib/models.py:379-405,425-464
+RESNET18_CONVS = [("conv1", 3, 224, 64, 7, 2, 3)]
+_h, _c = 56, 64
+for _li, (_planes, _stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+    for _bi in range(2):
+        _st = _stride if _bi == 0 else 1
+        RESNET18_CONVS.append((f"layer{_li}.{_bi}.conv1", _c, _h, _planes, 3, _st, 1))
+        _ho = (_h + 2 - 3) // _st + 1
+        RESNET18_CONVS.append((f"layer{_li}.{_bi}.conv2", _planes, _ho, _planes, 3, 1, 1))
+        if _st != 1 or _c != _planes:
+            RESNET18_CONVS.append((f"layer{_li}.{_bi}.downsample.0", _c, _h, _planes, 1, _st, 0))
+        _c, _h = _planes, _ho
+
+
+def triple_shapes(batch=1, num_classes=3):
+    """Beaver-triple shapes one encrypted image consumes (reference im2col-shaped: spdz.py:36-38)."""
+    out = []
+    for name, C, H, Co, k, s, p in RESNET18_CONVS:
+        Ho = (H + 2 * p - k) // s + 1
+        out.append((name, ((batch, Ho * Ho, C * k * k), (C * k * k, Co))))
+    out.append(("fc", ((batch, 512), (512, num_classes))))
+    return out
+
+
+class SharedLinearLayers:
+    """Holds the 2-party sharing of the 21 weight tensors and runs every linear layer's protocol."""
+
+    def __init__(self, parties, provider: TripleProvider, base=10, precision_fractional=16, num_classes=3, seed=42):
+        self.parties, self.provider = parties, provider
+        self.base, self.pf, self.ncls = base, precision_fractional, num_classes
+        dev = parties[0].device
+        g = torch.Generator().manual_seed(seed)
+        self.weights = {}
+        for name, C, H, Co, k, s, p in RESNET18_CONVS:
+            w = (torch.randn(Co, C, k, k, generator=g) * (2.0 / (Co * k * k)) ** 0.5).to(dev)
+            self.weights[name] = FixedPrecisionTensor.fix_precision(w, base, precision_fractional).share(
+                *parties, crypto_provider=provider)
+        self.fc_w = FixedPrecisionTensor.fix_precision((torch.randn(num_classes, 512, generator=g) * 0.04).to(dev), base,
+                                                       precision_fractional).share(*parties, crypto_provider=provider)
+        self.fc_b = FixedPrecisionTensor.fix_precision(torch.zeros(num_classes, device=dev), base,
+                                                       precision_fractional).share(*parties, crypto_provider=provider)
+
+    def make_inputs(self, batch=1, seed=7):
+        """synthetic activation shares of every layer's input shape (encode + share on GPU)."""
+        dev = self.parties[0].device
+        g = torch.Generator().manual_seed(seed)
+        xs = {}
+        for name, C, H, Co, k, s, p in RESNET18_CONVS:
+            x = torch.randn(batch, C, H, H, generator=g).to(dev)
+            xs[name] = FixedPrecisionTensor.fix_precision(x, self.base, self.pf).share(*self.parties,
+                                                                                       crypto_provider=self.provider)
+        f = torch.randn(batch, 512, generator=g).to(dev)
+        xs["fc"] = FixedPrecisionTensor.fix_precision(f, self.base, self.pf).share(*self.parties, crypto_provider=self.provider)
+        return xs
+
+    def preprocess(self, batch=1, n_images=1):
+        """offline phase: build and distribute the triples n_images forward passes will consume."""
+        for _ in range(n_images):
+            for _name, shapes in triple_shapes(batch, self.ncls):
+                self.provider.provide_primitives("matmul", shapes, self.parties, 1)
+
+    def forward(self, xs):
+        """online phase of all 21 linear layers; returns {name: FixedPrecisionTensor}."""
+        out = {}
+        for name, C, H, Co, k, s, p in RESNET18_CONVS:
+            out[name] = F.conv2d(xs[name], self.weights[name], None, s, p)
+        out["fc"] = F.linear(xs["fc"], self.fc_w, self.fc_b)
+        return out

@@ -1,0 +1,111 @@
+"""Federated round on GPUs: one hospital (PySyft VirtualWorker) == one ResNet18Engine pinned to one GPU.
+
+Mirrors torchlib/utils.py:
+  secure_aggregation_epoch :1108-1233  -> federated_round
+  aggregation              :1000-1092  -> aggregation  (sum over hospitals of the flat state, / n or weighted)
+  send_new_models          :1095-1105  -> the all-reduce result is already resident on every GPU
+  optimizer reset          :1131-1145,1209-1218 -> ResNet18Engine.reset_optimizer
+Two deployments:
+  * multi-process (one rank per GPU, torch.distributed NCCL): FedAvg = all_reduce(sum) of ``engine.flat``
+    over NVLink followed by ``pm_scale_f32`` (weighted averaging pre-scales by w_i, utils.py:953-957,1051-1055);
+  * single-process (several hospitals time-sharing one GPU, as the reference's VirtualWorkers share one
+    process): the same sum is formed locally with ``pm_scale_f32`` + in-place adds.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from .._lib import call, ptr, stream
+from .resnet18 import ResNet18Engine
+
+
+class HospitalWorker:
+    """A data owner: its engine (model + optimizer state) and its local batches."""
+
+    def __init__(self, id: str, engine: ResNet18Engine):
+        self.id = id
+        self.engine = engine
+        self.batches: List = []
+
+    def local_step(self, data, target):
+        """utils.py:1168-1174"""
+        return self.engine.train_step(data, target)
+
+    def local_step_host(self, host_data, host_target):
+        """Same step fed from HOST memory (pinned): the batch is copied host->device on the step's stream, as a worker
+        receiving its loader's batch does; the returned loss is a device scalar the caller reads back."""
+        eng = self.engine
+        if getattr(self, "_stage", None) is None or self._stage[0].shape != host_data.shape:
+            self._stage = (torch.empty(host_data.shape, dtype=host_data.dtype, device=eng.device),
+                           torch.empty(host_target.shape, dtype=host_target.dtype, device=eng.device))
+        with torch.cuda.device(eng.device):
+            self._stage[0].copy_(host_data, non_blocking=True)
+            self._stage[1].copy_(host_target, non_blocking=True)
+        return eng.train_step(self._stage[0], self._stage[1])
+
+
+def _scale(t: torch.Tensor, scale: float):
+    with torch.cuda.device(t.device):
+        call("pm_scale_f32", ptr(t), ctypes.c_float(scale), t.numel(), stream())
+
+
+def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float]] = None, group=None):
+    """FedAvg of every state entry except num_batches_tracked (utils.py:1027-1092).
+
+    With ``group`` (torch.distributed process group, one hospital per rank) this is one NCCL all-reduce of the
+    flat state; otherwise the hospitals of this process are reduced locally.  Returns nothing: every engine ends
+    with the averaged state (== aggregation + send_new_models)."""
+    import torch.distributed as dist
+
+    if group is not None or (dist.is_available() and dist.is_initialized() and len(workers) == 1):
+        eng = workers[0].engine
+        n = dist.get_world_size(group)
+        if weights is not None:
+            _scale(eng.flat, float(weights[workers[0].id]))
+        dist.all_reduce(eng.flat, op=dist.ReduceOp.SUM, group=group)
+        if weights is None:
+            _scale(eng.flat, 1.0 / n)
+        return
+    n = len(workers)
+    acc = workers[0].engine.flat
+    if weights is not None:
+        _scale(acc, float(weights[workers[0].id]))
+    for w in workers[1:]:
+        src = w.engine.flat
+        if weights is not None:
+            _scale(src, float(weights[w.id]))
+        acc.add_(src.to(acc.device))  # ring-free local reduction; torch add is plumbing, not the hot path
+    if weights is None:
+        _scale(acc, 1.0 / n)
+    for w in workers[1:]:
+        w.engine.flat.copy_(acc)
+
+
+def federated_round(workers: List[HospitalWorker], sync_every_n_batch: int = 1, weights=None, keep_optim_dict=False,
+                    group=None):
+    """secure_aggregation_epoch (utils.py:1108-1233) with unencrypted aggregation.  Hospitals of this process are
+    visited in order (utils.py:1160); with one hospital per rank they run concurrently on their own GPUs."""
+    if not keep_optim_dict:
+        for w in workers:
+            w.engine.reset_optimizer()
+    losses = []
+    nb = {w.id: len(w.batches) for w in workers}
+    max_b = max(nb.values())
+    for batch_idx in range(max_b):
+        for w in workers:
+            if batch_idx >= nb[w.id]:
+                continue
+            d, t = w.batches[batch_idx]
+            losses.append(w.local_step(d, t).clone())  # engine.loss is a reused device buffer
+        if batch_idx > 0 and batch_idx % sync_every_n_batch == 0:
+            aggregation(workers, weights, group)
+            if not keep_optim_dict:
+                for w in workers:
+                    w.engine.reset_optimizer()
+    aggregation(workers, weights, group)
+    if not losses:
+        return torch.zeros(())
+    return torch.stack([l.reshape(()).to(losses[0].device) for l in losses]).mean()

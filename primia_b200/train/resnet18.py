@@ -1,0 +1,538 @@
+"""ResNet-18 (torchlib/models.py:345-516) forward / backward / optimizer step as a fixed schedule of
+primia_b200 kernels.
+
+The engine owns ONE flat fp32 buffer ``flat`` = [all parameters in ``model.parameters()`` order |
+all BN running_mean/running_var], so that
+  * the optimizer is a single kernel over ``flat[:n_params]``            (train.py:280-303),
+  * FedAvg is a single all-reduce over ``flat``                          (torchlib/utils.py:1000-1092;
+    ``num_batches_tracked`` is skipped exactly as the reference does, utils.py:1040).
+Activations are NHWC, conv weights KRSC; ``state_dict()/load_state_dict()`` speak the reference's
+torch layout (NCHW/KCRS, torchvision key names) so checkpoints interchange (utils.py:1470-1493).
+
+mode "f32": fp32 activations, FFMA implicit-GEMM convs (the 1e-5 parity gate runs here).
+mode "bf16": bf16 activations, tcgen05 tensor-core convs with fp32 accumulation (throughput mode).
+There is no PyTorch fallback: every arithmetic op is a C-ABI call.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from .._lib import ConvDesc, PrimiaError, call, ptr, stream
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class _Conv:
+    def __init__(self, name, B, H, W, C, K, R, stride, pad):
+        self.name = name
+        self.Ho = (H + 2 * pad - R) // stride + 1
+        self.Wo = (W + 2 * pad - R) // stride + 1
+        self.desc = ConvDesc(B, H, W, C, K, R, R, stride, pad, self.Ho, self.Wo)
+        self.B, self.H, self.W, self.C, self.K, self.R, self.stride, self.pad = B, H, W, C, K, R, stride, pad
+        self.P = B * self.Ho * self.Wo  # output rows
+
+    @property
+    def wshape(self):  # KRSC
+        return (self.K, self.R, self.R, self.C)
+
+
+class ResNet18Engine:
+    BN_EPS = 1e-5
+    BN_MOMENTUM = 0.1
+
+    def __init__(self, batch, num_classes=3, in_channels=3, input_size=224, pooling="max", device="cuda:0", mode="f32",
+                 optimizer="Adam", lr=1e-4, betas=(0.5, 0.99), weight_decay=5e-4, eps=1e-8, class_weights=None):
+        if pooling != "max":
+            raise NotImplementedError("pooling='max' (MaxPool2d(3,2,1), models.py:384-385) is the built path")
+        if mode not in ("f32", "bf16"):
+            raise ValueError(mode)
+        self.B, self.ncls, self.cin, self.size = batch, num_classes, in_channels, input_size
+        self.device = torch.device(device)
+        self.mode = mode
+        self.adt = torch.float32 if mode == "f32" else torch.bfloat16
+        self.sfx = "_f32" if mode == "f32" else "_bf16"
+        self.opt_name, self.lr, self.betas, self.wd, self.opt_eps = optimizer, lr, betas, weight_decay, eps
+        self.step_count = 0
+        self.training = True
+        self._prof = None
+        self._graph = None
+        self._build_graph()
+        self._alloc()
+        self.class_weights = None
+        if class_weights is not None:
+            self.class_weights = torch.as_tensor(class_weights, dtype=torch.float32, device=self.device).contiguous()
+
+    # ------------------------------------------------------------------ graph
+    def _build_graph(self):
+        B, S = self.B, self.size
+        self.cin_pad = self.cin if self.mode == "f32" else 8  # bf16 path pads the stem channels to 16 B per pixel
+        convs, bns = OrderedDict(), OrderedDict()
+        c1 = _Conv("conv1", B, S, S, self.cin_pad, 64, 7, 2, 3)
+        convs["conv1"] = c1
+        bns["bn1"] = 64
+        H = (c1.Ho + 2 - 3) // 2 + 1  # maxpool 3,2,1
+        self.pool_in, self.pool_out = c1.Ho, H
+        blocks = []
+        inpl = 64
+        for li, (planes, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+            for bi in range(2):
+                st = stride if bi == 0 else 1
+                pre = f"layer{li}.{bi}"
+                ca = _Conv(pre + ".conv1", B, H, H, inpl, planes, 3, st, 1)
+                cb = _Conv(pre + ".conv2", B, ca.Ho, ca.Ho, planes, planes, 3, 1, 1)
+                convs[ca.name], convs[cb.name] = ca, cb
+                bns[pre + ".bn1"], bns[pre + ".bn2"] = planes, planes
+                ds = None
+                if st != 1 or inpl != planes:
+                    ds = _Conv(pre + ".downsample.0", B, H, H, inpl, planes, 1, st, 0)
+                    convs[ds.name] = ds
+                    bns[pre + ".downsample.1"] = planes
+                blocks.append((pre, ca, cb, ds))
+                inpl, H = planes, ca.Ho
+        self.convs, self.bns, self.blocks = convs, bns, blocks
+        self.final_hw = H
+        if H * 32 != S and int(S / 32) != H:
+            pass
+        self.feat_dim = 512
+        # parameter order == model.parameters() order of the reference module
+        order = [("conv1.weight", c1.wshape), ("bn1.weight", (64,)), ("bn1.bias", (64,))]
+        for pre, ca, cb, ds in blocks:
+            order += [(ca.name + ".weight", ca.wshape), (pre + ".bn1.weight", (ca.K,)), (pre + ".bn1.bias", (ca.K,)),
+                      (cb.name + ".weight", cb.wshape), (pre + ".bn2.weight", (cb.K,)), (pre + ".bn2.bias", (cb.K,))]
+            if ds is not None:
+                order += [(ds.name + ".weight", ds.wshape), (pre + ".downsample.1.weight", (ds.K,)),
+                          (pre + ".downsample.1.bias", (ds.K,))]
+        order += [("fc.weight", (self.ncls, 512)), ("fc.bias", (self.ncls,))]
+        self.param_order = order
+        off = 0
+        self.offsets = OrderedDict()
+        for name, shape in order:
+            n = 1
+            for d in shape:
+                n *= d
+            self.offsets[name] = (off, n, shape)
+            off = _align(off + n)
+        self.n_param_flat = off
+        for bn, C in bns.items():
+            for stat in ("running_mean", "running_var"):
+                self.offsets[f"{bn}.{stat}"] = (off, C, (C,))
+                off = _align(off + C)
+        self.n_flat = off
+
+    # ------------------------------------------------------------------ memory
+    def _alloc(self):
+        dev, f32 = self.device, torch.float32
+        self.flat = torch.zeros(self.n_flat, dtype=f32, device=dev)
+        self.grads = torch.zeros(self.n_param_flat, dtype=f32, device=dev)
+        self.adam_m = torch.zeros(self.n_param_flat, dtype=f32, device=dev)
+        self.adam_v = torch.zeros(self.n_param_flat, dtype=f32, device=dev)
+        self.p = {k: self.flat[o:o + n].view(shape) for k, (o, n, shape) in self.offsets.items()}
+        self.g = {k: self.grads[o:o + n].view(shape) for k, (o, n, shape) in self.offsets.items() if o < self.n_param_flat}
+        for bn in self.bns:
+            self.p[bn + ".running_var"].fill_(1.0)
+            self.p[bn + ".weight"].fill_(1.0)
+        B, adt = self.B, self.adt
+        A = lambda *s: torch.empty(s, dtype=adt, device=dev)
+        c1 = self.convs["conv1"]
+        self.x0 = A(B, self.size, self.size, self.cin_pad)
+        self.act = {}   # forward tensors
+        self.grad = {}  # backward tensors
+        self.act["conv1"] = A(B, c1.Ho, c1.Wo, 64)
+        self.act["a1"] = A(B, c1.Ho, c1.Wo, 64)
+        self.act["p1"] = A(B, self.pool_out, self.pool_out, 64)
+        self.pool_idx = torch.empty((B, self.pool_out, self.pool_out, 64), dtype=torch.uint8, device=dev)
+        for pre, ca, cb, ds in self.blocks:
+            self.act[ca.name] = A(B, ca.Ho, ca.Wo, ca.K)
+            self.act[pre + ".a"] = A(B, ca.Ho, ca.Wo, ca.K)
+            self.act[cb.name] = A(B, cb.Ho, cb.Wo, cb.K)
+            self.act[pre + ".out"] = A(B, cb.Ho, cb.Wo, cb.K)
+            if ds is not None:
+                self.act[ds.name] = A(B, ds.Ho, ds.Wo, ds.K)
+                self.act[pre + ".idn"] = A(B, ds.Ho, ds.Wo, ds.K)
+        self.bn_mean = {bn: torch.empty(C, dtype=f32, device=dev) for bn, C in self.bns.items()}
+        self.bn_invstd = {bn: torch.empty(C, dtype=f32, device=dev) for bn, C in self.bns.items()}
+        self.stats = torch.zeros(len(self.bns) * 2 * 2 * 512, dtype=torch.float64, device=dev)  # fwd + bwd slots
+        self.feat = torch.empty((B, 512), dtype=f32, device=dev)
+        self.dfeat = torch.empty((B, 512), dtype=f32, device=dev)
+        self.logits = torch.empty((B, self.ncls), dtype=f32, device=dev)
+        self.loss = torch.zeros(1, dtype=f32, device=dev)
+        self.head_ws = torch.empty(B * (self.ncls + 1) + 4, dtype=f32, device=dev)
+        # gradient buffers: two ping-pong buffers per spatial stage + one for conv-output grads
+        self._gbufs = {}
+        ws_bytes = 0
+        for c in self.convs.values():
+            ws_bytes = max(ws_bytes, int(self._lib_size("pm_conv_wgrad_ws_bytes", c)))
+        self.wgrad_ws = torch.empty(max(ws_bytes, 16) // 4 + 4, dtype=f32, device=dev)
+        if self.mode == "bf16":
+            self.wbf = {}
+            for name, c in self.convs.items():
+                self.wbf[name] = (torch.empty(c.wshape, dtype=torch.bfloat16, device=dev),
+                                  torch.empty((c.C, c.R, c.R, c.K), dtype=torch.bfloat16, device=dev))
+
+    def _lib_size(self, fn, conv):
+        from .._lib import lib
+
+        return getattr(lib(), fn)(ctypes.byref(conv.desc))
+
+    def _gbuf(self, key, like):
+        t = self._gbufs.get(key)
+        if t is None or t.shape != like.shape:
+            t = torch.empty_like(like)
+            self._gbufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------ state (reference layout)
+    def load_state_dict(self, sd):
+        """Accepts the reference's ``model.state_dict()`` (NCHW/KCRS fp32, torchvision names)."""
+        with torch.cuda.device(self.device):
+            for name, (o, n, shape) in self.offsets.items():
+                if name not in sd:
+                    raise KeyError(name)
+                src = sd[name].detach().to(self.device, torch.float32).contiguous()
+                if name.endswith("weight") and src.dim() == 4:
+                    K, C, R, S_ = src.shape
+                    dst = self.p[name]
+                    if dst.shape[3] != C:  # padded stem channels (bf16 mode)
+                        tmp = torch.empty((K, R, S_, C), dtype=torch.float32, device=self.device)
+                        call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(tmp), stream())
+                        dst.zero_()
+                        dst[..., :C].copy_(tmp)
+                    else:
+                        call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(dst), stream())
+                else:
+                    self.p[name].copy_(src.view(shape))
+
+    def state_dict(self):
+        out = OrderedDict()
+        with torch.cuda.device(self.device):
+            for name, (o, n, shape) in self.offsets.items():
+                t = self.p[name]
+                if len(shape) == 4:
+                    K, R, S_, C = shape
+                    if C != self._true_cin(name):
+                        t = t[..., : self._true_cin(name)].contiguous()
+                        C = t.shape[3]
+                    dst = torch.empty((K, C, R, S_), dtype=torch.float32, device=self.device)
+                    call("pm_krsc_to_kcrs_f32", ptr(t.contiguous()), K, C, R, S_, ptr(dst), stream())
+                    out[name] = dst
+                else:
+                    out[name] = t.clone()
+        # reference key order (bn: weight, bias, running_mean, running_var, num_batches_tracked)
+        ordered = OrderedDict()
+        for name, _ in self.param_order:
+            ordered[name] = out[name]
+            if name.endswith(".bias") and name[:-5] in self.bns:
+                bn = name[:-5]
+                ordered[bn + ".running_mean"] = out[bn + ".running_mean"]
+                ordered[bn + ".running_var"] = out[bn + ".running_var"]
+                ordered[bn + ".num_batches_tracked"] = torch.tensor(self.step_count, dtype=torch.int64)
+        return ordered
+
+    def _true_cin(self, name):
+        return self.cin if name == "conv1.weight" else self.offsets[name][2][3]
+
+    def grad_dict(self):
+        """gradients in the reference layout (KCRS) -- used by the parity tests"""
+        out = OrderedDict()
+        with torch.cuda.device(self.device):
+            for name, _ in self.param_order:
+                t = self.g[name]
+                if t.dim() == 4:
+                    K, R, S_, C = t.shape
+                    tc = t[..., : self._true_cin(name)].contiguous()
+                    C = tc.shape[3]
+                    dst = torch.empty((K, C, R, S_), dtype=torch.float32, device=self.device)
+                    call("pm_krsc_to_kcrs_f32", ptr(tc), K, C, R, S_, ptr(dst), stream())
+                    out[name] = dst
+                else:
+                    out[name] = t.clone()
+        return out
+
+    # ------------------------------------------------------------------ kernels
+    def _prof_begin(self):
+        if self._prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _prof_end(self, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._prof.append((e0, e1))
+
+    def _conv_fwd(self, c, x, y, stats=None):
+        e0 = self._prof_begin()
+        self._conv_fwd_impl(c, x, y, stats)
+        self._prof_end(e0)
+
+    def _conv_dgrad(self, c, dy, dx, accumulate):
+        e0 = self._prof_begin()
+        self._conv_dgrad_impl(c, dy, dx, accumulate)
+        self._prof_end(e0)
+
+    def _conv_wgrad(self, c, x, dy):
+        e0 = self._prof_begin()
+        self._conv_wgrad_impl(c, x, dy)
+        self._prof_end(e0)
+
+    def _conv_fwd_impl(self, c, x, y, stats=None):
+        if self.mode == "f32":
+            call("pm_conv_fwd_f32", ctypes.byref(c.desc), ptr(x), ptr(self.p[c.name + ".weight"]), ptr(y), stream())
+        else:
+            call("pm_conv_fwd_bf16", ctypes.byref(c.desc), ptr(x), ptr(self.wbf[c.name][0]), ptr(y),
+                 ptr(stats) if stats is not None else None, stream())
+
+    def _conv_dgrad_impl(self, c, dy, dx, accumulate):
+        if self.mode == "f32":
+            call("pm_conv_dgrad_f32", ctypes.byref(c.desc), ptr(dy), ptr(self.p[c.name + ".weight"]), ptr(dx),
+                 int(accumulate), stream())
+        else:
+            call("pm_conv_dgrad_bf16", ctypes.byref(c.desc), ptr(dy), ptr(self.wbf[c.name][1]), ptr(dx), int(accumulate),
+                 stream())
+
+    def _conv_wgrad_impl(self, c, x, dy):
+        fn = "pm_conv_wgrad_f32" if self.mode == "f32" else "pm_conv_wgrad_bf16"
+        call(fn, ctypes.byref(c.desc), ptr(x), ptr(dy), ptr(self.g[c.name + ".weight"]), ptr(self.wgrad_ws), stream())
+
+    def _stat_slot(self, idx):
+        return self.stats[idx * 1024:(idx + 1) * 1024]
+
+    def _bn_fwd(self, bn, idx, x, y, residual, relu, P, stats_done=False):
+        C = self.bns[bn]
+        st = self._stat_slot(idx)
+        if self.training:
+            if not stats_done:
+                call("pm_bn_stats" + self.sfx, ptr(x), P, C, ptr(st), stream())
+            call("pm_bn_finalize", ptr(st), P, C, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM),
+                 ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".running_mean"]),
+                 ptr(self.p[bn + ".running_var"]), stream())
+        else:
+            # eval: normalise with the running statistics (F.batch_norm(training=False))
+            self.bn_mean[bn].copy_(self.p[bn + ".running_mean"])
+            torch.rsqrt(self.p[bn + ".running_var"] + self.BN_EPS, out=self.bn_invstd[bn])
+        call("pm_bn_apply" + self.sfx, ptr(x), ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".weight"]),
+             ptr(self.p[bn + ".bias"]), ptr(residual) if residual is not None else None, int(relu), P, C, ptr(y), stream())
+
+    def _bn_bwd(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
+        C = self.bns[bn]
+        st = self._stat_slot(len(self.bns) + idx)
+        call("pm_bn_bwd_reduce" + self.sfx, ptr(dy), ptr(y_out) if y_out is not None else None, ptr(x),
+             ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), P, C, ptr(st), ptr(g_out) if g_out is not None else None, stream())
+        src = g_out if g_out is not None else dy
+        call("pm_bn_bwd_apply" + self.sfx, ptr(src), None if g_out is not None else (ptr(y_out) if y_out is not None else None),
+             ptr(x), ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".weight"]), ptr(st), P, C, ptr(dx),
+             ptr(self.g[bn + ".weight"]), ptr(self.g[bn + ".bias"]), stream())
+
+    # ------------------------------------------------------------------ forward / backward
+    def set_input(self, x_nchw):
+        """x: [B,C,H,W] fp32 CUDA (the reference's loader layout) -> internal NHWC."""
+        if tuple(x_nchw.shape) != (self.B, self.cin, self.size, self.size):
+            raise PrimiaError(f"expected input {(self.B, self.cin, self.size, self.size)}, got {tuple(x_nchw.shape)}")
+        x_nchw = x_nchw.contiguous()
+        if self.mode == "f32":
+            call("pm_nchw_to_nhwc_f32", ptr(x_nchw), self.B, self.cin, self.size, self.size, ptr(self.x0), stream())
+        else:
+            call("pm_nchw_to_nhwc_f32_bf16", ptr(x_nchw), self.B, self.cin, self.size, self.size, self.cin_pad, ptr(self.x0),
+                 stream())
+
+    def refresh_bf16_weights(self):
+        for name, c in self.convs.items():
+            wf, wd = self.wbf[name]
+            call("pm_krsc_to_bf16_fwd_dgrad", ptr(self.p[name + ".weight"]), c.K, c.C, c.R, c.R, c.C, ptr(wf),
+                 ptr(wd) if name != "conv1" else None, stream())
+
+    def forward(self, x_nchw=None):
+        with torch.cuda.device(self.device):
+            if x_nchw is not None:
+                self.set_input(x_nchw)
+            if self.training:
+                self.stats.zero_()
+            if self.mode == "bf16":
+                self.refresh_bf16_weights()
+            bn_ids = {bn: i for i, bn in enumerate(self.bns)}
+            fuse = False  # fused conv+BN-statistics epilogue: not wired yet
+            c1 = self.convs["conv1"]
+            self._conv_fwd(c1, self.x0, self.act["conv1"], self._stat_slot(bn_ids["bn1"]) if fuse else None)
+            self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
+            call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
+                 ptr(self.pool_idx), stream())
+            xin = self.act["p1"]
+            for pre, ca, cb, ds in self.blocks:
+                ia, ib = bn_ids[pre + ".bn1"], bn_ids[pre + ".bn2"]
+                self._conv_fwd(ca, xin, self.act[ca.name], self._stat_slot(ia) if fuse else None)
+                self._bn_fwd(pre + ".bn1", ia, self.act[ca.name], self.act[pre + ".a"], None, True, ca.P, fuse)
+                self._conv_fwd(cb, self.act[pre + ".a"], self.act[cb.name], self._stat_slot(ib) if fuse else None)
+                idn = xin
+                if ds is not None:
+                    idd = bn_ids[pre + ".downsample.1"]
+                    self._conv_fwd(ds, xin, self.act[ds.name], self._stat_slot(idd) if fuse else None)
+                    self._bn_fwd(pre + ".downsample.1", idd, self.act[ds.name], self.act[pre + ".idn"], None, False, ds.P, fuse)
+                    idn = self.act[pre + ".idn"]
+                self._bn_fwd(pre + ".bn2", ib, self.act[cb.name], self.act[pre + ".out"], idn, True, cb.P, fuse)
+                xin = self.act[pre + ".out"]
+            hw = self.final_hw * self.final_hw
+            call("pm_gap_fwd" + self.sfx, ptr(xin), self.B, hw, 512, ptr(self.feat), stream())
+            return xin
+
+    def logits_only(self):
+        with torch.cuda.device(self.device):
+            call("pm_linear_fwd_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]), self.B, 512, self.ncls,
+                 ptr(self.logits), stream())
+        return self.logits
+
+    def loss_and_backward(self, target):
+        """target: int64 [B] hard labels, or float [B,ncls] soft targets (Cross_entropy_one_hot, utils.py:404-441)."""
+        with torch.cuda.device(self.device):
+            hard = target.dtype == torch.int64
+            target = target.contiguous()
+            call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
+                 ptr(target) if hard else None, None if hard else ptr(target),
+                 ptr(self.class_weights) if self.class_weights is not None else None, self.B, 512, self.ncls,
+                 ptr(self.logits), ptr(self.loss), ptr(self.dfeat), ptr(self.g["fc.weight"]), ptr(self.g["fc.bias"]),
+                 ptr(self.head_ws), stream())
+            bn_ids = {bn: i for i, bn in enumerate(self.bns)}
+            last = self.act[self.blocks[-1][0] + ".out"]
+            d_out = self._gbuf(("d", last.shape, 0), last)
+            hw = self.final_hw * self.final_hw
+            call("pm_gap_bwd" + self.sfx, ptr(self.dfeat), self.B, hw, 512, ptr(d_out), stream())
+            for bi in range(len(self.blocks) - 1, -1, -1):
+                pre, ca, cb, ds = self.blocks[bi]
+                xin = self.act[self.blocks[bi - 1][0] + ".out"] if bi > 0 else self.act["p1"]
+                out = self.act[pre + ".out"]
+                # out = relu(bn2(cB) + idn).  g = d_out * (out > 0) may alias d_out (element-wise in place).
+                g = self._gbuf(("g", out.shape), out)
+                dcb = self._gbuf(("dc", out.shape), out)
+                self._bn_bwd(pre + ".bn2", bn_ids[pre + ".bn2"], d_out, out, self.act[cb.name], dcb, cb.P, g_out=g)
+                if ds is not None:
+                    d_xin = self._gbuf(("dx", xin.shape), xin)
+                    dcd = self._gbuf(("dcd", out.shape), out)
+                    self._bn_bwd(pre + ".downsample.1", bn_ids[pre + ".downsample.1"], g, None, self.act[ds.name], dcd, ds.P)
+                    self._conv_wgrad(ds, xin, dcd)
+                    self._conv_dgrad(ds, dcd, d_xin, False)
+                else:
+                    d_xin = g  # identity branch: the masked gradient flows straight through; conv1's dgrad accumulates
+                self._conv_wgrad(cb, self.act[pre + ".a"], dcb)
+                d_a = self._gbuf(("da", out.shape), out)
+                self._conv_dgrad(cb, dcb, d_a, False)
+                dca = dcb  # dcb is dead after the two calls above (stream order)
+                self._bn_bwd(pre + ".bn1", bn_ids[pre + ".bn1"], d_a, self.act[pre + ".a"], self.act[ca.name], dca, ca.P)
+                self._conv_wgrad(ca, xin, dca)
+                self._conv_dgrad(ca, dca, d_xin, True)
+                d_out = d_xin
+            c1 = self.convs["conv1"]
+            d_a1 = self._gbuf(("da1",), self.act["a1"])
+            call("pm_maxpool3s2_bwd" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
+            dc1 = self._gbuf(("dc1",), self.act["conv1"])
+            self._bn_bwd("bn1", bn_ids["bn1"], d_a1, self.act["a1"], self.act["conv1"], dc1, c1.P)
+            self._conv_wgrad(c1, self.x0, dc1)
+        return self.loss
+
+    def optimizer_step(self):
+        with torch.cuda.device(self.device):
+            self.step_count += 1
+            n = self.n_param_flat
+            if self.opt_name == "Adam":
+                call("pm_adam_step_f32", ptr(self.flat), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), n,
+                     ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
+                     ctypes.c_float(self.opt_eps), ctypes.c_float(self.wd), self.step_count, stream())
+            elif self.opt_name == "SGD":
+                call("pm_sgd_step_f32", ptr(self.flat), ptr(self.grads), n, ctypes.c_float(self.lr), ctypes.c_float(self.wd),
+                     stream())
+            else:
+                raise NotImplementedError("only Adam or SGD supported.")  # utils.py:1141
+
+    def reset_optimizer(self):
+        """utils.py:1131-1145,1209-1218: optimizers are re-created (state zeroed) after every aggregation."""
+        self.adam_m.zero_()
+        self.adam_v.zero_()
+        self.step_count = 0
+
+    def _train_step_eager(self, x_nchw, target):
+        self.forward(x_nchw)
+        loss = self.loss_and_backward(target)
+        self.optimizer_step()
+        return loss
+
+    def train_step(self, x_nchw, target):
+        """utils.py:1168-1174: zero_grad; pred = model(data); loss; backward; step.
+        Replays the captured CUDA graph when one exists for this (optimizer step index, target kind)."""
+        gr = self._graph
+        if gr is not None and gr["step"] == self.step_count + 1 and gr["tdtype"] == target.dtype:
+            gr["x"].copy_(x_nchw, non_blocking=True)
+            gr["y"].copy_(target, non_blocking=True)
+            gr["graph"].replay()
+            self.step_count += 1
+            return self.loss
+        return self._train_step_eager(x_nchw, target)
+
+    def capture_graph(self, x_nchw, target):
+        """Capture one local step (all ~190 kernel launches) in a CUDA graph.  Adam's bias correction bakes the step
+        index into the graph, so the replay is used only when the optimizer is at the captured step (always true for
+        the reference's default FedAvg-after-every-step + optimizer-reset schedule, utils.py:1175-1218)."""
+        from .. import _lib
+
+        with torch.cuda.device(self.device):
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            gx, gy = x_nchw.clone(), target.clone()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._train_step_eager(gx, gy)  # warm-up on the capture stream: allocates every lazily created buffer
+            torch.cuda.current_stream().wait_stream(side)
+            self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_counter
+            with torch.cuda.graph(graph):
+                self._train_step_eager(gx, gy)
+            launches = _lib.launch_counter - n0 + 1  # + stats.zero_()
+            self.step_count = snap[3]
+            self._graph = {"graph": graph, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype, "launches": launches}
+        return launches
+
+    def profile_conv_time(self, x_nchw, target, steps=2):
+        """Device time of the convolution kernels per local step (CUDA events on the launching stream around each of the
+        60 conv launches, eager mode) and the number of kernel launches per step."""
+        from .. import _lib
+
+        with torch.cuda.device(self.device):
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            self._train_step_eager(x_nchw, target)
+            torch.cuda.synchronize(self.device)
+            self._prof = []
+            n0 = _lib.launch_counter
+            for _ in range(steps):
+                self._train_step_eager(x_nchw, target)
+            torch.cuda.synchronize(self.device)
+            launches = (_lib.launch_counter - n0) // steps + 1
+            ms = sum(a.elapsed_time(b) for a, b in self._prof) / steps
+            self._prof = None
+            self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+        return ms, launches
+
+    def init_random(self, seed=42):
+        """Random-init weights of the reference architecture (models.py:408-413: Kaiming-normal fan_out convs, BN 1/0;
+        nn.Linear default init for fc), generated on the device."""
+        with torch.cuda.device(self.device):
+            g = torch.Generator(device=self.device).manual_seed(seed)
+            self.flat.zero_()
+            for name, c in self.convs.items():
+                w = self.p[name + ".weight"]
+                std = (2.0 / (c.K * c.R * c.R)) ** 0.5
+                w.copy_(torch.randn(w.shape, device=self.device, generator=g) * std)
+                if w.shape[3] != self._true_cin(name + ".weight"):
+                    w[..., self._true_cin(name + ".weight"):].zero_()
+            for bn in self.bns:
+                self.p[bn + ".weight"].fill_(1.0)
+                self.p[bn + ".running_var"].fill_(1.0)
+            bound = 1.0 / (512 ** 0.5)
+            self.p["fc.weight"].copy_((torch.rand((self.ncls, 512), device=self.device, generator=g) * 2 - 1) * bound)
+            self.p["fc.bias"].copy_((torch.rand((self.ncls,), device=self.device, generator=g) * 2 - 1) * bound)
+            self.reset_optimizer()
