@@ -77,6 +77,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """cores this process may actually use (affinity mask and cgroup cpu quota), not the machine's core count"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path (oracle restatement of torchlib/utils.py:1108-1233 +
@@ -88,7 +100,7 @@ def run_reference(args):
 
     from oracle import train_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     n_workers = args.gpus
     # bounded sample: size the per-hospital batch so that (steps + warmup) rounds fit in ~150 s of host time
@@ -145,7 +157,7 @@ def cpu_baseline_sample(seconds_cap=25.0):
 
     from oracle import train_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     m = O.resnet18(seed=42)
     opt = O.make_optimizer(m)

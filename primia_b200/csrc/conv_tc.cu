@@ -12,6 +12,7 @@
 //   wgrad: D[(r,s,c), k] = A[pix, (r,s,c)]^T    (gather, MN-major) x  dy[pix, k]         (dense, MN-major)
 //          reduction over pixels, split across CTAs, fp32 red.add into dW.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -447,17 +448,36 @@ int tc_wgrad_splits(const pm_conv_t* p, int BN) {
 
 }  // namespace
 
+// TMA-fed variants (conv_tma.cu): 0 = launched, 1 = shape not eligible (use the cp.async variant), 2 = error
+int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, cudaStream_t st);
+int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
+int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
+static bool use_tma() {
+  const char* e = getenv("PRIMIA_NO_TMA");
+  return !(e && e[0] == '1');
+}
+
 extern "C" {
 
 int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && x && w && y);
   PM_CHECK_ARG(stats == nullptr);  // fused BN statistics: not wired yet (use pm_bn_stats_bf16)
+  if (use_tma()) {
+    const int r = pm_tma_conv_fwd(p, x, w, y, S(s));
+    if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv fwd setup failed");
+    if (r == 0) PM_LAUNCH_OK();
+  }
   if (launch_conv<0>(p, x, w, y, 0, S(s))) return PM_ECUDA;
   PM_LAUNCH_OK();
 }
 
 int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && dy && wt && dx && p->C % 64 == 0);
+  if (use_tma()) {
+    const int r = pm_tma_conv_dgrad(p, dy, wt, dx, accumulate, S(s));
+    if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv dgrad setup failed");
+    if (r == 0) PM_LAUNCH_OK();
+  }
   if (launch_conv<1>(p, dy, wt, dx, accumulate, S(s))) return PM_ECUDA;
   PM_LAUNCH_OK();
 }
@@ -465,6 +485,11 @@ int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void*
 int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, void* ws, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && x && dy && dw);
   (void)ws;
+  if (use_tma()) {
+    const int r = pm_tma_conv_wgrad(p, x, dy, dw, S(s));
+    if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv wgrad setup failed");
+    if (r == 0) PM_LAUNCH_OK();
+  }
   const int M = p->B * p->Ho * p->Wo;
   const int Kg = p->R * p->S * p->C;
   PM_CUDA(cudaMemsetAsync(dw, 0, (size_t)p->K * Kg * sizeof(float), S(s)));

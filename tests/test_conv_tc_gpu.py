@@ -17,6 +17,8 @@ CASES = [  # B, H, C, K, R, stride, pad
     (3, 8, 256, 512, 3, 2, 1),
     (2, 32, 8, 64, 7, 2, 3),        # stem geometry, channels padded 3 -> 8, K = 392 (tail k-block)
     (1, 14, 512, 512, 3, 1, 1),
+    (5, 12, 64, 64, 3, 1, 1),       # 128-pixel tiles straddle image boundaries (144 px / image)
+    (2, 10, 128, 128, 3, 2, 1),
 ]
 
 
@@ -36,9 +38,12 @@ def bf(t):
     return t.to(torch.bfloat16)
 
 
+@pytest.mark.parametrize("no_tma", ["0", "1"])  # 0: TMA im2col producer where eligible; 1: cp.async gather everywhere
 @pytest.mark.parametrize("case", CASES)
-def test_fwd_dgrad_wgrad_bf16(case):
+def test_fwd_dgrad_wgrad_bf16(case, no_tma, monkeypatch):
     from primia_b200._lib import call, ptr, stream
+
+    monkeypatch.setenv("PRIMIA_NO_TMA", no_tma)
 
     B, H, C, K, R, s, p = case
     g = torch.Generator().manual_seed(sum(case))
