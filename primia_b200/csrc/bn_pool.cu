@@ -3,6 +3,7 @@
 // double accumulation for the statistics (the CPU reference accumulates in double too), grids sized as a
 // multiple of the SM count.  T = float (parity mode) or __nv_bfloat16 (throughput mode).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -42,31 +43,43 @@ struct Vec<__nv_bfloat16> {
 constexpr int BT = 256;
 
 // ---- per-channel sums: out[0..C) += sum f0 , out[C..2C) += sum f1   (f0,f1 produced by Functor per element)
+// Each thread owns one 16-byte channel group (column v) and walks rows, U rows in flight; partial sums are kept in
+// double in fp32 (parity) mode -- ATen's CPU kernels accumulate in double -- and in float in bf16 mode.
 template <typename T, typename F>
 __global__ void __launch_bounds__(BT) chan_reduce_kernel(size_t P, int C, double* __restrict__ out, F f) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
+  using acc_t = typename std::conditional<sizeof(T) == 4, double, float>::type;
   const int vr = C / V;                 // vectors per row (divides BT)
   const int v = threadIdx.x % vr;
   const int rpb = BT / vr;              // rows per block pass
   const int r0 = threadIdx.x / vr;
-  double s0[V], s1[V];
+  acc_t s0[V], s1[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0.0;
-  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += (size_t)gridDim.x * rpb) {
-    float a[V], b[V];
-    f(row, v * V, a, b);
+  for (int i = 0; i < V; ++i) s0[i] = s1[i] = 0;
+  const size_t stride = (size_t)gridDim.x * rpb;
+  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
+    float a[U][V], b[U][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { s0[i] += (double)a[i]; s1[i] += (double)b[i]; }
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) f(r, v * V, a[u], b[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[u][i] = b[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s0[i] += (acc_t)a[u][i]; s1[i] += (acc_t)b[u][i]; }
   }
-  // combine threads sharing a column group through shared memory
-  __shared__ double sh[2][BT][Vec<T>::N > 4 ? 1 : 1];
   extern __shared__ double dyn[];       // [2][BT*V]
   double* d0 = dyn;
   double* d1 = dyn + BT * V;
 #pragma unroll
-  for (int i = 0; i < V; ++i) { d0[threadIdx.x * V + i] = s0[i]; d1[threadIdx.x * V + i] = s1[i]; }
+  for (int i = 0; i < V; ++i) { d0[threadIdx.x * V + i] = (double)s0[i]; d1[threadIdx.x * V + i] = (double)s1[i]; }
   __syncthreads();
-  (void)sh;
   for (int c = threadIdx.x; c < C; c += BT) {
     const int vv = c / V, ii = c % V;
     double t0 = 0.0, t1 = 0.0;
@@ -128,22 +141,39 @@ template <typename T>
 __global__ void __launch_bounds__(BT)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ res, int relu,
-                size_t nvec, int C, T* __restrict__ y) {
+                size_t P, int C, T* __restrict__ y) {
   constexpr int V = Vec<T>::N;
-  for (size_t i = blockIdx.x * (size_t)BT + threadIdx.x; i < nvec; i += (size_t)gridDim.x * BT) {
-    const size_t e = i * V;
-    const int c = (int)(e % C);
-    float xv[V], rv[V];
-    Vec<T>::load(x + e, xv);
-    if (res) Vec<T>::load(res + e, rv);
+  constexpr int U = 4;
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  float mu[V], is[V], ga[V], be[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float v = (xv[k] - mean[c + k]) * invstd[c + k] * gamma[c + k] + beta[c + k];
-      if (res) v += rv[k];
-      if (relu) v = v > 0.f ? v : 0.f;
-      xv[k] = v;
+  for (int k = 0; k < V; ++k) { mu[k] = mean[c + k]; is[k] = invstd[c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+  const size_t stride = (size_t)gridDim.x * rpb;
+  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
+    float xv[U][V], rv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+        Vec<T>::load(x + r * C + c, xv[u]);
+        if (res) Vec<T>::load(res + r * C + c, rv[u]);
+      }
     }
-    Vec<T>::store(y + e, xv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float t = (xv[u][k] - mu[k]) * is[k] * ga[k] + be[k];
+          if (res) t += rv[u][k];
+          if (relu) t = t > 0.f ? t : 0.f;
+          xv[u][k] = t;
+        }
+        Vec<T>::store(y + r * C + c, xv[u]);
+      }
+    }
   }
 }
 
@@ -151,34 +181,52 @@ template <typename T>
 __global__ void __launch_bounds__(BT)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const T* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                    const double* __restrict__ sums, double invP, size_t nvec, int C, T* __restrict__ dx) {
+                    const double* __restrict__ sums, double invP, size_t P, int C, T* __restrict__ dx) {
   constexpr int V = Vec<T>::N;
-  for (size_t i = blockIdx.x * (size_t)BT + threadIdx.x; i < nvec; i += (size_t)gridDim.x * BT) {
-    const size_t e = i * V;
-    const int c = (int)(e % C);
-    float g[V], xv[V], yv[V];
-    Vec<T>::load(dy + e, g);
-    Vec<T>::load(x + e, xv);
-    if (y_out) Vec<T>::load(y_out + e, yv);
+  constexpr int U = sizeof(T) == 4 ? 2 : 4;
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  float mu[V], is[V], ga[V];
+  double mgd[V], mgxd[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float gg = g[k];
-      if (y_out) gg = yv[k] > 0.f ? gg : 0.f;
-      if (sizeof(T) == 4) {
-        // parity mode: ATen's CPU kernel evaluates dy - mean(dy) - xhat*mean(dy*xhat) in double (acc_type<float>);
-        // the per-channel common mode of dy can exceed its fluctuation by 1e3-1e4, so fp32 here costs 1e-4 relative.
-        const double is = (double)invstd[c + k];
-        const double xhat = ((double)xv[k] - (double)mean[c + k]) * is;
-        const double mg = sums[c + k] * invP, mgx = sums[C + c + k] * invP;
-        g[k] = (float)((double)gamma[c + k] * is * ((double)gg - mg - xhat * mgx));
-      } else {
-        const float is = invstd[c + k];
-        const float xhat = (xv[k] - mean[c + k]) * is;
-        const float mg = (float)(sums[c + k] * invP), mgx = (float)(sums[C + c + k] * invP);
-        g[k] = gamma[c + k] * is * (gg - mg - xhat * mgx);
+  for (int k = 0; k < V; ++k) {
+    mu[k] = mean[c + k]; is[k] = invstd[c + k]; ga[k] = gamma[c + k];
+    mgd[k] = sums[c + k] * invP; mgxd[k] = sums[C + c + k] * invP;
+  }
+  const size_t stride = (size_t)gridDim.x * rpb;
+  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
+    float g[U][V], xv[U][V], yv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+        Vec<T>::load(dy + r * C + c, g[u]);
+        Vec<T>::load(x + r * C + c, xv[u]);
+        if (y_out) Vec<T>::load(y_out + r * C + c, yv[u]);
       }
     }
-    Vec<T>::store(dx + e, g);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = g[u][k];
+          if (y_out) gg = yv[u][k] > 0.f ? gg : 0.f;
+          if (sizeof(T) == 4) {
+            // parity mode: ATen's CPU kernel evaluates dy - mean(dy) - xhat*mean(dy*xhat) in double (acc_type<float>); the
+            // per-channel common mode of dy can exceed its fluctuation by 1e3-1e4, so fp32 here would cost 1e-4 relative.
+            const double isd = (double)is[k];
+            const double xhat = ((double)xv[u][k] - (double)mu[k]) * isd;
+            g[u][k] = (float)((double)ga[k] * isd * ((double)gg - mgd[k] - xhat * mgxd[k]));
+          } else {
+            const float xhat = (xv[u][k] - mu[k]) * is[k];
+            g[u][k] = ga[k] * is[k] * (gg - (float)mgd[k] - xhat * (float)mgxd[k]);
+          }
+        }
+        Vec<T>::store(dx + r * C + c, g[u]);
+      }
+    }
   }
 }
 
@@ -190,18 +238,20 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, flo
   dgamma[c] = (float)sums[C + c];
 }
 
-// ---- max pool 3x3 s2 p1 (first max wins, like ATen's CPU kernel)
+// ---- max pool 3x3 s2 p1 (first max wins, like ATen's CPU kernel); one thread = one 16-byte channel group
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int H, int W, int C, int Ho, int Wo, size_t total,
                                    T* __restrict__ y, uint8_t* __restrict__ idx) {
+  constexpr int V = Vec<T>::N;
+  const int CV = C / V;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    size_t t = i / C;
+    const int cv = (int)(i % CV);
+    size_t t = i / CV;
     const int ow = (int)(t % Wo); t /= Wo;
     const int oh = (int)(t % Ho);
     const size_t b = t / Ho;
-    float best = -INFINITY;
-    int bi = 0;
+    float best[V];
+    int bi[V];
     bool first = true;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -211,25 +261,35 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int H, int W, int C,
       for (int s = 0; s < 3; ++s) {
         const int iw = ow * 2 - 1 + s;
         if (iw < 0 || iw >= W) continue;
-        const float v = to_f<T>(x[((b * H + ih) * W + iw) * C + c]);
-        if (first || v > best || v != v) { best = v; bi = r * 3 + s; first = false; }
+        float v[V];
+        Vec<T>::load(x + ((b * H + ih) * W + iw) * C + cv * V, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if (first || v[k] > best[k] || v[k] != v[k]) { best[k] = v[k]; bi[k] = r * 3 + s; }
+        first = false;
       }
     }
-    y[i] = from_f<T>(best);
-    idx[i] = (uint8_t)bi;
+    const size_t o = i * V;
+    Vec<T>::store(y + o, best);
+#pragma unroll
+    for (int k = 0; k < V; ++k) idx[o + k] = (uint8_t)bi[k];
   }
 }
 
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, int H, int W, int C,
                                    int Ho, int Wo, size_t total, T* __restrict__ dx) {
+  constexpr int V = Vec<T>::N;
+  const int CV = C / V;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    size_t t = i / C;
+    const int cv = (int)(i % CV);
+    size_t t = i / CV;
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const size_t b = t / H;
-    float acc = 0.f;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
     for (int oh = h / 2; oh <= (h + 1) / 2; ++oh) {
       if (oh >= Ho) continue;
       const int r = h - (oh * 2 - 1);
@@ -238,11 +298,18 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __re
         if (ow >= Wo) continue;
         const int s = w - (ow * 2 - 1);
         if (s < 0 || s > 2) continue;
-        const size_t o = ((b * Ho + oh) * Wo + ow) * C + c;
-        if (idx[o] == r * 3 + s) acc += to_f<T>(dy[o]);
+        const size_t o = (((b * Ho + oh) * Wo + ow) * CV + cv) * V;
+        float g[V];
+        Vec<T>::load(dy + o, g);
+        uint8_t id[V];
+        if (V == 8) *reinterpret_cast<uint2*>(id) = *reinterpret_cast<const uint2*>(idx + o);
+        else *reinterpret_cast<uint32_t*>(id) = *reinterpret_cast<const uint32_t*>(idx + o);
+        const int want = r * 3 + s;
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += id[k] == want ? g[k] : 0.f;
       }
     }
-    dx[i] = from_f<T>(acc);
+    Vec<T>::store(dx + i * V, acc);
   }
 }
 
@@ -269,6 +336,17 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dy, int HW, int C, size
 template <typename T>
 bool chan_ok(int C) { return C > 0 && C % Vec<T>::N == 0 && BT % (C / Vec<T>::N) == 0; }
 
+// grid for the row-walking kernels: every thread gets >= `min_rows` rows, at most 8 resident blocks per SM
+template <typename T>
+int row_grid(size_t P, int C, int min_rows) {
+  const int rpb = BT / (C / Vec<T>::N);
+  size_t blocks = (P + (size_t)rpb * min_rows - 1) / ((size_t)rpb * min_rows);
+  const size_t cap = (size_t)pm_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
 template <typename T, typename F>
 int launch_reduce(size_t P, int C, double* out, F f, cudaStream_t st) {
   const int rpb = BT / (C / Vec<T>::N);
@@ -291,8 +369,8 @@ template <typename T>
 int bn_apply_t(const T* x, const float* mean, const float* invstd, const float* gamma, const float* beta, const T* res,
                int relu, size_t P, int C, T* y, pm_stream_t s) {
   PM_CHECK_ARG(x && mean && invstd && gamma && beta && y && C % Vec<T>::N == 0);
-  const size_t nvec = P * C / Vec<T>::N;
-  bn_apply_kernel<T><<<pm_grid(nvec, BT, 1, 16), BT, 0, S(s)>>>(x, mean, invstd, gamma, beta, res, relu, nvec, C, y);
+  PM_CHECK_ARG(chan_ok<T>(C));
+  bn_apply_kernel<T><<<row_grid<T>(P, C, 4), BT, 0, S(s)>>>(x, mean, invstd, gamma, beta, res, relu, P, C, y);
   PM_LAUNCH_OK();
 }
 template <typename T>
@@ -306,9 +384,8 @@ template <typename T>
 int bn_bwd_apply_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma,
                    const double* sums, size_t P, int C, T* dx, float* dgamma, float* dbeta, pm_stream_t s) {
   PM_CHECK_ARG(dy && x && mean && invstd && gamma && sums && dx && C % Vec<T>::N == 0);
-  const size_t nvec = P * C / Vec<T>::N;
-  bn_bwd_apply_kernel<T><<<pm_grid(nvec, BT, 1, 16), BT, 0, S(s)>>>(dy, y_out, x, mean, invstd, gamma, sums,
-                                                                    1.0 / (double)P, nvec, C, dx);
+  PM_CHECK_ARG(chan_ok<T>(C));
+  bn_bwd_apply_kernel<T><<<row_grid<T>(P, C, 4), BT, 0, S(s)>>>(dy, y_out, x, mean, invstd, gamma, sums, 1.0 / (double)P, P, C, dx);
   if (dgamma && dbeta) bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, S(s)>>>(sums, C, dgamma, dbeta);
   PM_LAUNCH_OK();
 }
@@ -316,7 +393,8 @@ template <typename T>
 int maxpool_fwd_t(const T* x, int B, int H, int W, int C, T* y, uint8_t* idx, pm_stream_t s) {
   PM_CHECK_ARG(x && y && idx && B > 0);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const size_t total = (size_t)B * Ho * Wo * C;
+  PM_CHECK_ARG(C % Vec<T>::N == 0);
+  const size_t total = (size_t)B * Ho * Wo * (C / Vec<T>::N);
   maxpool_fwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(x, H, W, C, Ho, Wo, total, y, idx);
   PM_LAUNCH_OK();
 }
@@ -324,7 +402,8 @@ template <typename T>
 int maxpool_bwd_t(const T* dy, const uint8_t* idx, int B, int H, int W, int C, T* dx, pm_stream_t s) {
   PM_CHECK_ARG(dy && dx && idx && B > 0);
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const size_t total = (size_t)B * H * W * C;
+  PM_CHECK_ARG(C % Vec<T>::N == 0);
+  const size_t total = (size_t)B * H * W * (C / Vec<T>::N);
   maxpool_bwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(dy, idx, H, W, C, Ho, Wo, total, dx);
   PM_LAUNCH_OK();
 }

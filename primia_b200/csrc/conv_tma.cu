@@ -216,6 +216,132 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dgrad, stride 2
+// Decomposed by output parity class (a,b) = (h & 1, w & 1) -> blockIdx.z: dx[2i+a, 2j+b] only receives the taps with
+// r = (a+pad) mod 2, s = (b+pad) mod 2 (1+2+2+4 = 9 taps for 3x3/pad 1, 1 tap for 1x1/pad 0: no zero-stuffed work), and
+// each class is a plain stride-1 correlation of dy with row offset (a+pad-r)/2 in {0,1} -- an im2col TMA load.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, bf16* __restrict__ dst,
+                    int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t s_base = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, accum_bar = full0 + 16 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ca = blockIdx.z >> 1, cb = blockIdx.z & 1;       // parity class of (h, w)
+  const int H2 = p.H / 2, W2 = p.W / 2;                      // class-pixel grid (== Ho x Wo)
+  const int M = p.B * H2 * W2;
+  const int N = p.C;
+  const int cblocks = p.K / 64;
+  const int r_first = (ca + p.pad) & 1, s_first = (cb + p.pad) & 1;
+  const int nr = r_first < p.R ? (p.R - r_first + 1) / 2 : 0, ns = s_first < p.S ? (p.S - s_first + 1) / 2 : 0;
+  const int nkb = nr * ns * cblocks;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (tid == 0) {
+    const int nb = m0 / (H2 * W2);
+    const int rem = m0 - nb * H2 * W2;
+    const int pi = rem / W2, pj = rem - pi * W2;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+      const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+      const int ti = kb / cblocks, k0 = (kb - ti * cblocks) * 64;
+      const int ri = ti / ns, si = ti - ri * ns;
+      const int r = r_first + 2 * ri, sx = s_first + 2 * si;
+      const int off_h = (ca + p.pad - r) / 2, off_w = (cb + p.pad - sx) / 2;  // in {0, 1} for 3x3/p1 and 1x1/p0
+      mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+      tma_load_im2col(a_tile, &tmA, full0 + 8 * s, k0, pj, pi, nb, (uint16_t)off_w, (uint16_t)off_h);
+      tma_load_2d(b_tile, &tmB, full0 + 8 * s, (r * p.S + sx) * p.K + k0, n0);
+    }
+  } else if (tid == 32) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+      const uint64_t adesc = make_desc(a_tile, 16, 1024), bdesc = make_desc(b_tile, 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+      umma_commit(empty0 + 8 * s);
+    }
+    if (nkb > 0) umma_commit(accum_bar);
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int m = m0 + quad * 32 + (tid & 31);
+    const bool row_ok = m < M;
+    const int mm = row_ok ? m : 0;
+    const int nb = mm / (H2 * W2);
+    const int rem = mm - nb * H2 * W2;
+    const int pi = rem / W2, pj = rem - pi * W2;
+    bf16* out = dst + (((size_t)nb * p.H + 2 * pi + ca) * p.W + 2 * pj + cb) * N + n0;
+    if (nkb == 0) {
+      if (!accumulate && row_ok) {  // class receives no tap (1x1 / stride 2): gradient is exactly zero there
+        for (int q = 0; q < BN / 8; ++q) reinterpret_cast<uint4*>(out)[q] = make_uint4(0, 0, 0, 0);
+      }
+    } else {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            uint4* o = reinterpret_cast<uint4*>(out + cc * 32 + q * 8);
+            if (accumulate) {
+              const uint4 old = *o;
+              const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(oh[e]);
+                f[2 * e] += t.x; f[2 * e + 1] += t.y;
+              }
+            }
+            uint4 pk;
+            __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            *o = pk;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // D[kg (128 rows = two 64-wide (tap,c) blocks), n (BN couts)] += sum over the split's pixels.
 // A = im2col(x) (MN-major), B = dy [M][K] (MN-major).  grid: (ceil(Kg/128), K/BN, splits)
@@ -403,9 +529,29 @@ int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, c
 
 int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st) {
   using namespace tma;
-  if (p->stride != 1 || p->C % 64 != 0 || p->K % 64 != 0 || !load_driver()) return 1;
+  if (p->C % 64 != 0 || p->K % 64 != 0 || !load_driver()) return 1;
   CUtensorMap tmA, tmB;
   const int Ktot = p->R * p->S * p->K;
+  if (p->stride == 2) {
+    const bool geom_ok = p->H % 2 == 0 && p->W % 2 == 0 && p->Ho == p->H / 2 && p->Wo == p->W / 2 &&
+                         ((p->R == 3 && p->S == 3 && p->pad == 1) || (p->R == 1 && p->S == 1 && p->pad == 0));
+    if (!geom_ok) return 1;
+    if (!map_im2col(&tmA, dy, p->B, p->Ho, p->Wo, p->K, 0, 0, 0, 0, 1)) return 2;
+    const int Mc = p->B * p->Ho * p->Wo;
+    if (p->C % 128 == 0) {
+      if (!map_dense(&tmB, wt, p->C, Ktot, 128)) return 2;
+      if (!set_smem(dgrad_s2_tma_kernel<128, FSTAGES>, smem_conv(128, FSTAGES))) return 2;
+      dim3 grid((Mc + 127) / 128, p->C / 128, 4);
+      dgrad_s2_tma_kernel<128, FSTAGES><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate);
+    } else {
+      if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
+      if (!set_smem(dgrad_s2_tma_kernel<64, FSTAGES>, smem_conv(64, FSTAGES))) return 2;
+      dim3 grid((Mc + 127) / 128, p->C / 64, 4);
+      dgrad_s2_tma_kernel<64, FSTAGES><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate);
+    }
+    return 0;
+  }
+  if (p->stride != 1) return 1;
   // dgrad with stride 1 == correlation of dy with the mirrored filter: window base = out + pad - (R-1)
   const int lw = p->pad - (p->S - 1), lh = p->pad - (p->R - 1);
   const int uw = lw + (p->W - p->Wo), uh = lh + (p->H - p->Ho);

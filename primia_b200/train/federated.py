@@ -47,7 +47,17 @@ class HospitalWorker:
         return eng.train_step(self._stage[0], self._stage[1])
 
 
+def fedavg_scales(worker_id, n_workers: int, weights: Optional[Dict[str, float]]):
+    """(pre, post) factors around the SUM all-reduce: unweighted FedAvg divides by n afterwards (utils.py:1090);
+    weighted averaging multiplies each hospital's state by w_i before the sum (utils.py:1051-1055)."""
+    if weights is not None:
+        return float(weights[worker_id]), 1.0
+    return 1.0, 1.0 / n_workers
+
+
 def _scale(t: torch.Tensor, scale: float):
+    if scale == 1.0:
+        return
     with torch.cuda.device(t.device):
         call("pm_scale_f32", ptr(t), ctypes.c_float(scale), t.numel(), stream())
 
@@ -62,12 +72,10 @@ def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float
 
     if group is not None or (dist.is_available() and dist.is_initialized() and len(workers) == 1):
         eng = workers[0].engine
-        n = dist.get_world_size(group)
-        if weights is not None:
-            _scale(eng.flat, float(weights[workers[0].id]))
+        pre, post = fedavg_scales(workers[0].id, dist.get_world_size(group), weights)
+        _scale(eng.flat, pre)
         dist.all_reduce(eng.flat, op=dist.ReduceOp.SUM, group=group)
-        if weights is None:
-            _scale(eng.flat, 1.0 / n)
+        _scale(eng.flat, post)
         return
     n = len(workers)
     acc = workers[0].engine.flat

@@ -243,7 +243,8 @@ def test_maxpool_tie_breaking_matches_aten():
     import ctypes
     from primia_b200._lib import call, ptr, stream
 
-    x = torch.zeros(1, 2, 6, 6)
+    x = torch.zeros(1, 4, 6, 6)
+    x[0, 2, 3, 3] = -1.0
     x[0, 0, 1, 1] = 1.0
     x[0, 0, 1, 2] = 1.0
     x.requires_grad_(True)
@@ -251,11 +252,11 @@ def test_maxpool_tie_breaking_matches_aten():
     gy = torch.arange(1, y.numel() + 1, dtype=torch.float32).view_as(y)
     y.backward(gy)
     xn = x.detach().permute(0, 2, 3, 1).contiguous().to(DEV)
-    yn = torch.empty(1, 3, 3, 2, device=DEV)
-    idx = torch.empty(1, 3, 3, 2, dtype=torch.uint8, device=DEV)
-    call("pm_maxpool3s2_fwd_f32", ptr(xn), 1, 6, 6, 2, ptr(yn), ptr(idx), stream())
+    yn = torch.empty(1, 3, 3, 4, device=DEV)
+    idx = torch.empty(1, 3, 3, 4, dtype=torch.uint8, device=DEV)
+    call("pm_maxpool3s2_fwd_f32", ptr(xn), 1, 6, 6, 4, ptr(yn), ptr(idx), stream())
     gyn = gy.permute(0, 2, 3, 1).contiguous().to(DEV)
     dx = torch.empty_like(xn)
-    call("pm_maxpool3s2_bwd_f32", ptr(gyn), ptr(idx), 1, 6, 6, 2, ptr(dx), stream())
+    call("pm_maxpool3s2_bwd_f32", ptr(gyn), ptr(idx), 1, 6, 6, 4, ptr(dx), stream())
     assert torch.equal(yn.permute(0, 3, 1, 2).cpu(), y.detach())
     assert torch.equal(dx.permute(0, 3, 1, 2).cpu(), x.grad)
