@@ -118,6 +118,8 @@ int pm_conv_wgrad_f32(const pm_conv_t* p, const float* x, const float* dy, float
  * sum / sum-of-squares of the fp32 accumulators into stats[2*K] (doubles) for BatchNorm. */
 int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, pm_stream_t s);
 int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, pm_stream_t s);
+/* NB: the bf16 wgrad ACCUMULATES into dw (fp32 red.add over pixel splits): the caller zeroes dw (the engine clears the whole
+ * flat gradient buffer once per step). */
 int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, void* ws, pm_stream_t s);
 
 /* BatchNorm2d (training) -- F.batch_norm, models.py:261,264,382 ; P = B*H*W rows of C channels.
@@ -132,6 +134,14 @@ int pm_bn_apply_f32(const float* x, const float* mean, const float* invstd, cons
                     const float* residual, int relu, size_t P, int C, float* y, pm_stream_t s);
 int pm_bn_apply_bf16(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                      const void* residual, int relu, size_t P, int C, void* y, pm_stream_t s);
+/* fused finalize + apply (training): mean/invstd are derived from `stats` inside the kernel (one launch instead of two);
+ * block 0 also stores mean/invstd (needed by the backward pass) and updates the running statistics. */
+int pm_bn_fwd_fused_f32(const float* x, const double* stats, size_t P, int C, float eps, float momentum,
+                        const float* gamma, const float* beta, const float* residual, int relu, float* y, float* mean,
+                        float* invstd, float* running_mean, float* running_var, pm_stream_t s);
+int pm_bn_fwd_fused_bf16(const void* x, const double* stats, size_t P, int C, float eps, float momentum,
+                         const float* gamma, const float* beta, const void* residual, int relu, void* y, float* mean,
+                         float* invstd, float* running_mean, float* running_var, pm_stream_t s);
 /* backward: g = dy * (y_out > 0 if relu_mask) ; sums[0..C) = sum g , sums[C..2C) = sum g*xhat (doubles, zeroed by caller).
  * If g_out != NULL the masked gradient is also written (used for the identity branch). */
 int pm_bn_bwd_reduce_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
@@ -180,6 +190,19 @@ int pm_kcrs_to_krsc_f32(const float* w, int K, int C, int R, int S, float* out, 
 int pm_krsc_to_kcrs_f32(const float* w, int K, int C, int R, int S, float* out, pm_stream_t s);
 int pm_krsc_to_bf16_fwd_dgrad(const float* w, int K, int C, int R, int S, int Cpad, void* w_fwd, void* w_dgrad,
                               pm_stream_t s);
+/* the same conversion for a whole model in ONE launch: `table` is a DEVICE array of n entries */
+typedef struct {
+  const float* w;   /* fp32 master  [K][RS][C]            */
+  void* w_fwd;      /* bf16         [K][RS][Cpad]         */
+  void* w_dgrad;    /* bf16         [C][RS][K]  or NULL   */
+  int K, C, RS, Cpad;
+} pm_wcvt_t;
+/* max_tiles = max over entries of RS * ceil(K/32) * ceil(Cpad/32) (grid.x; smaller entries exit early) */
+int pm_krsc_to_bf16_batched(const pm_wcvt_t* table, int n, int max_tiles, pm_stream_t s);
+/* stem im2col for the bf16 path: x NCHW fp32 [B,Cin,H,W] -> [B,Ho,Wo,Kpad] bf16 with k = (r*S+s)*Cin + c (zeros for
+ * k >= R*S*Cin), so that the 7x7/stride-2 stem becomes a dense 1x1 problem for the TMA-fed tensor-core kernels */
+int pm_im2col_stem_bf16(const float* x, int B, int Cin, int H, int W, int R, int stride, int pad, int Kpad, void* out,
+                        pm_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,13 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("B", "H", "W", "C", "K", "R", "S", "stride", "pad", "Ho", "Wo")]
 
 
+class WCvt(ctypes.Structure):
+    """pm_wcvt_t"""
+
+    _fields_ = [("w", ctypes.c_void_p), ("w_fwd", ctypes.c_void_p), ("w_dgrad", ctypes.c_void_p), ("K", ctypes.c_int),
+                ("C", ctypes.c_int), ("RS", ctypes.c_int), ("Cpad", ctypes.c_int)]
+
+
 _SCALARS = {
     "int": ctypes.c_int,
     "size_t": ctypes.c_size_t,
@@ -104,7 +111,7 @@ def stream():
 
 # kernels launched per entry point when it is not exactly one (used for the gpu_launches claim in bench.py)
 KERNELS_PER_CALL = {
-    "pm_conv_wgrad_f32": 2, "pm_bn_bwd_apply_f32": 2, "pm_bn_bwd_apply_bf16": 2, "pm_linear_ce_f32": 2,
+    "pm_conv_wgrad_f32": 2, "pm_linear_ce_f32": 2,
     "pm_spdz_combine_matmul_i64": 1,
 }
 launch_counter = 0

@@ -137,27 +137,59 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double P, i
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BT)
+// FUSED = true: mean / invstd are derived from the batch statistics here (replaces bn_finalize + bn_apply).
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(BT, 3)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                const double* __restrict__ stats, double Pd, float eps, float momentum, float* __restrict__ mean_out,
+                float* __restrict__ invstd_out, float* __restrict__ rm, float* __restrict__ rv,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ res, int relu,
                 size_t P, int C, T* __restrict__ y) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 4;
+  constexpr int U = 2;
   const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
   const int c = v * V;
-  float mu[V], is[V], ga[V], be[V];
+  float mu[V], sc[V], be[V];  // y = (x - mu) * sc + be   with sc = invstd * gamma
 #pragma unroll
-  for (int k = 0; k < V; ++k) { mu[k] = mean[c + k]; is[k] = invstd[c + k]; ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+  for (int k = 0; k < V; ++k) {
+    float is;
+    if (FUSED) {
+      const double m = stats[c + k] / Pd;
+      double var = stats[C + c + k] / Pd - m * m;
+      if (var < 0.0) var = 0.0;
+      mu[k] = (float)m;
+      is = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0 && r0 == 0) {
+        mean_out[c + k] = mu[k];
+        invstd_out[c + k] = is;
+        if (rm) {
+          const double unbiased = Pd > 1.0 ? var * Pd / (Pd - 1.0) : var;
+          rm[c + k] = (float)((1.0 - momentum) * (double)rm[c + k] + momentum * m);
+          rv[c + k] = (float)((1.0 - momentum) * (double)rv[c + k] + momentum * unbiased);
+        }
+      }
+    } else {
+      mu[k] = mean[c + k];
+      is = invstd[c + k];
+    }
+    if (sizeof(T) == 4) sc[k] = is;  // parity mode keeps the (x-mean)*invstd*gamma+beta evaluation order
+    else sc[k] = is * gamma[c + k];
+    be[k] = beta[c + k];
+  }
+  float ga[V];
+  if (sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) ga[k] = gamma[c + k];
+  }
   const size_t stride = (size_t)gridDim.x * rpb;
   for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
-    float xv[U][V], rv[U][V];
+    float xv[U][V], rvv[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t r = row + u * stride;
       if (r < P) {
         Vec<T>::load(x + r * C + c, xv[u]);
-        if (res) Vec<T>::load(res + r * C + c, rv[u]);
+        if (res) Vec<T>::load(res + r * C + c, rvv[u]);
       }
     }
 #pragma unroll
@@ -166,8 +198,10 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const f
       if (r < P) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          float t = (xv[u][k] - mu[k]) * is[k] * ga[k] + be[k];
-          if (res) t += rv[u][k];
+          float t;
+          if (sizeof(T) == 4) t = (xv[u][k] - mu[k]) * sc[k] * ga[k] + be[k];
+          else t = (xv[u][k] - mu[k]) * sc[k] + be[k];
+          if (res) t += rvv[u][k];
           if (relu) t = t > 0.f ? t : 0.f;
           xv[u][k] = t;
         }
@@ -178,20 +212,27 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const f
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BT)
+__global__ void __launch_bounds__(BT, sizeof(T) == 4 ? 1 : 3)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const T* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                    const double* __restrict__ sums, double invP, size_t P, int C, T* __restrict__ dx) {
+                    const double* __restrict__ sums, double invP, size_t P, int C, T* __restrict__ dx,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = sizeof(T) == 4 ? 2 : 4;
+  constexpr int U = 2;
+  using par_t = typename std::conditional<sizeof(T) == 4, double, float>::type;
   const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
   const int c = v * V;
-  float mu[V], is[V], ga[V];
-  double mgd[V], mgxd[V];
+  float mu[V], is[V], gi[V];  // gi = gamma * invstd
+  par_t mg[V], mgx[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    mu[k] = mean[c + k]; is[k] = invstd[c + k]; ga[k] = gamma[c + k];
-    mgd[k] = sums[c + k] * invP; mgxd[k] = sums[C + c + k] * invP;
+    mu[k] = mean[c + k]; is[k] = invstd[c + k]; gi[k] = gamma[c + k];
+    mg[k] = (par_t)(sums[c + k] * invP); mgx[k] = (par_t)(sums[C + c + k] * invP);
+    if (dgamma && blockIdx.x == 0 && r0 == 0) {
+      dbeta[c + k] = (float)sums[c + k];
+      dgamma[c + k] = (float)sums[C + c + k];
+    }
+    if (sizeof(T) != 4) gi[k] *= is[k];
   }
   const size_t stride = (size_t)gridDim.x * rpb;
   for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
@@ -218,24 +259,16 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
             // per-channel common mode of dy can exceed its fluctuation by 1e3-1e4, so fp32 here would cost 1e-4 relative.
             const double isd = (double)is[k];
             const double xhat = ((double)xv[u][k] - (double)mu[k]) * isd;
-            g[u][k] = (float)((double)ga[k] * isd * ((double)gg - mgd[k] - xhat * mgxd[k]));
+            g[u][k] = (float)((double)gi[k] * isd * ((double)gg - (double)mg[k] - xhat * (double)mgx[k]));
           } else {
             const float xhat = (xv[u][k] - mu[k]) * is[k];
-            g[u][k] = ga[k] * is[k] * (gg - (float)mgd[k] - xhat * (float)mgxd[k]);
+            g[u][k] = gi[k] * (gg - (float)mg[k] - xhat * (float)mgx[k]);
           }
         }
         Vec<T>::store(dx + r * C + c, g[u]);
       }
     }
   }
-}
-
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  dbeta[c] = (float)sums[c];
-  dgamma[c] = (float)sums[C + c];
 }
 
 // ---- max pool 3x3 s2 p1 (first max wins, like ATen's CPU kernel); one thread = one 16-byte channel group
@@ -370,7 +403,17 @@ int bn_apply_t(const T* x, const float* mean, const float* invstd, const float* 
                int relu, size_t P, int C, T* y, pm_stream_t s) {
   PM_CHECK_ARG(x && mean && invstd && gamma && beta && y && C % Vec<T>::N == 0);
   PM_CHECK_ARG(chan_ok<T>(C));
-  bn_apply_kernel<T><<<row_grid<T>(P, C, 4), BT, 0, S(s)>>>(x, mean, invstd, gamma, beta, res, relu, P, C, y);
+  bn_apply_kernel<T, false><<<row_grid<T>(P, C, 2), BT, 0, S(s)>>>(x, mean, invstd, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr,
+                                                                   nullptr, gamma, beta, res, relu, P, C, y);
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int bn_fwd_fused_t(const T* x, const double* stats, size_t P, int C, float eps, float momentum, const float* gamma,
+                   const float* beta, const T* res, int relu, T* y, float* mean, float* invstd, float* rm, float* rv,
+                   pm_stream_t s) {
+  PM_CHECK_ARG(x && stats && gamma && beta && y && mean && invstd && P > 0 && chan_ok<T>(C) && ((rm == nullptr) == (rv == nullptr)));
+  bn_apply_kernel<T, true><<<row_grid<T>(P, C, 2), BT, 0, S(s)>>>(x, nullptr, nullptr, stats, (double)P, eps, momentum, mean, invstd,
+                                                                  rm, rv, gamma, beta, res, relu, P, C, y);
   PM_LAUNCH_OK();
 }
 template <typename T>
@@ -384,9 +427,9 @@ template <typename T>
 int bn_bwd_apply_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma,
                    const double* sums, size_t P, int C, T* dx, float* dgamma, float* dbeta, pm_stream_t s) {
   PM_CHECK_ARG(dy && x && mean && invstd && gamma && sums && dx && C % Vec<T>::N == 0);
-  PM_CHECK_ARG(chan_ok<T>(C));
-  bn_bwd_apply_kernel<T><<<row_grid<T>(P, C, 4), BT, 0, S(s)>>>(dy, y_out, x, mean, invstd, gamma, sums, 1.0 / (double)P, P, C, dx);
-  if (dgamma && dbeta) bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, S(s)>>>(sums, C, dgamma, dbeta);
+  PM_CHECK_ARG(chan_ok<T>(C) && ((dgamma == nullptr) == (dbeta == nullptr)));
+  bn_bwd_apply_kernel<T><<<row_grid<T>(P, C, 2), BT, 0, S(s)>>>(dy, y_out, x, mean, invstd, gamma, sums, 1.0 / (double)P, P, C, dx,
+                                                                dgamma, dbeta);
   PM_LAUNCH_OK();
 }
 template <typename T>
@@ -432,6 +475,17 @@ int pm_bn_apply_f32(const float* x, const float* mean, const float* invstd, cons
 int pm_bn_apply_bf16(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                      const void* residual, int relu, size_t P, int C, void* y, pm_stream_t s) {
   return bn_apply_t<bf16>((const bf16*)x, mean, invstd, gamma, beta, (const bf16*)residual, relu, P, C, (bf16*)y, s);
+}
+int pm_bn_fwd_fused_f32(const float* x, const double* stats, size_t P, int C, float eps, float momentum,
+                        const float* gamma, const float* beta, const float* residual, int relu, float* y, float* mean,
+                        float* invstd, float* running_mean, float* running_var, pm_stream_t s) {
+  return bn_fwd_fused_t<float>(x, stats, P, C, eps, momentum, gamma, beta, residual, relu, y, mean, invstd, running_mean, running_var, s);
+}
+int pm_bn_fwd_fused_bf16(const void* x, const double* stats, size_t P, int C, float eps, float momentum,
+                         const float* gamma, const float* beta, const void* residual, int relu, void* y, float* mean,
+                         float* invstd, float* running_mean, float* running_var, pm_stream_t s) {
+  return bn_fwd_fused_t<bf16>((const bf16*)x, stats, P, C, eps, momentum, gamma, beta, (const bf16*)residual, relu, (bf16*)y, mean,
+                              invstd, running_mean, running_var, s);
 }
 int pm_bn_bwd_reduce_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
                          size_t P, int C, double* sums, float* g_out, pm_stream_t s) {

@@ -449,7 +449,7 @@ int tc_wgrad_splits(const pm_conv_t* p, int BN) {
 }  // namespace
 
 // TMA-fed variants (conv_tma.cu): 0 = launched, 1 = shape not eligible (use the cp.async variant), 2 = error
-int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, cudaStream_t st);
+int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, cudaStream_t st);
 int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
 int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
 static bool use_tma() {
@@ -461,13 +461,13 @@ extern "C" {
 
 int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && x && w && y);
-  PM_CHECK_ARG(stats == nullptr);  // fused BN statistics: not wired yet (use pm_bn_stats_bf16)
   if (use_tma()) {
-    const int r = pm_tma_conv_fwd(p, x, w, y, S(s));
+    const int r = pm_tma_conv_fwd(p, x, w, y, stats, S(s));  // statistics fused into the epilogue
     if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv fwd setup failed");
     if (r == 0) PM_LAUNCH_OK();
   }
   if (launch_conv<0>(p, x, w, y, 0, S(s))) return PM_ECUDA;
+  if (stats) return pm_bn_stats_bf16(y, (size_t)p->B * p->Ho * p->Wo, p->K, stats, s);  // cp.async variant: separate pass
   PM_LAUNCH_OK();
 }
 
@@ -492,7 +492,6 @@ int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float*
   }
   const int M = p->B * p->Ho * p->Wo;
   const int Kg = p->R * p->S * p->C;
-  PM_CUDA(cudaMemsetAsync(dw, 0, (size_t)p->K * Kg * sizeof(float), S(s)));
   if (p->K % 128 == 0) {
     const int splits = tc_wgrad_splits(p, 128);
     int pps = ((M + splits - 1) / splits + 127) / 128 * 128;

@@ -10,6 +10,7 @@
 //   warps 2-5: epilogue (tcgen05.ld -> registers -> bf16 / fp32 global).
 #include "common.cuh"
 #include <cuda.h>
+#include <algorithm>
 
 namespace tma {
 
@@ -100,119 +101,179 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 }
 
 // ------------------------------------------------------------------------------------------------ fwd / dgrad(stride 1)
+// PERSISTENT: one CTA per SM loops over output tiles (n fastest, so co-scheduled CTAs share the activation tile in L2).
 // D[128 pixels, BN] ; A = im2col(src) via tmA ; B = dense [N][Ktot] via tmB.  FLIP: dgrad (taps mirrored).
+// Two TMEM accumulator stages: the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
+// Barriers: full/empty[STAGES] (TMA <-> MMA), tmem_full/tmem_empty[2] (MMA <-> epilogue).
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int BN, int STAGES, bool FLIP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, bf16* __restrict__ dst,
-                int accumulate) {
+                int accumulate, double* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 128 or 256)
   const uint32_t s_base = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, accum_bar = full0 + 16 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES;
+  const uint32_t tfull0 = full0 + 16 * STAGES, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* scratch_all = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // 4 x [32][33] transposition scratch
+  float* cta_stats = scratch_all + 4 * 32 * 33;                         // [2][N] per-CTA partial statistics
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  // geometry in "output pixel" space of this GEMM: fwd -> (Ho,Wo), channels C ; dgrad(s=1) -> (H,W), channels K
   const int OH = FLIP ? p.H : p.Ho, OW = FLIP ? p.W : p.Wo;
   const int CR = FLIP ? p.K : p.C;
   const int N = FLIP ? p.C : p.K;
   const int M = p.B * OH * OW;
   const int cblocks = CR / 64;
   const int nkb = p.R * p.S * cblocks;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int ntn = N / BN;
+  const int ntiles = ((M + 127) / 128) * ntn;
+  const bool do_stats = !FLIP && stats != nullptr;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (do_stats)
+    for (int i = tid; i < 2 * N; i += NTHREADS) cta_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (tid == 0) {
     // ------------------------------------------------------------ TMA producer
-    const int nb = m0 / (OH * OW);
-    const int rem = m0 - nb * OH * OW;
-    const int py = rem / OW, px = rem - py * OW;
-    // base pixel of the im2col window: fwd: out*stride - pad ; dgrad(s=1): out + pad - (R-1)
-    const int bw = FLIP ? px + p.pad - (p.S - 1) : px * p.stride - p.pad;
-    const int bh = FLIP ? py + p.pad - (p.R - 1) : py * p.stride - p.pad;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-      const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
-      const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * 64;
-      const int r = tap / p.S, sx = tap - r * p.S;
-      mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-      tma_load_im2col(a_tile, &tmA, full0 + 8 * s, c0, bw, bh, nb, (uint16_t)(FLIP ? p.S - 1 - sx : sx),
-                      (uint16_t)(FLIP ? p.R - 1 - r : r));
-      tma_load_2d(b_tile, &tmB, full0 + 8 * s, kb * 64, n0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * BN;
+      const int nb = m0 / (OH * OW);
+      const int rem = m0 - nb * OH * OW;
+      const int py = rem / OW, px = rem - py * OW;
+      const int bw = FLIP ? px + p.pad - (p.S - 1) : px * p.stride - p.pad;
+      const int bh = FLIP ? py + p.pad - (p.R - 1) : py * p.stride - p.pad;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty0 + 8 * s, ((it / STAGES) & 1) ^ 1);
+        const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * 64;
+        const int r = tap / p.S, sx = tap - r * p.S;
+        mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+        tma_load_im2col(a_tile, &tmA, full0 + 8 * s, c0, bw, bh, nb, (uint16_t)(FLIP ? p.S - 1 - sx : sx),
+                        (uint16_t)(FLIP ? p.R - 1 - r : r));
+        tma_load_2d(b_tile, &tmB, full0 + 8 * s, kb * 64, n0);
+      }
     }
   } else if (tid == 32) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int as = lt & 1;
+      mbar_wait(tempty0 + 8 * as, ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
-      const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
-      const uint64_t adesc = make_desc(a_tile, 16, 1024), bdesc = make_desc(b_tile, 16, 1024);
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+        const uint64_t adesc = make_desc(a_tile, 16, 1024), bdesc = make_desc(b_tile, 16, 1024);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-      umma_commit(empty0 + 8 * s);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull0 + 8 * as);
     }
-    umma_commit(accum_bar);
   } else if (warp >= 2) {
-    // ------------------------------------------------------------ epilogue
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int row = m0 + quad * 32 + (tid & 31);
-    bf16* out = dst + (size_t)row * N + n0;
+    // ------------------------------------------------------------ epilogue (4 warps)
+    const int quad = warp & 3, lane = tid & 31;
+    float* scratch = scratch_all + quad * (32 * 33);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int as = lt & 1;
+      const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * BN;
+      mbar_wait(tfull0 + 8 * as, (lt >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      bf16* out = dst + (size_t)row * N + n0;
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
-      if (row < M) {
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + as * BN + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
+        if (do_stats) {
+          // BatchNorm batch statistics fused here: per-channel sum / sum of squares of the bf16-rounded outputs (what a
+          // separate bn_stats pass would read back from HBM).  Each warp transposes its 32x32 chunk through smem, every
+          // lane reduces one channel and adds it to the CTA-wide partial sums; one double atomic per channel per CTA at
+          // the end of the kernel.
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
+          for (int e = 0; e < 32; ++e)
+            scratch[lane * 33 + e] = row < M ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[e]))) : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
-          uint4* o = reinterpret_cast<uint4*>(out + cc * 32 + q * 8);
-          if (accumulate) {
-            const uint4 old = *o;
-            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __bfloat1622float2(oh[e]);
-              f[2 * e] += t.x; f[2 * e + 1] += t.y;
-            }
+          for (int r = 0; r < 32; ++r) {
+            const float t = scratch[r * 33 + lane];
+            s1 += t;
+            s2 = fmaf(t, t, s2);
           }
-          uint4 pk;
-          __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+          atomicAdd(&cta_stats[n0 + cc * 32 + lane], s1);
+          atomicAdd(&cta_stats[N + n0 + cc * 32 + lane], s2);
+          __syncwarp();
+        }
+        if (row < M) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-          *o = pk;
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            uint4* o = reinterpret_cast<uint4*>(out + cc * 32 + q * 8);
+            if (accumulate) {
+              const uint4 old = *o;
+              const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __bfloat1622float2(oh[e]);
+                f[2 * e] += t.x; f[2 * e + 1] += t.y;
+              }
+            }
+            uint4 pk;
+            __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            *o = pk;
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * as);  // this warp is done reading the accumulator stage
     }
-    tc_fence_before();
   }
   __syncthreads();
+  if (do_stats)
+    for (int i = tid; i < 2 * N; i += NTHREADS) {
+      const float v = cta_stats[i];
+      if (v != 0.f) atomicAdd(stats + i, (double)v);
+    }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -497,7 +558,7 @@ static bool set_smem(Kern k, int bytes) {
 }
 
 constexpr int FSTAGES = 5;
-constexpr int smem_conv(int BN, int stages) { return stages * (TILE_BYTES + BN * 128) + 1024 + 256; }
+constexpr int smem_conv(int BN, int stages) { return stages * (TILE_BYTES + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4 + 2 * 512 * 4; }
 constexpr int smem_wg(int BN, int stages) { return stages * (2 * TILE_BYTES + (BN / 64) * TILE_BYTES) + 1024 + 256; }
 
 static Geo geo(const pm_conv_t* p) { return Geo{p->B, p->H, p->W, p->C, p->K, p->R, p->S, p->stride, p->pad, p->Ho, p->Wo}; }
@@ -506,7 +567,7 @@ static Geo geo(const pm_conv_t* p) { return Geo{p->B, p->H, p->W, p->C, p->K, p-
 
 // Entry points used by conv_tc.cu's dispatcher.  Return 0 on success, 1 if this shape is not eligible
 // (caller falls back to the cp.async variant), 2 on a CUDA/driver error.
-int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, cudaStream_t st) {
+int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, cudaStream_t st) {
   using namespace tma;
   if (p->C % 64 != 0 || p->K % 64 != 0 || !load_driver()) return 1;
   CUtensorMap tmA, tmB;
@@ -516,13 +577,13 @@ int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, c
   if (p->K % 128 == 0) {
     if (!map_dense(&tmB, w, p->K, Ktot, 128)) return 2;
     if (!set_smem(conv_tma_kernel<128, FSTAGES, false>, smem_conv(128, FSTAGES))) return 2;
-    dim3 grid((M + 127) / 128, p->K / 128);
-    conv_tma_kernel<128, FSTAGES, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0);
+    dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 128)));
+    conv_tma_kernel<128, FSTAGES, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
   } else {
     if (!map_dense(&tmB, w, p->K, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, FSTAGES, false>, smem_conv(64, FSTAGES))) return 2;
-    dim3 grid((M + 127) / 128, p->K / 64);
-    conv_tma_kernel<64, FSTAGES, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0);
+    dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 64)));
+    conv_tma_kernel<64, FSTAGES, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
   }
   return 0;
 }
@@ -560,13 +621,13 @@ int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* 
   if (p->C % 128 == 0) {
     if (!map_dense(&tmB, wt, p->C, Ktot, 128)) return 2;
     if (!set_smem(conv_tma_kernel<128, FSTAGES, true>, smem_conv(128, FSTAGES))) return 2;
-    dim3 grid((M + 127) / 128, p->C / 128);
-    conv_tma_kernel<128, FSTAGES, true><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate);
+    dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 128)));
+    conv_tma_kernel<128, FSTAGES, true><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
   } else {
     if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, FSTAGES, true>, smem_conv(64, FSTAGES))) return 2;
-    dim3 grid((M + 127) / 128, p->C / 64);
-    conv_tma_kernel<64, FSTAGES, true><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate);
+    dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 64)));
+    conv_tma_kernel<64, FSTAGES, true><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
   }
   return 0;
 }
@@ -579,7 +640,6 @@ int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* 
   const int Kg = p->R * p->S * p->C;
   if (!map_im2col(&tmA, x, p->B, p->H, p->W, p->C, -p->pad, -p->pad, p->pad - (p->S - 1), p->pad - (p->R - 1), p->stride)) return 2;
   if (!map_dense(&tmB, dy, (uint64_t)M, p->K, 128)) return 2;
-  if (cudaMemsetAsync(dw, 0, (size_t)p->K * Kg * sizeof(float), st) != cudaSuccess) return 2;
   const int BN = p->K % 128 == 0 ? 128 : 64;
   const long tiles = ((Kg + 127) / 128) * (long)(p->K / BN);
   long splits = (2L * pm_num_sms() + tiles - 1) / tiles;

@@ -155,6 +155,90 @@ __global__ void krsc_to_bf16_kernel(const float* __restrict__ w, int K, int C, i
   }
 }
 
+// Batched weight conversion, one launch for the whole model.  blockIdx.y = conv; blockIdx.x enumerates 32x32 (k, c) tiles
+// of every filter tap (early exit past the conv's own tile count).  Each tile is read once from the fp32 master
+// (coalesced along c), written to the forward operand [K][RS][Cpad] (coalesced along c) and, transposed through shared
+// memory, to the dgrad operand [C][RS][K] (coalesced along k).
+__global__ void __launch_bounds__(256)
+krsc_to_bf16_batched_kernel(const pm_wcvt_t* __restrict__ table) {
+  __shared__ float tile[32][33];
+  const pm_wcvt_t e = table[blockIdx.y];
+  const int tk = (e.K + 31) / 32, tc = (e.Cpad + 31) / 32;
+  const int ntiles = e.RS * tk * tc;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int rs = blockIdx.x / (tk * tc);
+  const int rem = blockIdx.x - rs * tk * tc;
+  const int k0 = (rem / tc) * 32, c0 = (rem % tc) * 32;
+  __nv_bfloat16* wf = (__nv_bfloat16*)e.w_fwd;
+  __nv_bfloat16* wd = (__nv_bfloat16*)e.w_dgrad;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (k < e.K && c < e.C) v = e.w[((size_t)k * e.RS + rs) * e.C + c];
+    tile[i][tx] = v;
+    if (k < e.K && c < e.Cpad) wf[((size_t)k * e.RS + rs) * e.Cpad + c] = __float2bfloat16_rn(v);
+  }
+  if (wd) {
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, k = k0 + tx;
+      if (c < e.C && k < e.K) wd[((size_t)c * e.RS + rs) * e.K + k] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
+// one block per (image, output row): the R input rows it needs are staged in shared memory (coalesced), then every
+// thread assembles 16-byte chunks (8 consecutive k = (r*S+s)*Cin + c) of the im2col rows.  blockDim = 10 pixels x
+// (Kpad/8) chunks: a thread always produces the same chunk index, so its 8 smem offsets live in registers.
+__global__ void __launch_bounds__(256)
+im2col_stem_kernel(const float* __restrict__ x, int Cin, int H, int W, int R, int stride, int pad, int Ho, int Wo, int Kpad,
+                   __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float srow[];  // [Cin*R][W + 2*pad]
+  const int WP = W + 2 * pad;
+  const int oh = blockIdx.x, b = blockIdx.y;
+  const int ih0 = oh * stride - pad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int cr = warp; cr < Cin * R; cr += nwarps) {
+    const int c = cr / R, r = cr - c * R;
+    const int ih = ih0 + r;
+    const bool row_ok = ih >= 0 && ih < H;
+    const float* src = x + (((size_t)b * Cin + c) * H + (row_ok ? ih : 0)) * W;
+    for (int wp = lane; wp < WP; wp += 32) {
+      const int iw = wp - pad;
+      srow[cr * WP + wp] = (row_ok && iw >= 0 && iw < W) ? src[iw] : 0.f;
+    }
+  }
+  const int chunks = Kpad / 8;
+  const int Ktrue = R * R * Cin;
+  const int j = threadIdx.x % chunks, p0 = threadIdx.x / chunks, ppb = blockDim.x / chunks;
+  int off[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = j * 8 + e;
+    off[e] = -1;
+    if (k < Ktrue) {
+      const int c = k % Cin, rs = k / Cin;
+      const int s_ = rs % R, r = rs / R;
+      off[e] = (c * R + r) * WP + s_;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* orow = out + ((size_t)b * Ho + oh) * Wo * Kpad;
+  if (p0 < ppb) {
+    for (int ow = p0; ow < Wo; ow += ppb) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? srow[off[e] + ow * stride] : 0.f;
+      uint4 pk;
+      __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      *reinterpret_cast<uint4*>(orow + ((size_t)ow * chunks + j) * 8) = pk;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,6 +306,27 @@ int pm_krsc_to_bf16_fwd_dgrad(const float* w, int K, int C, int R, int S_, int C
   const size_t total = (size_t)K * R * S_ * Cpad;
   krsc_to_bf16_kernel<<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(w, K, C, R * S_, Cpad, (__nv_bfloat16*)w_fwd,
                                                                     (__nv_bfloat16*)w_dgrad);
+  PM_LAUNCH_OK();
+}
+
+int pm_krsc_to_bf16_batched(const pm_wcvt_t* table, int n, int max_tiles, pm_stream_t s) {
+  PM_CHECK_ARG(table && n > 0 && n <= 65535 && max_tiles > 0);
+  dim3 grid(max_tiles, n);  // max_tiles = max over entries of RS * ceil(K/32) * ceil(Cpad/32)
+  krsc_to_bf16_batched_kernel<<<grid, 256, 0, S(s)>>>(table);
+  PM_LAUNCH_OK();
+}
+
+int pm_im2col_stem_bf16(const float* x, int B, int Cin, int H, int W, int R, int stride, int pad, int Kpad, void* out,
+                        pm_stream_t s) {
+  PM_CHECK_ARG(x && out && B > 0 && B <= 65535 && Kpad % 8 == 0 && Kpad >= R * R * Cin);
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - R) / stride + 1;
+  const size_t smem = (size_t)Cin * R * (W + 2 * pad) * sizeof(float);
+  PM_CHECK_ARG(smem <= 48 * 1024);
+  dim3 grid(Ho, B);
+  const int chunks = Kpad / 8;
+  PM_CHECK_ARG(chunks <= 256);
+  const int threads = (256 / chunks) * chunks;  // whole pixels per pass
+  im2col_stem_kernel<<<grid, threads, smem, S(s)>>>(x, Cin, H, W, R, stride, pad, Ho, Wo, Kpad, (__nv_bfloat16*)out);
   PM_LAUNCH_OK();
 }
 

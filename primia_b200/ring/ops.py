@@ -111,6 +111,7 @@ def mask_wt(w2d, b):
 
 
 def open_add(local, peer):
+    """out = local + peer ; ``peer`` may live on another GPU (peer-mapped pointer, NVLink load)."""
     local, peer = _chk(local), _chk(peer)
     out = torch.empty_like(local)
     with torch.cuda.device(local.device):

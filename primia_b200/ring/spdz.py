@@ -148,14 +148,35 @@ def spdz_compute(party: Party, j: int, delta, epsilon, op: str):
     return ops.combine_mul(j, delta, epsilon, a, b, c)
 
 
+_PEER_READY = set()
+
+
+def _ensure_peer(dev_a: torch.device, dev_b: torch.device) -> bool:
+    """Make dev_b's memory dereferenceable from kernels running on dev_a (cudaDeviceEnablePeerAccess, which PyTorch
+    performs on the first peer copy between the pair)."""
+    key = (dev_a.index, dev_b.index)
+    if key in _PEER_READY:
+        return True
+    if not torch.cuda.can_device_access_peer(dev_a.index, dev_b.index):
+        return False
+    torch.zeros(1, device=dev_b).to(dev_a)  # triggers peer-access enablement for the pair
+    torch.zeros(1, device=dev_a).to(dev_b)
+    torch.cuda.synchronize(dev_a)
+    torch.cuda.synchronize(dev_b)
+    _PEER_READY.add(key)
+    return True
+
+
 def open_shares(parties, shares):
     """delta = sum(shares) made available on every party (spdz.py:162-163), via peer reads."""
     outs = []
     for j, p in enumerate(parties):
         peer = shares[1 - j]
         if peer.device != p.device:
-            # symmetric NVLink exchange: read the peer's share through its device pointer
-            if not torch.cuda.can_device_access_peer(p.device.index, peer.device.index):
+            # symmetric NVLink exchange: the add kernel on party j's GPU loads the peer's share through its peer-mapped
+            # device pointer; the producer's stream must have finished writing it first
+            torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(peer.device))
+            if not _ensure_peer(p.device, peer.device):
                 peer = peer.to(p.device)  # staged copy when no P2P mapping exists
         outs.append(ops.open_add(shares[j], peer))
     return outs

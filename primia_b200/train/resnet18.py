@@ -61,6 +61,7 @@ class ResNet18Engine:
         self.training = True
         self._prof = None
         self._graph = None
+        self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -70,10 +71,12 @@ class ResNet18Engine:
     # ------------------------------------------------------------------ graph
     def _build_graph(self):
         B, S = self.B, self.size
-        self.cin_pad = self.cin if self.mode == "f32" else 8  # bf16 path pads the stem channels to 16 B per pixel
         convs, bns = OrderedDict(), OrderedDict()
-        c1 = _Conv("conv1", B, S, S, self.cin_pad, 64, 7, 2, 3)
+        c1 = _Conv("conv1", B, S, S, self.cin, 64, 7, 2, 3)
         convs["conv1"] = c1
+        # bf16 mode runs the stem as a dense 1x1 problem over a bf16 im2col tensor [B,Ho,Wo,KPAD] (k = (r*7+s)*Cin + c)
+        self.stem_kpad = (7 * 7 * self.cin + 63) // 64 * 64
+        self.c1_gemm = _Conv("conv1", B, c1.Ho, c1.Wo, self.stem_kpad, 64, 1, 1, 0)
         bns["bn1"] = 64
         H = (c1.Ho + 2 - 3) // 2 + 1  # maxpool 3,2,1
         self.pool_in, self.pool_out = c1.Ho, H
@@ -139,7 +142,11 @@ class ResNet18Engine:
         B, adt = self.B, self.adt
         A = lambda *s: torch.empty(s, dtype=adt, device=dev)
         c1 = self.convs["conv1"]
-        self.x0 = A(B, self.size, self.size, self.cin_pad)
+        if self.mode == "f32":
+            self.x0 = A(B, self.size, self.size, self.cin)
+        else:
+            self.x0 = A(B, c1.Ho, c1.Wo, self.stem_kpad)  # im2col of the input
+            self.dw_stem = torch.zeros((64, self.stem_kpad), dtype=f32, device=dev)
         self.act = {}   # forward tensors
         self.grad = {}  # backward tensors
         self.act["conv1"] = A(B, c1.Ho, c1.Wo, 64)
@@ -169,10 +176,24 @@ class ResNet18Engine:
             ws_bytes = max(ws_bytes, int(self._lib_size("pm_conv_wgrad_ws_bytes", c)))
         self.wgrad_ws = torch.empty(max(ws_bytes, 16) // 4 + 4, dtype=f32, device=dev)
         if self.mode == "bf16":
+            from .._lib import WCvt
+
             self.wbf = {}
+            entries = []
             for name, c in self.convs.items():
-                self.wbf[name] = (torch.empty(c.wshape, dtype=torch.bfloat16, device=dev),
-                                  torch.empty((c.C, c.R, c.R, c.K), dtype=torch.bfloat16, device=dev))
+                if name == "conv1":
+                    wf = torch.empty((64, 1, 1, self.stem_kpad), dtype=torch.bfloat16, device=dev)
+                    self.wbf[name] = (wf, None)
+                    entries.append(WCvt(self.p[name + ".weight"].data_ptr(), wf.data_ptr(), None, 64, 7 * 7 * self.cin, 1, self.stem_kpad))
+                else:
+                    wf = torch.empty(c.wshape, dtype=torch.bfloat16, device=dev)
+                    wd = torch.empty((c.C, c.R, c.R, c.K), dtype=torch.bfloat16, device=dev)
+                    self.wbf[name] = (wf, wd)
+                    entries.append(WCvt(self.p[name + ".weight"].data_ptr(), wf.data_ptr(), wd.data_ptr(), c.K, c.C, c.R * c.R, c.C))
+            arr = (WCvt * len(entries))(*entries)
+            self.wcvt_n = len(entries)
+            self.wcvt_tiles = max(e.RS * ((e.K + 31) // 32) * ((e.Cpad + 31) // 32) for e in entries)
+            self.wcvt_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
 
     def _lib_size(self, fn, conv):
         from .._lib import lib
@@ -196,14 +217,7 @@ class ResNet18Engine:
                 src = sd[name].detach().to(self.device, torch.float32).contiguous()
                 if name.endswith("weight") and src.dim() == 4:
                     K, C, R, S_ = src.shape
-                    dst = self.p[name]
-                    if dst.shape[3] != C:  # padded stem channels (bf16 mode)
-                        tmp = torch.empty((K, R, S_, C), dtype=torch.float32, device=self.device)
-                        call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(tmp), stream())
-                        dst.zero_()
-                        dst[..., :C].copy_(tmp)
-                    else:
-                        call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(dst), stream())
+                    call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(self.p[name]), stream())
                 else:
                     self.p[name].copy_(src.view(shape))
 
@@ -214,9 +228,6 @@ class ResNet18Engine:
                 t = self.p[name]
                 if len(shape) == 4:
                     K, R, S_, C = shape
-                    if C != self._true_cin(name):
-                        t = t[..., : self._true_cin(name)].contiguous()
-                        C = t.shape[3]
                     dst = torch.empty((K, C, R, S_), dtype=torch.float32, device=self.device)
                     call("pm_krsc_to_kcrs_f32", ptr(t.contiguous()), K, C, R, S_, ptr(dst), stream())
                     out[name] = dst
@@ -233,9 +244,6 @@ class ResNet18Engine:
                 ordered[bn + ".num_batches_tracked"] = torch.tensor(self.step_count, dtype=torch.int64)
         return ordered
 
-    def _true_cin(self, name):
-        return self.cin if name == "conv1.weight" else self.offsets[name][2][3]
-
     def grad_dict(self):
         """gradients in the reference layout (KCRS) -- used by the parity tests"""
         out = OrderedDict()
@@ -244,10 +252,8 @@ class ResNet18Engine:
                 t = self.g[name]
                 if t.dim() == 4:
                     K, R, S_, C = t.shape
-                    tc = t[..., : self._true_cin(name)].contiguous()
-                    C = tc.shape[3]
                     dst = torch.empty((K, C, R, S_), dtype=torch.float32, device=self.device)
-                    call("pm_krsc_to_kcrs_f32", ptr(tc), K, C, R, S_, ptr(dst), stream())
+                    call("pm_krsc_to_kcrs_f32", ptr(t), K, C, R, S_, ptr(dst), stream())
                     out[name] = dst
                 else:
                     out[name] = t.clone()
@@ -310,9 +316,11 @@ class ResNet18Engine:
         if self.training:
             if not stats_done:
                 call("pm_bn_stats" + self.sfx, ptr(x), P, C, ptr(st), stream())
-            call("pm_bn_finalize", ptr(st), P, C, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM),
-                 ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".running_mean"]),
+            call("pm_bn_fwd_fused" + self.sfx, ptr(x), ptr(st), P, C, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM),
+                 ptr(self.p[bn + ".weight"]), ptr(self.p[bn + ".bias"]), ptr(residual) if residual is not None else None,
+                 int(relu), ptr(y), ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".running_mean"]),
                  ptr(self.p[bn + ".running_var"]), stream())
+            return
         else:
             # eval: normalise with the running statistics (F.batch_norm(training=False))
             self.bn_mean[bn].copy_(self.p[bn + ".running_mean"])
@@ -339,14 +347,11 @@ class ResNet18Engine:
         if self.mode == "f32":
             call("pm_nchw_to_nhwc_f32", ptr(x_nchw), self.B, self.cin, self.size, self.size, ptr(self.x0), stream())
         else:
-            call("pm_nchw_to_nhwc_f32_bf16", ptr(x_nchw), self.B, self.cin, self.size, self.size, self.cin_pad, ptr(self.x0),
+            call("pm_im2col_stem_bf16", ptr(x_nchw), self.B, self.cin, self.size, self.size, 7, 2, 3, self.stem_kpad, ptr(self.x0),
                  stream())
 
     def refresh_bf16_weights(self):
-        for name, c in self.convs.items():
-            wf, wd = self.wbf[name]
-            call("pm_krsc_to_bf16_fwd_dgrad", ptr(self.p[name + ".weight"]), c.K, c.C, c.R, c.R, c.C, ptr(wf),
-                 ptr(wd) if name != "conv1" else None, stream())
+        call("pm_krsc_to_bf16_batched", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_tiles, stream())
 
     def forward(self, x_nchw=None):
         with torch.cuda.device(self.device):
@@ -357,9 +362,10 @@ class ResNet18Engine:
             if self.mode == "bf16":
                 self.refresh_bf16_weights()
             bn_ids = {bn: i for i, bn in enumerate(self.bns)}
-            fuse = False  # fused conv+BN-statistics epilogue: not wired yet
+            fuse = self.mode == "bf16" and self.training and self.fuse_stats
             c1 = self.convs["conv1"]
-            self._conv_fwd(c1, self.x0, self.act["conv1"], self._stat_slot(bn_ids["bn1"]) if fuse else None)
+            self._conv_fwd(c1 if self.mode == "f32" else self.c1_gemm, self.x0, self.act["conv1"],
+                           self._stat_slot(bn_ids["bn1"]) if fuse else None)
             self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
             call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
                  ptr(self.pool_idx), stream())
@@ -392,6 +398,9 @@ class ResNet18Engine:
         with torch.cuda.device(self.device):
             hard = target.dtype == torch.int64
             target = target.contiguous()
+            if self.mode == "bf16":
+                self.grads.zero_()  # the tensor-core wgrad accumulates (split over pixels) into a cleared buffer
+                self.dw_stem.zero_()
             call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
                  ptr(target) if hard else None, None if hard else ptr(target),
                  ptr(self.class_weights) if self.class_weights is not None else None, self.B, 512, self.ncls,
@@ -431,7 +440,13 @@ class ResNet18Engine:
             call("pm_maxpool3s2_bwd" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
             dc1 = self._gbuf(("dc1",), self.act["conv1"])
             self._bn_bwd("bn1", bn_ids["bn1"], d_a1, self.act["a1"], self.act["conv1"], dc1, c1.P)
-            self._conv_wgrad(c1, self.x0, dc1)
+            if self.mode == "f32":
+                self._conv_wgrad(c1, self.x0, dc1)
+            else:
+                e0 = self._prof_begin()
+                call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
+                self._prof_end(e0)
+                self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
         return self.loss
 
     def optimizer_step(self):
@@ -527,8 +542,6 @@ class ResNet18Engine:
                 w = self.p[name + ".weight"]
                 std = (2.0 / (c.K * c.R * c.R)) ** 0.5
                 w.copy_(torch.randn(w.shape, device=self.device, generator=g) * std)
-                if w.shape[3] != self._true_cin(name + ".weight"):
-                    w[..., self._true_cin(name + ".weight"):].zero_()
             for bn in self.bns:
                 self.p[bn + ".weight"].fill_(1.0)
                 self.p[bn + ".running_var"].fill_(1.0)

@@ -58,11 +58,16 @@ def test_fwd_dgrad_wgrad_bf16(case, no_tma, monkeypatch):
     xd, wd_, dyd = x.to(DEV), w.to(DEV), dy.to(DEV)  # keep device tensors alive across the raw-pointer calls
     # forward
     y = torch.empty(B, Ho, Ho, K, dtype=torch.bfloat16, device=DEV)
-    call("pm_conv_fwd_bf16", ctypes.byref(d), ptr(xd), ptr(wd_), ptr(y), None, stream())
+    stats = torch.zeros(2 * K, dtype=torch.float64, device=DEV)
+    call("pm_conv_fwd_bf16", ctypes.byref(d), ptr(xd), ptr(wd_), ptr(y), ptr(stats), stream())
     torch.cuda.synchronize()
     assert rel(y.float().permute(0, 3, 1, 2), yr.detach()) < 4e-3, "fwd"
+    # BatchNorm statistics produced by the conv (fused epilogue on the TMA path, separate pass otherwise):
+    # per-channel sum and sum of squares of the stored bf16 outputs
+    yf = y.double().reshape(-1, K)
+    assert rel(stats[:K], yf.sum(0)) < 1e-6 and rel(stats[K:], (yf * yf).sum(0)) < 1e-6, "fused BN statistics"
     # wgrad
-    dw = torch.empty(K, R, R, C, dtype=torch.float32, device=DEV)
+    dw = torch.zeros(K, R, R, C, dtype=torch.float32, device=DEV)  # wgrad accumulates
     call("pm_conv_wgrad_bf16", ctypes.byref(d), ptr(xd), ptr(dyd), ptr(dw), None, stream())
     torch.cuda.synchronize()
     assert rel(dw.permute(0, 3, 1, 2), wr.grad) < 1e-3, "wgrad"
@@ -76,3 +81,31 @@ def test_fwd_dgrad_wgrad_bf16(case, no_tma, monkeypatch):
         call("pm_conv_dgrad_bf16", ctypes.byref(d), ptr(dyd), ptr(wt), ptr(dx), 1, stream())
         torch.cuda.synchronize()
         assert rel(dx.float().permute(0, 3, 1, 2), 2 * xr.grad) < 8e-3, "dgrad accumulate"
+
+
+def test_stem_im2col_plus_dense_gemm_matches_conv7x7():
+    """bf16 stem: NCHW fp32 input -> bf16 im2col [B,Ho,Wo,192] -> 1x1 tensor-core GEMM == conv 7x7 / stride 2 / pad 3."""
+    from primia_b200._lib import ConvDesc, call, ptr, stream
+
+    g = torch.Generator().manual_seed(3)
+    B, H = 3, 40
+    x = torch.randn(B, 3, H, H, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    Ho = (H + 6 - 7) // 2 + 1
+    xd = x.to(DEV)
+    im = torch.empty(B, Ho, Ho, 192, dtype=torch.bfloat16, device=DEV)
+    call("pm_im2col_stem_bf16", ptr(xd), B, 3, H, H, 7, 2, 3, 192, ptr(im), stream())
+    # reference im2col in the same k order (r, s, c)
+    cols = F.unfold(x.bfloat16().float(), 7, padding=3, stride=2)  # [B, 3*49, L] ordered (c, r, s)
+    cols = cols.view(B, 3, 49, Ho, Ho).permute(0, 3, 4, 2, 1).reshape(B, Ho, Ho, 147)
+    assert torch.equal(im[..., :147].float().cpu(), cols)
+    assert torch.count_nonzero(im[..., 147:]) == 0
+    wk = torch.zeros(64, 1, 1, 192)
+    wk[:, 0, 0, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    wk = wk.bfloat16().to(DEV)
+    d = ConvDesc(B, Ho, Ho, 192, 64, 1, 1, 1, 0, Ho, Ho)
+    y = torch.empty(B, Ho, Ho, 64, dtype=torch.bfloat16, device=DEV)
+    call("pm_conv_fwd_bf16", ctypes.byref(d), ptr(im), ptr(wk), ptr(y), None, stream())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), None, 2, 3)
+    assert rel(y.float().permute(0, 3, 1, 2), ref) < 4e-3
