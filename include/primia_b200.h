@@ -156,6 +156,18 @@ int pm_bn_bwd_apply_bf16(const void* dy, const void* y_out, const void* x, const
                          const float* gamma, const double* sums, size_t P, int C, void* dx, float* dgamma,
                          float* dbeta, pm_stream_t s);
 
+/* BatchNorm backward in ONE launch (reduce -> grid barrier -> apply; deterministic, no floating-point atomics).
+ * g = dy * (y_out > 0) when y_out != NULL; if g_out != NULL the masked gradient is also written (identity branch).
+ * ws: pm_bn_bwd_fused_ws_doubles(C) doubles, ZERO-INITIALISED ONCE by the caller (the first 16 bytes are the barrier state,
+ * which the kernel leaves ready for the next launch, CUDA-graph replays included). g_out may alias dy; dx must not alias g_out. */
+size_t pm_bn_bwd_fused_ws_doubles(int C);
+int pm_bn_bwd_fused_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                        const float* gamma, size_t P, int C, double* ws, float* g_out, float* dx, float* dgamma, float* dbeta,
+                        pm_stream_t s);
+int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                         const float* gamma, size_t P, int C, double* ws, void* g_out, void* dx, float* dgamma, float* dbeta,
+                         pm_stream_t s);
+
 /* MaxPool2d(3,2,1) / AvgPool2d(3,2,1) (models.py:384-389) on NHWC; idx: uint8 argmax per output (first max wins) */
 int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s);
 int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s);

@@ -41,6 +41,8 @@ struct Vec<__nv_bfloat16> {
 };
 
 constexpr int BT = 256;
+template <typename T>
+bool chan_ok(int C);
 
 // ---- per-channel sums: out[0..C) += sum f0 , out[C..2C) += sum f1   (f0,f1 produced by Functor per element)
 // Each thread owns one 16-byte channel group (column v) and walks rows, U rows in flight; partial sums are kept in
@@ -138,6 +140,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double P, i
 }
 
 // FUSED = true: mean / invstd are derived from the batch statistics here (replaces bn_finalize + bn_apply).
+// The per-channel constants are computed once per block by C threads into shared memory (mu, scale, shift), so the
+// per-thread prologue is a few LDS instead of 4*V global loads and V double-precision evaluations.
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(BT, 3)
 bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -147,40 +151,45 @@ bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const f
                 size_t P, int C, T* __restrict__ y) {
   constexpr int V = Vec<T>::N;
   constexpr int U = 2;
-  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
-  const int c = v * V;
-  float mu[V], sc[V], be[V];  // y = (x - mu) * sc + be   with sc = invstd * gamma
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    float is;
+  extern __shared__ float sp[];  // [4][C]: mu, invstd (or invstd*gamma), gamma, beta
+  const double invPd = FUSED ? 1.0 / Pd : 0.0;
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    float m, is;
     if (FUSED) {
-      const double m = stats[c + k] / Pd;
-      double var = stats[C + c + k] / Pd - m * m;
+      // no double division / sqrt (software sequences): one double multiply each for mean and E[x^2]-mean^2,
+      // invstd = rsqrt in float + one Newton step (<= 1 ulp)
+      const double md = stats[ch] * invPd;
+      double var = stats[C + ch] * invPd - md * md;
       if (var < 0.0) var = 0.0;
-      mu[k] = (float)m;
-      is = (float)(1.0 / sqrt(var + (double)eps));
-      if (blockIdx.x == 0 && r0 == 0) {
-        mean_out[c + k] = mu[k];
-        invstd_out[c + k] = is;
+      m = (float)md;
+      const float ve = (float)(var + (double)eps);
+      is = rsqrtf(ve);
+      is = is * (1.5f - 0.5f * ve * is * is);
+      if (blockIdx.x == 0) {
+        mean_out[ch] = m;
+        invstd_out[ch] = is;
         if (rm) {
           const double unbiased = Pd > 1.0 ? var * Pd / (Pd - 1.0) : var;
-          rm[c + k] = (float)((1.0 - momentum) * (double)rm[c + k] + momentum * m);
-          rv[c + k] = (float)((1.0 - momentum) * (double)rv[c + k] + momentum * unbiased);
+          rm[ch] = (float)((1.0 - momentum) * (double)rm[ch] + momentum * md);
+          rv[ch] = (float)((1.0 - momentum) * (double)rv[ch] + momentum * unbiased);
         }
       }
     } else {
-      mu[k] = mean[c + k];
-      is = invstd[c + k];
+      m = mean[ch];
+      is = invstd[ch];
     }
-    if (sizeof(T) == 4) sc[k] = is;  // parity mode keeps the (x-mean)*invstd*gamma+beta evaluation order
-    else sc[k] = is * gamma[c + k];
-    be[k] = beta[c + k];
+    const float ga = gamma[ch];
+    sp[ch] = m;
+    sp[C + ch] = sizeof(T) == 4 ? is : is * ga;  // parity mode keeps the (x-mean)*invstd*gamma+beta evaluation order
+    sp[2 * C + ch] = ga;
+    sp[3 * C + ch] = beta[ch];
   }
-  float ga[V];
-  if (sizeof(T) == 4) {
+  __syncthreads();
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  float mu[V], sc[V], ga[V], be[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) ga[k] = gamma[c + k];
-  }
+  for (int k = 0; k < V; ++k) { mu[k] = sp[c + k]; sc[k] = sp[C + c + k]; ga[k] = sp[2 * C + c + k]; be[k] = sp[3 * C + c + k]; }
   const size_t stride = (size_t)gridDim.x * rpb;
   for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
     float xv[U][V], rvv[U][V];
@@ -269,6 +278,187 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
       }
     }
   }
+}
+
+// ---- BatchNorm backward in ONE launch: reduce -> grid barrier -> distributed total -> grid barrier -> apply.
+// All blocks are co-resident (grid <= 2 blocks/SM), so a sense-reversing barrier on two words of device memory is safe,
+// needs no host-side epoch and survives CUDA-graph replay.  No floating-point atomics: per-block partial sums are
+// combined in a fixed order (deterministic).  For the mid-size layers the second pass over dy / x / y_out hits L2.
+__device__ __forceinline__ void grid_barrier(unsigned* count, volatile unsigned* gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned my_gen = *gen;
+    __threadfence();
+    if (atomicAdd(count, 1u) == gridDim.x - 1) {
+      *count = 0;
+      __threadfence();
+      atomicAdd((unsigned*)gen, 1u);
+    } else {
+      while (*gen == my_gen) { __nanosleep(40); }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT, 2)
+bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const T* __restrict__ x,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    size_t P, int C, double invP, double* __restrict__ partial /* [grid][2C] */,
+                    double* __restrict__ totals /* [2C] */, unsigned* __restrict__ sync /* [2] */, T* __restrict__ g_out,
+                    T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = 2;
+  using acc_t = typename std::conditional<sizeof(T) == 4, double, float>::type;
+  extern __shared__ double dyn[];  // [2][BT*V]
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  // contiguous row range per block (keeps the second pass of mid-size layers inside L2 and DRAM pages sequential)
+  const size_t rows_per_block = ((P + gridDim.x - 1) / gridDim.x + rpb - 1) / rpb * rpb;
+  const size_t row_begin = (size_t)blockIdx.x * rows_per_block;
+  const size_t row_end = row_begin + rows_per_block < P ? row_begin + rows_per_block : P;
+  float mu[V], is[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = mean[c + k]; is[k] = invstd[c + k]; }
+
+  // ---- phase 1: per-block partial sums of g and g * xhat (g = dy masked by the ReLU decision)
+  acc_t s0[V], s1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0;
+  for (size_t row = row_begin + r0; row < row_end; row += (size_t)rpb * U) {
+    float g[U][V], xv[U][V], yv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        Vec<T>::load(dy + r * C + c, g[u]);
+        Vec<T>::load(x + r * C + c, xv[u]);
+        if (y_out) Vec<T>::load(y_out + r * C + c, yv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = g[u][k];
+          if (y_out) gg = yv[u][k] > 0.f ? gg : 0.f;
+          g[u][k] = gg;
+          s0[k] += (acc_t)gg;
+          s1[k] += (acc_t)(gg * ((xv[u][k] - mu[k]) * is[k]));
+        }
+        if (g_out) Vec<T>::store(g_out + r * C + c, g[u]);
+      }
+    }
+  }
+  double* d0 = dyn;
+  double* d1 = dyn + BT * V;
+#pragma unroll
+  for (int k = 0; k < V; ++k) { d0[threadIdx.x * V + k] = (double)s0[k]; d1[threadIdx.x * V + k] = (double)s1[k]; }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const int vv = ch / V, ii = ch % V;
+    double t0 = 0.0, t1 = 0.0;
+    for (int r = 0; r < rpb; ++r) { t0 += d0[(r * vr + vv) * V + ii]; t1 += d1[(r * vr + vv) * V + ii]; }
+    partial[(size_t)blockIdx.x * 2 * C + ch] = t0;
+    partial[(size_t)blockIdx.x * 2 * C + C + ch] = t1;
+  }
+  grid_barrier(sync, sync + 1);
+
+  // ---- phase 1b: the 2C totals are spread over all warps of the grid; each warp sums one column of the per-block
+  // partials (lanes stride over blocks, fixed-order shuffle tree => deterministic)
+  {
+    const int lane = threadIdx.x & 31, gw = blockIdx.x * (BT / 32) + (threadIdx.x >> 5), nw = gridDim.x * (BT / 32);
+    for (int q = gw; q < 2 * C; q += nw) {
+      double t = 0.0;
+      for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (size_t)b * 2 * C + q);
+      t = warp_sum(t);
+      if (lane == 0) {
+        totals[q] = t;
+        if (dgamma) {
+          if (q < C) dbeta[q] = (float)t;
+          else dgamma[q - C] = (float)t;
+        }
+      }
+    }
+  }
+  grid_barrier(sync, sync + 1);
+
+  // ---- phase 2: dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); per-channel constants via shared memory
+  using par_t = typename std::conditional<sizeof(T) == 4, double, float>::type;
+  double* sm_mg = dyn;        // [C]
+  double* sm_mgx = dyn + C;   // [C]
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    sm_mg[ch] = __ldcg(totals + ch) * invP;
+    sm_mgx[ch] = __ldcg(totals + C + ch) * invP;
+  }
+  __syncthreads();
+  par_t mg[V], mgx[V];
+  float gi[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    mg[k] = (par_t)sm_mg[c + k];
+    mgx[k] = (par_t)sm_mgx[c + k];
+    gi[k] = gamma[c + k];
+    if (sizeof(T) != 4) gi[k] *= is[k];
+  }
+  const T* gsrc = g_out ? g_out : dy;   // the masked gradient was materialised in phase 1 when g_out != NULL
+  const T* ymask = g_out ? nullptr : y_out;
+  for (size_t row = row_begin + r0; row < row_end; row += (size_t)rpb * U) {
+    float g[U][V], xv[U][V], yv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        Vec<T>::load(gsrc + r * C + c, g[u]);
+        Vec<T>::load(x + r * C + c, xv[u]);
+        if (ymask) Vec<T>::load(ymask + r * C + c, yv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = g[u][k];
+          if (ymask) gg = yv[u][k] > 0.f ? gg : 0.f;
+          if (sizeof(T) == 4) {
+            const double isd = (double)is[k];
+            const double xhat = ((double)xv[u][k] - (double)mu[k]) * isd;
+            g[u][k] = (float)((double)gi[k] * isd * ((double)gg - (double)mg[k] - xhat * (double)mgx[k]));
+          } else {
+            const float xhat = (xv[u][k] - mu[k]) * is[k];
+            g[u][k] = gi[k] * (gg - (float)mg[k] - xhat * (float)mgx[k]);
+          }
+        }
+        Vec<T>::store(dx + r * C + c, g[u]);
+      }
+    }
+  }
+}
+
+template <typename T>
+int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma, size_t P,
+                   int C, double* ws, T* g_out, T* dx, float* dgamma, float* dbeta, pm_stream_t s) {
+  PM_CHECK_ARG(dy && x && mean && invstd && gamma && ws && dx && P > 0 && chan_ok<T>(C) && ((dgamma == nullptr) == (dbeta == nullptr)));
+  PM_CHECK_ARG(g_out != dx);
+  const int rpb = BT / (C / Vec<T>::N);
+  size_t blocks = (P + (size_t)rpb * 8 - 1) / ((size_t)rpb * 8);
+  const size_t cap = (size_t)pm_num_sms() * 2;  // all blocks must be co-resident (grid barrier)
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  // ws layout: [2 x unsigned sync | pad to 16 B][2C totals][grid x 2C partials]
+  unsigned* sync = reinterpret_cast<unsigned*>(ws);
+  double* totals = ws + 2;
+  double* partial = totals + 2 * C;
+  const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
+  bn_bwd_fused_kernel<T><<<(int)blocks, BT, smem, S(s)>>>(dy, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals,
+                                                          sync, g_out, dx, dgamma, dbeta);
+  PM_LAUNCH_OK();
 }
 
 // ---- max pool 3x3 s2 p1 (first max wins, like ATen's CPU kernel); one thread = one 16-byte channel group
@@ -403,7 +593,7 @@ int bn_apply_t(const T* x, const float* mean, const float* invstd, const float* 
                int relu, size_t P, int C, T* y, pm_stream_t s) {
   PM_CHECK_ARG(x && mean && invstd && gamma && beta && y && C % Vec<T>::N == 0);
   PM_CHECK_ARG(chan_ok<T>(C));
-  bn_apply_kernel<T, false><<<row_grid<T>(P, C, 2), BT, 0, S(s)>>>(x, mean, invstd, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr,
+  bn_apply_kernel<T, false><<<row_grid<T>(P, C, 4), BT, 4 * C * sizeof(float), S(s)>>>(x, mean, invstd, nullptr, 0.0, 0.f, 0.f, nullptr, nullptr, nullptr,
                                                                    nullptr, gamma, beta, res, relu, P, C, y);
   PM_LAUNCH_OK();
 }
@@ -412,7 +602,7 @@ int bn_fwd_fused_t(const T* x, const double* stats, size_t P, int C, float eps, 
                    const float* beta, const T* res, int relu, T* y, float* mean, float* invstd, float* rm, float* rv,
                    pm_stream_t s) {
   PM_CHECK_ARG(x && stats && gamma && beta && y && mean && invstd && P > 0 && chan_ok<T>(C) && ((rm == nullptr) == (rv == nullptr)));
-  bn_apply_kernel<T, true><<<row_grid<T>(P, C, 2), BT, 0, S(s)>>>(x, nullptr, nullptr, stats, (double)P, eps, momentum, mean, invstd,
+  bn_apply_kernel<T, true><<<row_grid<T>(P, C, 4), BT, 4 * C * sizeof(float), S(s)>>>(x, nullptr, nullptr, stats, (double)P, eps, momentum, mean, invstd,
                                                                   rm, rv, gamma, beta, res, relu, P, C, y);
   PM_LAUNCH_OK();
 }
@@ -505,6 +695,19 @@ int pm_bn_bwd_apply_bf16(const void* dy, const void* y_out, const void* x, const
                          float* dbeta, pm_stream_t s) {
   return bn_bwd_apply_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, sums, P, C, (bf16*)dx,
                               dgamma, dbeta, s);
+}
+
+size_t pm_bn_bwd_fused_ws_doubles(int C) { return 2 + 2 * (size_t)C + (size_t)pm_num_sms() * 2 * 2 * C; }
+int pm_bn_bwd_fused_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
+                        const float* gamma, size_t P, int C, double* ws, float* g_out, float* dx, float* dgamma, float* dbeta,
+                        pm_stream_t s) {
+  return bn_bwd_fused_t<float>(dy, y_out, x, mean, invstd, gamma, P, C, ws, g_out, dx, dgamma, dbeta, s);
+}
+int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const float* mean, const float* invstd,
+                         const float* gamma, size_t P, int C, double* ws, void* g_out, void* dx, float* dgamma, float* dbeta,
+                         pm_stream_t s) {
+  return bn_bwd_fused_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, P, C, ws, (bf16*)g_out,
+                              (bf16*)dx, dgamma, dbeta, s);
 }
 
 int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s) {

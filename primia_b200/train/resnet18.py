@@ -62,6 +62,7 @@ class ResNet18Engine:
         self._prof = None
         self._graph = None
         self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
+        self.fuse_bn_bwd = True  # BN backward as one launch with a grid barrier
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -164,6 +165,9 @@ class ResNet18Engine:
         self.bn_mean = {bn: torch.empty(C, dtype=f32, device=dev) for bn, C in self.bns.items()}
         self.bn_invstd = {bn: torch.empty(C, dtype=f32, device=dev) for bn, C in self.bns.items()}
         self.stats = torch.zeros(len(self.bns) * 2 * 2 * 512, dtype=torch.float64, device=dev)  # fwd + bwd slots
+        from .._lib import lib as _l
+        _l().pm_bn_bwd_fused_ws_doubles.restype = ctypes.c_size_t
+        self.bn_bwd_ws = torch.zeros(int(_l().pm_bn_bwd_fused_ws_doubles(512)), dtype=torch.float64, device=dev)
         self.feat = torch.empty((B, 512), dtype=f32, device=dev)
         self.dfeat = torch.empty((B, 512), dtype=f32, device=dev)
         self.logits = torch.empty((B, self.ncls), dtype=f32, device=dev)
@@ -330,6 +334,11 @@ class ResNet18Engine:
 
     def _bn_bwd(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
         C = self.bns[bn]
+        if self.fuse_bn_bwd:
+            call("pm_bn_bwd_fused" + self.sfx, ptr(dy), ptr(y_out) if y_out is not None else None, ptr(x), ptr(self.bn_mean[bn]),
+                 ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".weight"]), P, C, ptr(self.bn_bwd_ws), ptr(g_out) if g_out is not None else None,
+                 ptr(dx), ptr(self.g[bn + ".weight"]), ptr(self.g[bn + ".bias"]), stream())
+            return
         st = self._stat_slot(len(self.bns) + idx)
         call("pm_bn_bwd_reduce" + self.sfx, ptr(dy), ptr(y_out) if y_out is not None else None, ptr(x),
              ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), P, C, ptr(st), ptr(g_out) if g_out is not None else None, stream())

@@ -260,3 +260,39 @@ def test_maxpool_tie_breaking_matches_aten():
     call("pm_maxpool3s2_bwd_f32", ptr(gyn), ptr(idx), 1, 6, 6, 4, ptr(dx), stream())
     assert torch.equal(yn.permute(0, 3, 1, 2).cpu(), y.detach())
     assert torch.equal(dx.permute(0, 3, 1, 2).cpu(), x.grad)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("P,C,masked,emit_g", [(3136, 512, True, False), (50000, 64, True, True), (777, 128, False, False)])
+def test_bn_backward_single_launch_matches_two_kernel_path(dtype, P, C, masked, emit_g):
+    """pm_bn_bwd_fused_* (reduce -> grid barrier -> apply in one launch) == pm_bn_bwd_reduce_* + pm_bn_bwd_apply_*;
+    run twice to exercise the self-resetting barrier state."""
+    from primia_b200._lib import call, lib, ptr, stream
+
+    sfx = "_f32" if dtype == torch.float32 else "_bf16"
+    g = torch.Generator().manual_seed(P)
+    x = torch.randn(P, C, generator=g).to(dtype).to(DEV)
+    dy = (torch.randn(P, C, generator=g) + 0.5).to(dtype).to(DEV)
+    y = torch.relu(torch.randn(P, C, generator=g)).to(dtype).to(DEV) if masked else None
+    mean = x.float().mean(0).contiguous()
+    invstd = (1.0 / (x.float().var(0, unbiased=False) + 1e-5).sqrt()).contiguous()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    g_ref = torch.empty_like(x) if emit_g else None
+    dx_ref, dg_ref, db_ref = torch.empty_like(x), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    call("pm_bn_bwd_reduce" + sfx, ptr(dy), ptr(y) if masked else None, ptr(x), ptr(mean), ptr(invstd), P, C, ptr(sums),
+         ptr(g_ref) if emit_g else None, stream())
+    call("pm_bn_bwd_apply" + sfx, ptr(g_ref if emit_g else dy), None if emit_g else (ptr(y) if masked else None), ptr(x), ptr(mean),
+         ptr(invstd), ptr(gamma), ptr(sums), P, C, ptr(dx_ref), ptr(dg_ref), ptr(db_ref), stream())
+    lib().pm_bn_bwd_fused_ws_doubles.restype = __import__("ctypes").c_size_t
+    ws = torch.zeros(int(lib().pm_bn_bwd_fused_ws_doubles(C)), dtype=torch.float64, device=DEV)
+    for _ in range(2):
+        g_out = torch.empty_like(x) if emit_g else None
+        dx, dg, db = torch.empty_like(x), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        call("pm_bn_bwd_fused" + sfx, ptr(dy), ptr(y) if masked else None, ptr(x), ptr(mean), ptr(invstd), ptr(gamma), P, C, ptr(ws),
+             ptr(g_out) if emit_g else None, ptr(dx), ptr(dg), ptr(db), stream())
+        torch.cuda.synchronize()
+        tol = 1e-6 if dtype == torch.float32 else 1e-2
+        assert rel(dx, dx_ref) < tol and rel(dg, dg_ref) < max(tol, 2e-6) and rel(db, db_ref) < max(tol, 2e-6)
+        if emit_g:
+            assert torch.equal(g_out, g_ref)
