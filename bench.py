@@ -278,8 +278,9 @@ def run_ours(args):
     host_loss = torch.zeros(1).pin_memory()
 
     def fed_round_host(i):
-        loss = worker.local_step_host(hx[i % nbuf], hy[i % nbuf])
-        host_loss.copy_(loss, non_blocking=False)
+        loss = worker.local_step_host(hx[i % nbuf], hy[i % nbuf])           # H2D of this step's batch (pinned -> device)
+        worker.prefetch_host(hx[(i + 1) % nbuf], hy[(i + 1) % nbuf])        # loader look-ahead: next batch's H2D overlaps
+        host_loss.copy_(loss, non_blocking=False)                           # D2H of this step's loss (blocks the host)
         aggregation([worker], None, group)
         eng.reset_optimizer()
 

@@ -168,6 +168,16 @@ int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const
                          const float* gamma, size_t P, int C, double* ws, void* g_out, void* dx, float* dgamma, float* dbeta,
                          pm_stream_t s);
 
+/* Stem variant: the BN input gradient is MaxPool2d(3,2,1)'s backward of `dpool` [B,Ho,Wo,C], gathered from the stored
+ * argmax inside the reduce pass (saves the separate max-pool-backward launch and one pass over the full-resolution
+ * gradient); `g_scratch` [B,H,W,C] receives the gathered+masked gradient for the apply pass; x / y_out / dx are [B,H,W,C]. */
+int pm_bn_bwd_fused_pool_f32(const float* dpool, const uint8_t* pool_idx, int B, int H, int W, const float* y_out, const float* x,
+                             const float* mean, const float* invstd, const float* gamma, int C, double* ws, float* g_scratch,
+                             float* dx, float* dgamma, float* dbeta, pm_stream_t s);
+int pm_bn_bwd_fused_pool_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* y_out, const void* x,
+                              const float* mean, const float* invstd, const float* gamma, int C, double* ws, void* g_scratch,
+                              void* dx, float* dgamma, float* dbeta, pm_stream_t s);
+
 /* MaxPool2d(3,2,1) / AvgPool2d(3,2,1) (models.py:384-389) on NHWC; idx: uint8 argmax per output (first max wins) */
 int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s);
 int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s);

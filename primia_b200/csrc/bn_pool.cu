@@ -301,9 +301,45 @@ __device__ __forceinline__ void grid_barrier(unsigned* count, volatile unsigned*
   __syncthreads();
 }
 
+// gradient of MaxPool2d(3,2,1) gathered on the fly: element (b,h,w,c..c+V) of the pool INPUT gradient from the pooled
+// gradient dpool [B,Ho,Wo,C] and the stored argmax (one byte per pooled element) -- lets the stem's BN backward read the
+// 4x smaller pooled tensors instead of a materialised full-resolution gradient.
+struct PoolGeo { int H, W, Ho, Wo; };
 template <typename T>
+__device__ __forceinline__ void load_pool_grad(const T* __restrict__ dpool, const uint8_t* __restrict__ idx, PoolGeo pg, size_t r,
+                                               int C, int c, float* g) {
+  constexpr int V = Vec<T>::N;
+  const int w = (int)(r % pg.W);
+  const size_t t = r / pg.W;
+  const int h = (int)(t % pg.H);
+  const size_t b = t / pg.H;
+#pragma unroll
+  for (int k = 0; k < V; ++k) g[k] = 0.f;
+  for (int oh = h / 2; oh <= (h + 1) / 2; ++oh) {
+    if (oh >= pg.Ho) continue;
+    const int rr = h - (oh * 2 - 1);
+    if (rr < 0 || rr > 2) continue;
+    for (int ow = w / 2; ow <= (w + 1) / 2; ++ow) {
+      if (ow >= pg.Wo) continue;
+      const int ss = w - (ow * 2 - 1);
+      if (ss < 0 || ss > 2) continue;
+      const size_t o = ((b * pg.Ho + oh) * pg.Wo + ow) * C + c;
+      float d[V];
+      Vec<T>::load(dpool + o, d);
+      uint8_t id[V];
+      if (V == 8) *reinterpret_cast<uint2*>(id) = *reinterpret_cast<const uint2*>(idx + o);
+      else *reinterpret_cast<uint32_t*>(id) = *reinterpret_cast<const uint32_t*>(idx + o);
+      const int want = rr * 3 + ss;
+#pragma unroll
+      for (int k = 0; k < V; ++k) g[k] += id[k] == want ? d[k] : 0.f;
+    }
+  }
+}
+
+template <typename T, bool POOL>
 __global__ void __launch_bounds__(BT, 2)
-bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const T* __restrict__ x,
+bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_idx, PoolGeo pg, const T* __restrict__ y_out,
+                    const T* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     size_t P, int C, double invP, double* __restrict__ partial /* [grid][2C] */,
                     double* __restrict__ totals /* [2C] */, unsigned* __restrict__ sync /* [2] */, T* __restrict__ g_out,
@@ -332,7 +368,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
     for (int u = 0; u < U; ++u) {
       const size_t r = row + (size_t)u * rpb;
       if (r < row_end) {
-        Vec<T>::load(dy + r * C + c, g[u]);
+        if (POOL) load_pool_grad<T>(dy, pool_idx, pg, r, C, c, g[u]);
+        else Vec<T>::load(dy + r * C + c, g[u]);
         Vec<T>::load(x + r * C + c, xv[u]);
         if (y_out) Vec<T>::load(y_out + r * C + c, yv[u]);
       }
@@ -413,7 +450,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
     for (int u = 0; u < U; ++u) {
       const size_t r = row + (size_t)u * rpb;
       if (r < row_end) {
-        Vec<T>::load(gsrc + r * C + c, g[u]);
+        Vec<T>::load(gsrc + r * C + c, g[u]);  // POOL: phase 1 materialised the gathered (and masked) gradient in g_out
         Vec<T>::load(x + r * C + c, xv[u]);
         if (ymask) Vec<T>::load(ymask + r * C + c, yv[u]);
       }
@@ -443,7 +480,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ y_out, const
 
 template <typename T>
 int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma, size_t P,
-                   int C, double* ws, T* g_out, T* dx, float* dgamma, float* dbeta, pm_stream_t s) {
+                   int C, double* ws, T* g_out, T* dx, float* dgamma, float* dbeta, pm_stream_t s,
+                   const uint8_t* pool_idx = nullptr, PoolGeo pg = PoolGeo{0, 0, 0, 0}) {
   PM_CHECK_ARG(dy && x && mean && invstd && gamma && ws && dx && P > 0 && chan_ok<T>(C) && ((dgamma == nullptr) == (dbeta == nullptr)));
   PM_CHECK_ARG(g_out != dx);
   const int rpb = BT / (C / Vec<T>::N);
@@ -456,8 +494,14 @@ int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, c
   double* totals = ws + 2;
   double* partial = totals + 2 * C;
   const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
-  bn_bwd_fused_kernel<T><<<(int)blocks, BT, smem, S(s)>>>(dy, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals,
-                                                          sync, g_out, dx, dgamma, dbeta);
+  if (pool_idx) {
+    PM_CHECK_ARG(g_out != nullptr);  // scratch for the gathered gradient (written in phase 1, re-read in phase 2)
+    bn_bwd_fused_kernel<T, true><<<(int)blocks, BT, smem, S(s)>>>(dy, pool_idx, pg, y_out, x, mean, invstd, gamma, P, C,
+                                                                  1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+  } else {
+    bn_bwd_fused_kernel<T, false><<<(int)blocks, BT, smem, S(s)>>>(dy, nullptr, pg, y_out, x, mean, invstd, gamma, P, C,
+                                                                   1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+  }
   PM_LAUNCH_OK();
 }
 
@@ -708,6 +752,23 @@ int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const
                          pm_stream_t s) {
   return bn_bwd_fused_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, P, C, ws, (bf16*)g_out,
                               (bf16*)dx, dgamma, dbeta, s);
+}
+
+int pm_bn_bwd_fused_pool_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* y_out, const void* x,
+                              const float* mean, const float* invstd, const float* gamma, int C, double* ws, void* g_scratch,
+                              void* dx, float* dgamma, float* dbeta, pm_stream_t s) {
+  PM_CHECK_ARG(dpool && pool_idx && B > 0 && H > 0 && W > 0);
+  const PoolGeo pg{H, W, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1};
+  return bn_bwd_fused_t<bf16>((const bf16*)dpool, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, (size_t)B * H * W, C, ws,
+                              (bf16*)g_scratch, (bf16*)dx, dgamma, dbeta, s, pool_idx, pg);
+}
+int pm_bn_bwd_fused_pool_f32(const float* dpool, const uint8_t* pool_idx, int B, int H, int W, const float* y_out, const float* x,
+                             const float* mean, const float* invstd, const float* gamma, int C, double* ws, float* g_scratch,
+                             float* dx, float* dgamma, float* dbeta, pm_stream_t s) {
+  PM_CHECK_ARG(dpool && pool_idx && B > 0 && H > 0 && W > 0);
+  const PoolGeo pg{H, W, (H + 2 - 3) / 2 + 1, (W + 2 - 3) / 2 + 1};
+  return bn_bwd_fused_t<float>(dpool, y_out, x, mean, invstd, gamma, (size_t)B * H * W, C, ws, g_scratch, dx, dgamma, dbeta, s,
+                               pool_idx, pg);
 }
 
 int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, pm_stream_t s) {

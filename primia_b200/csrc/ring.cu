@@ -230,11 +230,15 @@ ring_gemm2_kernel(const u64* __restrict__ A1, const u64* __restrict__ B1, const 
   // compute mapping
   const int tx = tid & 15, ty = tid >> 4;
 
+  // 64-bit MAC mod 2^64 in three integer-pipe instructions: lo(a)*lo(b) is accumulated at full width with
+  // IMAD.WIDE.U32, the two cross terms lo*hi + hi*lo only matter mod 2^32 and go to a separate 32-bit accumulator that
+  // is folded in (<< 32) once at the end; hi*hi vanishes mod 2^64.
   u64 acc[4][4];
+  uint32_t acch[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0; acch[i][j] = 0; }
 
   u64 ra[4], rb[4];
   auto gload = [&](int chunk) {
@@ -278,10 +282,20 @@ ring_gemm2_kernel(const u64* __restrict__ A1, const u64* __restrict__ B1, const 
         const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&Bs[buf][k][tx * 4 + 2]);
         a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
         b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+        uint32_t alo[4], ahi[4], blo[4], bhi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          alo[i] = (uint32_t)a[i]; ahi[i] = (uint32_t)(a[i] >> 32);
+          blo[i] = (uint32_t)b[i]; bhi[i] = (uint32_t)(b[i] >> 32);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+          for (int j = 0; j < 4; ++j) {
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i][j]) : "r"(alo[i]), "r"(blo[j]));
+            acch[i][j] += alo[i] * bhi[j];
+            acch[i][j] += ahi[i] * blo[j];
+          }
       }
       if (has_next) {
         sstore(buf ^ 1);
@@ -301,7 +315,7 @@ ring_gemm2_kernel(const u64* __restrict__ A1, const u64* __restrict__ B1, const 
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       const size_t o = c_off + (size_t)m * N + n;
-      u64 v = acc[i][j];
+      u64 v = acc[i][j] + ((u64)acch[i][j] << 32);
       if (split == 0 && Cinit) v += Cinit[o];
       if (atomic) atomicAdd(&Cout[o], v);
       else Cout[o] = v;

@@ -34,17 +34,51 @@ class HospitalWorker:
         """utils.py:1168-1174"""
         return self.engine.train_step(data, target)
 
-    def local_step_host(self, host_data, host_target):
-        """Same step fed from HOST memory (pinned): the batch is copied host->device on the step's stream, as a worker
-        receiving its loader's batch does; the returned loss is a device scalar the caller reads back."""
+    def _slots(self, host_data, host_target):
         eng = self.engine
-        if getattr(self, "_stage", None) is None or self._stage[0].shape != host_data.shape:
-            self._stage = (torch.empty(host_data.shape, dtype=host_data.dtype, device=eng.device),
-                           torch.empty(host_target.shape, dtype=host_target.dtype, device=eng.device))
+        if getattr(self, "_stage", None) is None or self._stage[0][0].shape != host_data.shape:
+            mk = lambda h: torch.empty(h.shape, dtype=h.dtype, device=eng.device)
+            self._stage = [(mk(host_data), mk(host_target)) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(eng.device)
+            self._ready = [None, None]     # event: slot filled
+            self._consumed = [None, None]  # event: the step that read the slot was enqueued and finished reading
+            self._pending = None           # (slot, host_data, host_target) staged ahead of time
+            self._next_slot = 0
+        return self._stage
+
+    def prefetch_host(self, host_data, host_target):
+        """Start the host->device copy of the NEXT batch (pinned memory) on a copy stream, so it overlaps the step that is
+        running -- what a data loader with one batch of look-ahead does."""
+        self._slots(host_data, host_target)
+        slot = self._next_slot
+        self._next_slot ^= 1
+        with torch.cuda.device(self.engine.device):
+            if self._consumed[slot] is not None:
+                self._copy_stream.wait_event(self._consumed[slot])
+            with torch.cuda.stream(self._copy_stream):
+                self._stage[slot][0].copy_(host_data, non_blocking=True)
+                self._stage[slot][1].copy_(host_target, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            self._ready[slot] = ev
+        self._pending = (slot, host_data, host_target)
+
+    def local_step_host(self, host_data, host_target):
+        """The same local step fed from HOST (pinned) memory: the batch crosses PCIe inside the call unless it was already
+        prefetched with ``prefetch_host``; the returned loss is a device scalar the caller reads back."""
+        eng = self.engine
+        self._slots(host_data, host_target)
+        if self._pending is None or self._pending[1] is not host_data:
+            self.prefetch_host(host_data, host_target)
+        slot = self._pending[0]
+        self._pending = None
         with torch.cuda.device(eng.device):
-            self._stage[0].copy_(host_data, non_blocking=True)
-            self._stage[1].copy_(host_target, non_blocking=True)
-        return eng.train_step(self._stage[0], self._stage[1])
+            torch.cuda.current_stream().wait_event(self._ready[slot])
+            loss = eng.train_step(self._stage[slot][0], self._stage[slot][1])
+            ev = torch.cuda.Event()
+            ev.record()
+            self._consumed[slot] = ev
+        return loss
 
 
 def fedavg_scales(worker_id, n_workers: int, weights: Optional[Dict[str, float]]):

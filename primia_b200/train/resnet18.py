@@ -63,6 +63,8 @@ class ResNet18Engine:
         self._graph = None
         self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
         self.fuse_bn_bwd = True  # BN backward as one launch with a grid barrier
+        self.overlap_wgrad = mode == "bf16"
+        self._side = None
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -288,9 +290,19 @@ class ResNet18Engine:
         self._prof_end(e0)
 
     def _conv_wgrad(self, c, x, dy):
-        e0 = self._prof_begin()
-        self._conv_wgrad_impl(c, x, dy)
-        self._prof_end(e0)
+        """Weight gradients are off the backward critical path (nothing downstream reads them before the optimizer),
+        so in bf16 mode they are issued on a side stream and overlap the BN / dgrad chain (the tensor-core wgrad CTAs
+        co-reside with the memory-bound BN kernels).  Each conv has its own dy buffer, so there is no reuse hazard."""
+        if self._side is None or self._prof is not None:
+            e0 = self._prof_begin()
+            self._conv_wgrad_impl(c, x, dy)
+            self._prof_end(e0)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            self._conv_wgrad_impl(c, x, dy)
 
     def _conv_fwd_impl(self, c, x, y, stats=None):
         if self.mode == "f32":
@@ -410,6 +422,8 @@ class ResNet18Engine:
             if self.mode == "bf16":
                 self.grads.zero_()  # the tensor-core wgrad accumulates (split over pixels) into a cleared buffer
                 self.dw_stem.zero_()
+                if self.overlap_wgrad and self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
             call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
                  ptr(target) if hard else None, None if hard else ptr(target),
                  ptr(self.class_weights) if self.class_weights is not None else None, self.B, 512, self.ncls,
@@ -426,11 +440,11 @@ class ResNet18Engine:
                 out = self.act[pre + ".out"]
                 # out = relu(bn2(cB) + idn).  g = d_out * (out > 0) may alias d_out (element-wise in place).
                 g = self._gbuf(("g", out.shape), out)
-                dcb = self._gbuf(("dc", out.shape), out)
+                dcb = self._gbuf(("dc", cb.name), out)
                 self._bn_bwd(pre + ".bn2", bn_ids[pre + ".bn2"], d_out, out, self.act[cb.name], dcb, cb.P, g_out=g)
                 if ds is not None:
                     d_xin = self._gbuf(("dx", xin.shape), xin)
-                    dcd = self._gbuf(("dcd", out.shape), out)
+                    dcd = self._gbuf(("dc", ds.name), out)
                     self._bn_bwd(pre + ".downsample.1", bn_ids[pre + ".downsample.1"], g, None, self.act[ds.name], dcd, ds.P)
                     self._conv_wgrad(ds, xin, dcd)
                     self._conv_dgrad(ds, dcd, d_xin, False)
@@ -439,23 +453,40 @@ class ResNet18Engine:
                 self._conv_wgrad(cb, self.act[pre + ".a"], dcb)
                 d_a = self._gbuf(("da", out.shape), out)
                 self._conv_dgrad(cb, dcb, d_a, False)
-                dca = dcb  # dcb is dead after the two calls above (stream order)
+                dca = self._gbuf(("dc", ca.name), out)
                 self._bn_bwd(pre + ".bn1", bn_ids[pre + ".bn1"], d_a, self.act[pre + ".a"], self.act[ca.name], dca, ca.P)
                 self._conv_wgrad(ca, xin, dca)
                 self._conv_dgrad(ca, dca, d_xin, True)
                 d_out = d_xin
             c1 = self.convs["conv1"]
-            d_a1 = self._gbuf(("da1",), self.act["a1"])
-            call("pm_maxpool3s2_bwd" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
             dc1 = self._gbuf(("dc1",), self.act["conv1"])
-            self._bn_bwd("bn1", bn_ids["bn1"], d_a1, self.act["a1"], self.act["conv1"], dc1, c1.P)
+            if self.fuse_bn_bwd:
+                # max-pool backward is gathered inside the stem's BN backward (no full-resolution gradient round trip)
+                call("pm_bn_bwd_fused_pool" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["a1"]),
+                     ptr(self.act["conv1"]), ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
+                     ptr(self.bn_bwd_ws), ptr(self._gbuf(("da1",), self.act["a1"])), ptr(dc1), ptr(self.g["bn1.weight"]),
+                     ptr(self.g["bn1.bias"]), stream())
+            else:
+                d_a1 = self._gbuf(("da1",), self.act["a1"])
+                call("pm_maxpool3s2_bwd" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
+                self._bn_bwd("bn1", bn_ids["bn1"], d_a1, self.act["a1"], self.act["conv1"], dc1, c1.P)
             if self.mode == "f32":
                 self._conv_wgrad(c1, self.x0, dc1)
             else:
-                e0 = self._prof_begin()
-                call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
-                self._prof_end(e0)
-                self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
+                if self._side is not None and self._prof is None:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self._side.wait_event(ev)
+                    with torch.cuda.stream(self._side):
+                        call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
+                        self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
+                else:
+                    e0 = self._prof_begin()
+                    call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
+                    self._prof_end(e0)
+                    self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)  # join: the optimizer needs every weight gradient
         return self.loss
 
     def optimizer_step(self):
