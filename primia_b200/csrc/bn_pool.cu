@@ -294,7 +294,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* count, volatile unsigned*
       __threadfence();
       atomicAdd((unsigned*)gen, 1u);
     } else {
-      while (*gen == my_gen) { __nanosleep(40); }
+      while (*gen == my_gen) { }
     }
     __threadfence();
   }
@@ -336,7 +336,11 @@ __device__ __forceinline__ void load_pool_grad(const T* __restrict__ dpool, cons
   }
 }
 
-template <typename T, bool POOL>
+// ATOMIC = true (bf16 / throughput mode): the per-block sums go straight into a ping-pong totals buffer with double
+// atomics and only ONE grid barrier is needed (parity = barrier generation & 1; the buffer of the other parity is cleared
+// for the next launch).  ATOMIC = false (fp32 / parity mode): per-block partials + fixed-order tree, two barriers,
+// bit-reproducible.
+template <typename T, bool POOL, bool ATOMIC>
 __global__ void __launch_bounds__(BT, 2)
 bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_idx, PoolGeo pg, const T* __restrict__ y_out,
                     const T* __restrict__ x,
@@ -395,18 +399,29 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
 #pragma unroll
   for (int k = 0; k < V; ++k) { d0[threadIdx.x * V + k] = (double)s0[k]; d1[threadIdx.x * V + k] = (double)s1[k]; }
   __syncthreads();
+  const unsigned parity = ATOMIC ? (*(volatile unsigned*)(sync + 1)) & 1u : 0u;  // generation before this launch's barrier
+  constexpr int CMAX = 512;  // fixed ping-pong stride so that launches with different C share one workspace safely
+  double* tot = ATOMIC ? totals + (size_t)parity * 2 * CMAX : totals;
+  const int TS = ATOMIC ? CMAX : C;  // offset of the second statistic inside `tot`
   for (int ch = threadIdx.x; ch < C; ch += BT) {
     const int vv = ch / V, ii = ch % V;
     double t0 = 0.0, t1 = 0.0;
     for (int r = 0; r < rpb; ++r) { t0 += d0[(r * vr + vv) * V + ii]; t1 += d1[(r * vr + vv) * V + ii]; }
-    partial[(size_t)blockIdx.x * 2 * C + ch] = t0;
-    partial[(size_t)blockIdx.x * 2 * C + C + ch] = t1;
+    if (ATOMIC) {
+      atomicAdd(tot + ch, t0);
+      atomicAdd(tot + TS + ch, t1);
+    } else {
+      partial[(size_t)blockIdx.x * 2 * C + ch] = t0;
+      partial[(size_t)blockIdx.x * 2 * C + C + ch] = t1;
+    }
   }
+  if (ATOMIC && blockIdx.x == 0)  // clear the WHOLE other-parity buffer for the next launch (its readers finished a launch ago)
+    for (int i = threadIdx.x; i < 2 * CMAX; i += BT) totals[(size_t)(parity ^ 1u) * 2 * CMAX + i] = 0.0;
   grid_barrier(sync, sync + 1);
 
-  // ---- phase 1b: the 2C totals are spread over all warps of the grid; each warp sums one column of the per-block
-  // partials (lanes stride over blocks, fixed-order shuffle tree => deterministic)
-  {
+  if (!ATOMIC) {
+    // ---- phase 1b: the 2C totals are spread over all warps of the grid; each warp sums one column of the per-block
+    // partials (lanes stride over blocks, fixed-order shuffle tree => deterministic)
     const int lane = threadIdx.x & 31, gw = blockIdx.x * (BT / 32) + (threadIdx.x >> 5), nw = gridDim.x * (BT / 32);
     for (int q = gw; q < 2 * C; q += nw) {
       double t = 0.0;
@@ -420,8 +435,13 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
         }
       }
     }
+    grid_barrier(sync, sync + 1);
+  } else if (dgamma && blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < C; ch += BT) {
+      dbeta[ch] = (float)__ldcg(tot + ch);
+      dgamma[ch] = (float)__ldcg(tot + TS + ch);
+    }
   }
-  grid_barrier(sync, sync + 1);
 
   // ---- phase 2: dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); per-channel constants via shared memory
   using par_t = typename std::conditional<sizeof(T) == 4, double, float>::type;
@@ -429,8 +449,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
   double* sm_mgx = dyn + C;   // [C]
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += BT) {
-    sm_mg[ch] = __ldcg(totals + ch) * invP;
-    sm_mgx[ch] = __ldcg(totals + C + ch) * invP;
+    sm_mg[ch] = __ldcg(tot + ch) * invP;
+    sm_mgx[ch] = __ldcg(tot + TS + ch) * invP;
   }
   __syncthreads();
   par_t mg[V], mgx[V];
@@ -491,16 +511,17 @@ int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, c
   if (blocks < 1) blocks = 1;
   // ws layout: [2 x unsigned sync | pad to 16 B][2C totals][grid x 2C partials]
   unsigned* sync = reinterpret_cast<unsigned*>(ws);
-  double* totals = ws + 2;
-  double* partial = totals + 2 * C;
+  PM_CHECK_ARG(C <= 512);
+  double* totals = ws + 2;          // [2][2*512] (ping-pong in ATOMIC mode)
+  double* partial = totals + 4 * 512;
   const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
   if (pool_idx) {
     PM_CHECK_ARG(g_out != nullptr);  // scratch for the gathered gradient (written in phase 1, re-read in phase 2)
-    bn_bwd_fused_kernel<T, true><<<(int)blocks, BT, smem, S(s)>>>(dy, pool_idx, pg, y_out, x, mean, invstd, gamma, P, C,
-                                                                  1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+    bn_bwd_fused_kernel<T, true, sizeof(T) != 4><<<(int)blocks, BT, smem, S(s)>>>(
+        dy, pool_idx, pg, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
   } else {
-    bn_bwd_fused_kernel<T, false><<<(int)blocks, BT, smem, S(s)>>>(dy, nullptr, pg, y_out, x, mean, invstd, gamma, P, C,
-                                                                   1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+    bn_bwd_fused_kernel<T, false, sizeof(T) != 4><<<(int)blocks, BT, smem, S(s)>>>(
+        dy, nullptr, pg, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
   }
   PM_LAUNCH_OK();
 }
@@ -741,7 +762,7 @@ int pm_bn_bwd_apply_bf16(const void* dy, const void* y_out, const void* x, const
                               dgamma, dbeta, s);
 }
 
-size_t pm_bn_bwd_fused_ws_doubles(int C) { return 2 + 2 * (size_t)C + (size_t)pm_num_sms() * 2 * 2 * C; }
+size_t pm_bn_bwd_fused_ws_doubles(int C) { return 2 + 4 * 512 + (size_t)pm_num_sms() * 2 * 2 * (size_t)(C > 0 ? C : 512); }
 int pm_bn_bwd_fused_f32(const float* dy, const float* y_out, const float* x, const float* mean, const float* invstd,
                         const float* gamma, size_t P, int C, double* ws, float* g_out, float* dx, float* dgamma, float* dbeta,
                         pm_stream_t s) {
