@@ -293,9 +293,13 @@ def run_ours(args):
     conv_ms, launches = eng.profile_conv_time(xs[0], ys[0], steps=2)
     pk = peaks()
     achieved = GFLOP_PER_IMAGE * B / conv_ms  # GFLOP / ms == TFLOP/s
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM: fwd+dgrad+wgrad, 60 launches/step)",
+    roof = {"bound": "tensor", "kernel": "tma::conv_tma_kernel + dgrad_s2_tma_kernel + wgrad_tma_kernel (tcgen05/TMEM implicit GEMM fed by im2col "
+                                         "TMA: 20 fwd + 19 dgrad + 20 wgrad launches per step)",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "traffic": None, "conv_ms_per_step": conv_ms, "step_share": conv_ms / (ms / args.steps),
+            "traffic": 1.479e9 if args.mode == "bf16" and B == 64 else None,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step, ncu pass "
+                            "profiles/r01_step_dram_traffic_ncu.csv (write-back of the outputs is not attributed to the kernel by ncu)",
+            "conv_ms_per_step": conv_ms, "step_share": conv_ms / (ms / args.steps),
             "algorithmic": f"{GFLOP_PER_IMAGE} GFLOP/image x {B} images per step", "peak_source": pk["source"] + ", sustained bf16 GEMM"}
     if args.mode != "bf16":
         roof["note"] = "fp32 parity mode runs on the FP32 pipe; fraction is still quoted against the bf16 tensor peak"

@@ -109,19 +109,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int STAGES, bool FLIP>
+// RB ("resident B"): when the whole dense operand of this CTA's n-tile fits in shared memory (N == BN and
+// R*S*C*BN*2 bytes <= RB_MAX_BYTES: the 64-channel layers and the stem), it is loaded ONCE per CTA and only the activation
+// tiles stream through the stage ring -- these layers are bound by L2->SM bandwidth, not by the tensor pipe.
+constexpr int RB_MAX_BYTES = 80 * 1024;
+
+template <int BN, int STAGES, bool FLIP, bool RB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, bf16* __restrict__ dst,
                 int accumulate, double* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = RB ? A_BYTES : A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 128 or 256)
   const uint32_t s_base = smem_u32(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t b_res = s_base + STAGES * STAGE_BYTES;  // RB: [nkb][BN rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (RB ? RB_MAX_BYTES : 0));
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES;
-  const uint32_t tfull0 = full0 + 16 * STAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t tfull0 = full0 + 16 * STAGES, tempty0 = tfull0 + 16, bfull = tempty0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
   float* scratch_all = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // 4 x [32][33] transposition scratch
   float* cta_stats = scratch_all + 4 * 32 * 33;                         // [2][N] per-CTA partial statistics
 
@@ -145,6 +151,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
     }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -160,6 +167,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (tid == 0) {
     // ------------------------------------------------------------ TMA producer
     int it = 0;
+    if (RB && (int)blockIdx.x < ntiles) {  // the whole dense operand, once (ntn == 1 => n0 == 0)
+      mbar_expect_tx(bfull, (uint32_t)(nkb * B_BYTES));
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(b_res + kb * B_BYTES, &tmB, bfull, kb * 64, 0);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * BN;
       const int nb = m0 / (OH * OW);
@@ -176,13 +187,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
         tma_load_im2col(a_tile, &tmA, full0 + 8 * s, c0, bw, bh, nb, (uint16_t)(FLIP ? p.S - 1 - sx : sx),
                         (uint16_t)(FLIP ? p.R - 1 - r : r));
-        tma_load_2d(b_tile, &tmB, full0 + 8 * s, kb * 64, n0);
+        if (!RB) tma_load_2d(b_tile, &tmB, full0 + 8 * s, kb * 64, n0);
       }
     }
   } else if (tid == 32) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
     int it = 0, lt = 0;
+    if (RB && (int)blockIdx.x < ntiles) mbar_wait(bfull, 0);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int as = lt & 1;
       mbar_wait(tempty0 + 8 * as, ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
@@ -192,7 +204,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int s = it % STAGES;
         mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = a_tile + A_BYTES;
+        const uint32_t a_tile = s_base + s * STAGE_BYTES, b_tile = RB ? b_res + kb * B_BYTES : a_tile + A_BYTES;
         const uint64_t adesc = make_desc(a_tile, 16, 1024), bdesc = make_desc(b_tile, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
@@ -558,7 +570,9 @@ static bool set_smem(Kern k, int bytes) {
 }
 
 constexpr int FSTAGES = 5;
+constexpr int RSTAGES = 6;  // resident-B variant: stages hold only the 16 KB activation tiles
 constexpr int smem_conv(int BN, int stages) { return stages * (TILE_BYTES + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4 + 2 * 512 * 4; }
+constexpr int smem_conv_rb(int stages) { return stages * TILE_BYTES + RB_MAX_BYTES + 1024 + 256 + 4 * 32 * 33 * 4 + 2 * 512 * 4; }
 constexpr int smem_wg(int BN, int stages) { return stages * (2 * TILE_BYTES + (BN / 64) * TILE_BYTES) + 1024 + 256; }
 
 static Geo geo(const pm_conv_t* p) { return Geo{p->B, p->H, p->W, p->C, p->K, p->R, p->S, p->stride, p->pad, p->Ho, p->Wo}; }
@@ -576,14 +590,19 @@ int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, d
   const int M = p->B * p->Ho * p->Wo;
   if (p->K % 128 == 0) {
     if (!map_dense(&tmB, w, p->K, Ktot, 128)) return 2;
-    if (!set_smem(conv_tma_kernel<128, FSTAGES, false>, smem_conv(128, FSTAGES))) return 2;
+    if (!set_smem(conv_tma_kernel<128, FSTAGES, false, false>, smem_conv(128, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 128)));
-    conv_tma_kernel<128, FSTAGES, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+    conv_tma_kernel<128, FSTAGES, false, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+  } else if (p->K == 64 && Ktot * 64 * 2 <= RB_MAX_BYTES) {
+    if (!map_dense(&tmB, w, p->K, Ktot, 64)) return 2;
+    if (!set_smem(conv_tma_kernel<64, RSTAGES, false, true>, smem_conv_rb(RSTAGES))) return 2;
+    dim3 grid(std::min(pm_num_sms(), (M + 127) / 128));
+    conv_tma_kernel<64, RSTAGES, false, true><<<grid, NTHREADS, smem_conv_rb(RSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
   } else {
     if (!map_dense(&tmB, w, p->K, Ktot, 64)) return 2;
-    if (!set_smem(conv_tma_kernel<64, FSTAGES, false>, smem_conv(64, FSTAGES))) return 2;
+    if (!set_smem(conv_tma_kernel<64, FSTAGES, false, false>, smem_conv(64, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 64)));
-    conv_tma_kernel<64, FSTAGES, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+    conv_tma_kernel<64, FSTAGES, false, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
   }
   return 0;
 }
@@ -620,14 +639,19 @@ int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* 
   const int M = p->B * p->H * p->W;
   if (p->C % 128 == 0) {
     if (!map_dense(&tmB, wt, p->C, Ktot, 128)) return 2;
-    if (!set_smem(conv_tma_kernel<128, FSTAGES, true>, smem_conv(128, FSTAGES))) return 2;
+    if (!set_smem(conv_tma_kernel<128, FSTAGES, true, false>, smem_conv(128, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 128)));
-    conv_tma_kernel<128, FSTAGES, true><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+    conv_tma_kernel<128, FSTAGES, true, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+  } else if (p->C == 64 && Ktot * 64 * 2 <= RB_MAX_BYTES) {
+    if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
+    if (!set_smem(conv_tma_kernel<64, RSTAGES, true, true>, smem_conv_rb(RSTAGES))) return 2;
+    dim3 grid(std::min(pm_num_sms(), (M + 127) / 128));
+    conv_tma_kernel<64, RSTAGES, true, true><<<grid, NTHREADS, smem_conv_rb(RSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
   } else {
     if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
-    if (!set_smem(conv_tma_kernel<64, FSTAGES, true>, smem_conv(64, FSTAGES))) return 2;
+    if (!set_smem(conv_tma_kernel<64, FSTAGES, true, false>, smem_conv(64, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 64)));
-    conv_tma_kernel<64, FSTAGES, true><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+    conv_tma_kernel<64, FSTAGES, true, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
   }
   return 0;
 }
