@@ -96,7 +96,82 @@ def _scale(t: torch.Tensor, scale: float):
         call("pm_scale_f32", ptr(t), ctypes.c_float(scale), t.numel(), stream())
 
 
-def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float]] = None, group=None):
+def _telescoping_shares(q: torch.Tensor, n: int, seed: int, counter: int):
+    """AdditiveSharingTensor.generate_shares for n workers (additive_shared.py:336-365): r_0..r_{n-2} random,
+    shares = [r_0, r_1 - r_0, ..., r_{n-2} - r_{n-3}, q - r_{n-2}]  (sum telescopes to q mod 2^64)."""
+    from ..ring import ops
+
+    if n == 1:
+        return [q]
+    rs = [ops.random_i64(q.shape, seed, counter + i, q.device) for i in range(n - 1)]
+    shares = [rs[0]]
+    for i in range(1, n - 1):
+        shares.append(ops.axpby(1, rs[i], -1, rs[i - 1]))
+    shares.append(ops.axpby(1, q, -1, rs[n - 2]))
+    return shares
+
+
+def secure_aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float]] = None, group=None,
+                       precision_fractional: int = 16, base: int = 10, seed: int = 0x5A6E):
+    """The reference's DEFAULT aggregation (``secure=True``, utils.py:1045-1060,1078-1090) on GPUs:
+
+        (param * w_i).fix_prec(pf).share(*workers).get()  ->  share-wise sum over hospitals  ->  .get()  ->  .float_prec()  [-> / n]
+
+    Every hospital fixed-point-encodes its flat state (pm_encode_f32_i64), splits it into one additive share per hospital
+    (Philox), share j travels to hospital j (all-to-all over NVLink when one hospital runs per rank), hospital j adds the
+    shares it received -- no party ever sees another hospital's plaintext weights -- and the per-hospital sums are
+    reconstructed with an int64 SUM all-reduce (two's-complement wraparound == arithmetic mod 2^64) and decoded.
+    Result (identical on every hospital) == decode(sum_i encode(theta_i * w_i)) [/ n], the reference's arithmetic."""
+    import torch.distributed as dist
+
+    from ..ring import ops
+
+    distributed = group is not None
+    n = dist.get_world_size(group) if distributed else len(workers)
+    rank = dist.get_rank(group) if distributed else 0
+    encoded = []
+    for w in workers:
+        eng = w.engine
+        x = eng.flat
+        if weights is not None:
+            x = x.clone()
+            _scale(x, float(weights[w.id]))  # (param * weight) in fp32, then encoded
+        with torch.cuda.device(eng.device):
+            encoded.append(ops.encode(x, base, precision_fractional))
+    if distributed:
+        q = encoded[0]
+        shares = _telescoping_shares(q, n, seed + rank, 1)
+        send = torch.stack(shares)                      # [n, len]: row j goes to hospital j
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        mine = recv[0]
+        for j in range(1, n):
+            mine = ops.axpby(1, mine, 1, recv[j])        # this hospital's share of the sum
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM, group=group)  # reconstruction (mod 2^64)
+        total = mine
+    else:
+        dev = workers[0].engine.device
+        held = [None] * n                                # held[j]: what hospital j accumulates
+        for i, q in enumerate(encoded):
+            for j, sh in enumerate(_telescoping_shares(q, n, seed + i, 1)):
+                sh = sh.to(workers[j].engine.device)
+                held[j] = sh if held[j] is None else ops.axpby(1, held[j], 1, sh)
+        total = held[0].to(dev)
+        for j in range(1, n):
+            total = ops.axpby(1, total, 1, held[j].to(dev))
+    for w in workers:
+        eng = w.engine
+        with torch.cuda.device(eng.device):
+            out = ops.decode(total.to(eng.device), base, precision_fractional)
+            eng.flat.copy_(out)
+            if weights is None:
+                # sumstacked / len(workers), utils.py:1090: IEEE fp32 division (a tensor divisor; a python-scalar divisor would
+                # be turned into a multiplication by the rounded reciprocal on CUDA and differ in the last bit for n = 3, 5, ...)
+                eng.flat.div_(torch.full((), float(n), dtype=torch.float32, device=eng.device))
+
+
+def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float]] = None, group=None, secure: bool = False,
+                precision_fractional: int = 16):
     """FedAvg of every state entry except num_batches_tracked (utils.py:1027-1092).
 
     With ``group`` (torch.distributed process group, one hospital per rank) this is one NCCL all-reduce of the
@@ -104,7 +179,11 @@ def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float
     with the averaged state (== aggregation + send_new_models)."""
     import torch.distributed as dist
 
-    if group is not None or (dist.is_available() and dist.is_initialized() and len(workers) == 1):
+    if group is None and dist.is_available() and dist.is_initialized() and len(workers) == 1:
+        group = dist.group.WORLD
+    if secure:
+        return secure_aggregation(workers, weights, group, precision_fractional)
+    if group is not None:
         eng = workers[0].engine
         pre, post = fedavg_scales(workers[0].id, dist.get_world_size(group), weights)
         _scale(eng.flat, pre)
@@ -127,7 +206,7 @@ def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float
 
 
 def federated_round(workers: List[HospitalWorker], sync_every_n_batch: int = 1, weights=None, keep_optim_dict=False,
-                    group=None):
+                    group=None, secure: bool = False, precision_fractional: int = 16):
     """secure_aggregation_epoch (utils.py:1108-1233) with unencrypted aggregation.  Hospitals of this process are
     visited in order (utils.py:1160); with one hospital per rank they run concurrently on their own GPUs."""
     if not keep_optim_dict:
@@ -143,11 +222,11 @@ def federated_round(workers: List[HospitalWorker], sync_every_n_batch: int = 1, 
             d, t = w.batches[batch_idx]
             losses.append(w.local_step(d, t).clone())  # engine.loss is a reused device buffer
         if batch_idx > 0 and batch_idx % sync_every_n_batch == 0:
-            aggregation(workers, weights, group)
+            aggregation(workers, weights, group, secure, precision_fractional)
             if not keep_optim_dict:
                 for w in workers:
                     w.engine.reset_optimizer()
-    aggregation(workers, weights, group)
+    aggregation(workers, weights, group, secure, precision_fractional)
     if not losses:
         return torch.zeros(())
     return torch.stack([l.reshape(()).to(losses[0].device) for l in losses]).mean()

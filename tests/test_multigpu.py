@@ -68,6 +68,16 @@ for weights in (None, {"alice": 0.25, "bob": 0.75}):
         if "num_batches_tracked" in k: continue
         err = ((sd[k].cpu().double() - v.double()).norm() / v.double().norm().clamp_min(1e-30)).item()
         assert err < 1e-6, (k, err)
+    # secure aggregation (reference default): shares travel by all-to-all, reconstruction by int64 all-reduce
+    eng.load_state_dict(models[ids[rank]].state_dict())
+    aggregation([HospitalWorker(ids[rank], eng)], weights, dist.group.WORLD, secure=True, precision_fractional=16)
+    sd = eng.state_dict()
+    for k in local.state_dict():
+        if "num_batches_tracked" in k: continue
+        ts = [models[w].state_dict()[k] for w in ids]
+        ref = O.secure_aggregation_value(ts, [weights[w] for w in ids] if weights else [1, 1], 10, 16)
+        if weights is None: ref = ref / 2
+        assert torch.equal(sd[k].cpu(), ref.reshape(sd[k].shape)), k
 dist.barrier()
 if rank == 0: print("NCCL_FEDAVG_OK")
 dist.destroy_process_group()

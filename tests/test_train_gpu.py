@@ -296,3 +296,33 @@ def test_bn_backward_single_launch_matches_two_kernel_path(dtype, P, C, masked, 
         assert rel(dx, dx_ref) < tol and rel(dg, dg_ref) < max(tol, 2e-6) and rel(db, db_ref) < max(tol, 2e-6)
         if emit_g:
             assert torch.equal(g_out, g_ref)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_secure_aggregation_matches_reference_arithmetic(weighted):
+    """secure=True (the reference default, utils.py:1045-1060,1078-1090): decode(sum_i encode(theta_i * w_i)) [/ n] -- bit-exact
+    in the ring, then compared after decoding with the oracle's restatement."""
+    from primia_b200.train import HospitalWorker, ResNet18Engine, aggregation
+
+    size, ids = 64, ["alice", "bob", "charlie"]
+    models = {}
+    for i, w in enumerate(ids):
+        torch.manual_seed(50 + i)
+        models[w] = O.ResNet18(input_size=size)
+    weights = {"alice": 0.2, "bob": 0.5, "charlie": 0.3} if weighted else None
+    workers = []
+    for w in ids:
+        e = ResNet18Engine(2, 3, 3, size, "max", DEV, "f32")
+        e.load_state_dict(models[w].state_dict())
+        workers.append(HospitalWorker(w, e))
+    aggregation(workers, weights, secure=True, precision_fractional=16)
+    sd = workers[1].engine.state_dict()
+    for k in models["alice"].state_dict():
+        if "num_batches_tracked" in k:
+            continue
+        ts = [models[w].state_dict()[k] for w in ids]
+        ref = O.secure_aggregation_value(ts, [weights[w] for w in ids] if weighted else [1, 1, 1], 10, 16)
+        if not weighted:
+            ref = ref / len(ids)
+        assert torch.equal(sd[k].cpu(), ref.reshape(sd[k].shape)), k
+    assert torch.equal(workers[0].engine.flat, workers[2].engine.flat)

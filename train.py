@@ -92,8 +92,6 @@ def main(argv=None):
         raise SystemExit("only the federated path (--train_federated) is built: it is the hot path (BASELINE.json north_star)")
     if args.model != "resnet-18":
         raise NotImplementedError("model unknown / out of scope: " + args.model)
-    if not args.unencrypted_aggregation:
-        print("note: secure aggregation on GPU is the next row (SURVEY.md 8f-2); running unencrypted FedAvg")
 
     import torch.distributed as dist
 
@@ -141,7 +139,8 @@ def main(argv=None):
             h.engine.lr = lr  # scheduler.adjust_learning_rate per worker, train.py:433-440
             h.batches = [(d.get(), t.get()) for d, t in loaders[h.id]]
         t0 = time.time()
-        loss = federated_round(hospitals, args.sync_every_n_batch, weights, args.keep_optim_dict, group)
+        loss = federated_round(hospitals, args.sync_every_n_batch, weights, args.keep_optim_dict, group,
+                               secure=not args.unencrypted_aggregation, precision_fractional=args.precision_fractional)
         torch.cuda.synchronize()
         dt = time.time() - t0
         n_img = sum(len(h.batches) for h in hospitals) * B * world
