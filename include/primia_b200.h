@@ -67,6 +67,15 @@ int pm_open_add_i64(const int64_t* local, const int64_t* peer, int64_t* out, siz
 int pm_spdz_combine_matmul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a,
                                const int64_t* b, const int64_t* c, int B, int M, int K, int N, int64_t* ws,
                                int64_t* z, pm_stream_t s);
+/* The same contraction on the INT8 tensor cores (exact): every int64 is split into 8 unsigned byte limbs and
+ * C = Cinit + A1@B1 (+ A2@B2) mod 2^64 is evaluated as 36 u8 x u8 -> s32 limb-pair GEMMs (tcgen05.mma.kind::i8) whose 14
+ * accumulators are recombined with shifts in the epilogue (primia_b200/csrc/ring_i8.cu).  Replaces triple_mat_mul /
+ * spdz_compute's three th.matmul calls (spdz.py:54-59,90-122) for N % 32 == 0.  rows = B*M (the batch is folded);
+ * A1,A2 [rows,K]; B1,B2 [K,N]; Cinit,C [rows,N]; ws: pm_ring_tc_ws_bytes(...) bytes of scratch for the limb planes. */
+size_t pm_ring_tc_ws_bytes(int rows, int K, int N, int nseg);
+int pm_ring_tc_supported(int rows, int K, int N);
+int pm_ring_gemm2_tc_i64(const int64_t* A1, const int64_t* B1, const int64_t* A2, const int64_t* B2, const int64_t* Cinit, int rows,
+                         int K, int N, void* ws, int64_t* C, pm_stream_t s);
 /* spdz_compute, op == "mul" with torch broadcasting of a [C]-vector against [P,C]:
  * mode 0: same shape n ; mode 1: left is [C], right is [P,C] ; mode 2: left is [P,C], right is [C]. */
 int pm_spdz_combine_mul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a, const int64_t* b,

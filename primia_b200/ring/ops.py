@@ -5,6 +5,7 @@ stream of the tensor's device.  No CPU path exists."""
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -119,8 +120,40 @@ def open_add(local, peer):
     return out
 
 
+USE_TENSOR_CORES = os.environ.get("PRIMIA_RING_TC", "1") != "0"
+
+
+def gemm2_tc(A1, B1, A2, B2, Cinit):
+    """C = Cinit + A1@B1 + A2@B2 over Z_2^64 on the int8 tensor cores (limb decomposition, exact). A: [rows,K], B: [K,N]."""
+    from .._lib import lib
+
+    rows, K = A1.shape
+    N = B1.shape[1]
+    l = lib()
+    l.pm_ring_tc_ws_bytes.restype = ctypes.c_size_t
+    nseg = 2 if A2 is not None else 1
+    ws = torch.empty(int(l.pm_ring_tc_ws_bytes(rows, K, N, nseg)), dtype=torch.uint8, device=A1.device)
+    C = torch.empty((rows, N), dtype=I64, device=A1.device)
+    with torch.cuda.device(A1.device):
+        call("pm_ring_gemm2_tc_i64", ptr(A1), ptr(B1), ptr(A2) if A2 is not None else None, ptr(B2) if B2 is not None else None,
+             ptr(Cinit) if Cinit is not None else None, rows, K, N, ptr(ws), ptr(C), stream())
+    return C
+
+
+def tc_supported(rows, K, N):
+    from .._lib import lib
+
+    return USE_TENSOR_CORES and bool(lib().pm_ring_tc_supported(int(rows), int(K), int(N)))
+
+
 def combine_matmul(j, delta, eps, a, b, c):
     delta, eps, a, b, c = map(_chk, (delta, eps, a, b, c))
+    if tc_supported(delta.numel() // delta.shape[-1], delta.shape[-1], eps.shape[1]):
+        # delta@b + delta@eps == delta@(b + eps) exactly in the ring (party 0); then one 2-segment limb GEMM
+        b_eff = axpby(1, b, 1, eps) if j == 0 else b
+        K = delta.shape[-1]
+        z = gemm2_tc(delta.reshape(-1, K), b_eff, a.reshape(-1, K), eps, c.reshape(-1, c.shape[-1]))
+        return z.view(c.shape)
     if delta.dim() == 2:  # plain [M,K] @ [K,N] (linear, functional.py:10-14)
         Bt, (M, K) = 1, delta.shape
         assert tuple(c.shape) == (M, eps.shape[1])
@@ -155,6 +188,8 @@ def combine_mul(j, delta, eps, a, b, c):
 
 def matmul(A, Bm):
     A, Bm = _chk(A), _chk(Bm)
+    if tc_supported(A.numel() // A.shape[-1], A.shape[-1], Bm.shape[1]):
+        return gemm2_tc(A.reshape(-1, A.shape[-1]), Bm, None, None, None).view(*A.shape[:-1], Bm.shape[1])
     squeeze = A.dim() == 2
     if squeeze:
         A = A.unsqueeze(0)

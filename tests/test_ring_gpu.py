@@ -259,3 +259,30 @@ def test_avgpool_and_linear_bit_exact(ring):
     out = ring.functional.linear(mk(feat), mk(ws), mk(bs))
     for j in range(2):
         assert torch.equal(out.child.child[j].cpu(), ref_l[j])
+
+
+@pytest.mark.parametrize("rows,K,N", [(128, 128, 32), (200, 147, 64), (49, 4608, 512), (12544, 147, 64), (777, 300, 96)])
+def test_int8_limb_tensor_core_gemm_equals_imad_gemm(ring, rows, K, N):
+    """tcgen05.mma.kind::i8 limb decomposition (ring_i8.cu) vs the integer-pipe GEMM and vs torch CPU: bit-exact mod 2^64."""
+    from primia_b200.ring import ops
+
+    g = torch.Generator().manual_seed(rows + K + N)
+    A1, A2 = rnd(g, (rows, K)), rnd(g, (rows, K))
+    B1, B2 = rnd(g, (K, N)), rnd(g, (K, N))
+    C0 = rnd(g, (rows, N))
+    assert ops.tc_supported(rows, K, N)
+    got = ops.gemm2_tc(cu(A1), cu(B1), cu(A2), cu(B2), cu(C0)).cpu()
+    want = torch.matmul(A1, B1) + torch.matmul(A2, B2) + C0
+    assert torch.equal(got, want)
+    # extreme limbs: all-ones bytes maximise every limb-pair sum
+    A1 = torch.full((rows, K), -1, dtype=torch.int64)
+    B1 = torch.full((K, N), -1, dtype=torch.int64)
+    got = ops.gemm2_tc(cu(A1), cu(B1), None, None, None).cpu()
+    assert torch.equal(got, torch.matmul(A1, B1))
+    old = ops.USE_TENSOR_CORES
+    try:
+        ops.USE_TENSOR_CORES = False
+        ref = ops.matmul(cu(A2), cu(B2)).cpu()
+    finally:
+        ops.USE_TENSOR_CORES = old
+    assert torch.equal(ops.matmul(cu(A2), cu(B2)).cpu(), ref)
