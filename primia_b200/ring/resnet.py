@@ -82,3 +82,47 @@ class SharedLinearLayers:
             out[name] = F.conv2d(xs[name], self.weights[name], None, s, p)
         out["fc"] = F.linear(xs["fc"], self.fc_w, self.fc_b)
         return out
+
+
+class EncryptedLinearGraph:
+    """The online phase of ``SharedLinearLayers.forward`` captured once in a CUDA graph (the ~330 launches of one encrypted
+    image are latency-bound at batch 1).  The Beaver triples live in static buffers: the offline phase generates fresh
+    triples (crypto provider, Philox + ring GEMM) and copies them into those buffers, the online phase is one graph replay.
+    The crypto-store bookkeeping (peek in spdz_mask / pop in spdz_compute, primitives.py:52-102) runs at capture time."""
+
+    def __init__(self, net: SharedLinearLayers, xs, batch=1):
+        self.net, self.xs, self.batch = net, xs, batch
+        net.preprocess(batch, 1)
+        # the triples the capture is going to consume, in consumption order, per party
+        self.static = []
+        for _name, shapes in triple_shapes(batch, net.ncls):
+            self.static.append([p.crypto_store.get_keys(op="matmul", shapes=shapes, remove=False) for p in net.parties])
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net.forward(xs)  # warm-up: loads kernels, sizes the caching allocator
+        torch.cuda.current_stream().wait_stream(side)
+        self._refill_store()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = net.forward(xs)
+
+    def _refill_store(self):
+        for (_name, shapes), per_party in zip(triple_shapes(self.batch, self.net.ncls), self.static):
+            for p, tri in zip(self.net.parties, per_party):
+                p.crypto_store.add_primitives("matmul", shapes, [tri])
+
+    def offline(self):
+        """fresh triples for the next image, written into the static buffers"""
+        prov, parties = self.net.provider, self.net.parties
+        for (_name, shapes), per_party in zip(triple_shapes(self.batch, self.net.ncls), self.static):
+            fresh = prov.build_triple("matmul", shapes)
+            for j in range(len(parties)):
+                for dst, src in zip(per_party[j], fresh[j]):
+                    dst.copy_(src, non_blocking=True)
+
+    def online(self):
+        self.graph.replay()
+        return self.out

@@ -220,9 +220,67 @@ def gen_train():
     )
 
 
+def gen_fss():
+    """Execute the reference's fss.py (DIF keygen / eval, the H PRG, compress / uncompress) with stand-ins for the modules
+    that cannot be imported here: ``shaloop`` -> hashlib (SHA-256 / SHA-512 of each 16-byte row), PySyft runtime -> stubs."""
+    import hashlib
+    import importlib.util
+
+    def sha_loop(name):
+        def f(x, out):
+            for i in range(x.shape[0]):
+                out[i] = np.frombuffer(getattr(hashlib, name)(x[i].tobytes()).digest(), dtype=np.uint8)
+        return f
+
+    sys.modules["shaloop"] = types.SimpleNamespace(sha256_loop_func=sha_loop("sha256"), sha512_loop_func=sha_loop("sha512"))
+    sy = types.ModuleType("syft")
+    sy.exceptions = types.ModuleType("syft.exceptions")
+    sy.exceptions.EmptyCryptoPrimitiveStoreError = type("EmptyCryptoPrimitiveStoreError", (Exception,), {})
+    sy.workers = types.ModuleType("syft.workers")
+    sy.workers.websocket_client = types.ModuleType("syft.workers.websocket_client")
+    sy.workers.websocket_client.WebsocketClientWorker = type("WebsocketClientWorker", (), {})
+    sy.generic = types.ModuleType("syft.generic")
+    sy.generic.utils = types.ModuleType("syft.generic.utils")
+    sy.generic.utils.allow_command = lambda f: f
+    sy.generic.utils.remote = lambda f, location=None: f
+    for name, mod in (("syft", sy), ("syft.exceptions", sy.exceptions), ("syft.workers", sy.workers),
+                      ("syft.workers.websocket_client", sy.workers.websocket_client), ("syft.generic", sy.generic),
+                      ("syft.generic.utils", sy.generic.utils)):
+        sys.modules[name] = mod
+    path = os.path.join(REF, "syft/frameworks/torch/mpc/fss.py")
+    src = open(path).read()
+    # numpy >= 2 (NEP 50) refuses ``(-1) ** uint64_array``; under the reference's numpy 1.x the python int was value-cast and
+    # the power promoted to float64.  Executing the same expression with an explicit float64 base reproduces that result.
+    src = src.replace("(-1) **", "np.float64(-1) **")
+    fss = types.ModuleType("ref_fss")
+    fss.__file__ = path
+    exec(compile(src, path, "exec"), fss.__dict__)
+    np.random.seed(1234)
+    n_values = 24
+    with np.errstate(all="ignore"):
+        alpha, s00, s01, *rest = fss.DIF.keygen(n_values)
+    cw, leaf = rest[:-1], rest[-1]
+    out = {"alpha": alpha, "s00": s00, "s01": s01, "leaf": leaf}
+    for i, c in enumerate(cw):
+        out[f"tauL{i}"], out[f"tL{i}"], out[f"tauR{i}"], out[f"tR{i}"] = (np.asarray(v) for v in c[:4])
+        out[f"sig{i}"], out[f"s{i}"] = c[4], c[5]
+    # inputs around alpha: equal, +-1, extremes, random
+    x = np.concatenate([alpha[:6], alpha[6:12] + 1, alpha[12:18] - 1, np.array([0, 2 ** 32 - 1, 1, 2 ** 31, 2 ** 31 - 1, 12345], dtype=np.uint64)])
+    x = x % (2 ** 32)
+    with np.errstate(all="ignore"):
+        e0 = fss.DIF.eval(0, x.copy(), s00, *cw, leaf)
+        e1 = fss.DIF.eval(1, x.copy(), s01, *cw, leaf)
+    assert np.array_equal((e0 + e1), (x <= alpha).astype(np.int64)), (e0 + e1, x <= alpha)
+    out["x"], out["e0"], out["e1"] = x, e0, e1
+    seed = np.stack([s00[:, :4], s01[:, :4]])[0]
+    out["H_in"], out["H_out"] = seed.copy(), fss.H(seed.copy()).copy()
+    np.savez_compressed(os.path.join(HERE, "fss_dif.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_preconv()
     gen_spdz()
     gen_newton()
     gen_train()
+    gen_fss()
     print("golden fixtures written to", HERE)

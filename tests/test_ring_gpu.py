@@ -286,3 +286,27 @@ def test_int8_limb_tensor_core_gemm_equals_imad_gemm(ring, rows, K, N):
     finally:
         ops.USE_TENSOR_CORES = old
     assert torch.equal(ops.matmul(cu(A2), cu(B2)).cpu(), ref)
+
+
+def test_encrypted_linear_graph_replay_is_bit_exact(ring):
+    """CUDA-graph replay of the online phase with triples refreshed into static buffers == eager protocol on the same triples."""
+    from primia_b200.ring.resnet import EncryptedLinearGraph, SharedLinearLayers, triple_shapes
+
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", DEV), seed=5)
+    net = SharedLinearLayers(parties, prov, 10, 16)
+    xs = net.make_inputs(1)
+    eg = EncryptedLinearGraph(net, xs, 1)
+    eg.offline()
+    torch.cuda.synchronize()
+    # eager run on clones of exactly these triples
+    for (_n, shapes), per_party in zip(triple_shapes(1, 3), eg.static):
+        for p, tri in zip(parties, per_party):
+            p.crypto_store.add_primitives("matmul", shapes, [tuple(t.clone() for t in tri)])
+    ref = net.forward(xs)
+    ref = {k: [s.clone() for s in v.child.child] for k, v in ref.items()}
+    out = eg.online()
+    torch.cuda.synchronize()
+    for k in ("conv1", "layer2.0.conv1", "layer4.1.conv2", "fc"):
+        for j in range(2):
+            assert torch.equal(out[k].child.child[j], ref[k][j]), k
