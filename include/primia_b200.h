@@ -99,6 +99,35 @@ int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t*
 int pm_nchw_to_pc_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);
 int pm_pc_to_nchw_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);
 
+/* ----- function secret sharing: the comparison behind ReLU and max-pool on shares (protocol="fss").
+ * Key material of n comparison instances, structure-of-arrays with row stride `stride` (>= n) so that a store can hand out
+ * sub-ranges of a larger pool:  s0 [2][stride] (party's root seed, 2 x uint64), bits [32][stride] (uint8: tauL | tL<<1 |
+ * tauR<<2 | tR<<3, the compressed correction bits fss.py:431-455), sigma_cw [32][2][stride], s_cw [32][2][stride],
+ * leaf [33][stride] int32. */
+/* the PRG H  syft/frameworks/torch/mpc/fss.py:553-601 : SHA-512 of each 16-byte seed (seed [2][n]) -> out [8][n], the digest
+ * as little-endian uint64 words (the reference calls the external `shaloop.sha512_loop_func`). */
+int pm_fss_prg_sha512(const uint64_t* seed, size_t n, uint64_t* out, pm_stream_t s);
+/* DIF.keygen  fss.py:341-399.  alpha [n] (values < 2^32), seeds [2 parties][2 words][n] (word 0 < 2^63, randbit :498-505).
+ * Both parties receive the same correction words; party b's key is (seeds[b], bits, sigma_cw, s_cw, leaf). */
+int pm_fss_dif_keygen(const uint64_t* alpha, const uint64_t* seeds, size_t n, size_t stride, uint8_t* bits,
+                      uint64_t* sigma_cw, uint64_t* s_cw, int32_t* leaf, pm_stream_t s);
+/* DIF.eval  fss.py:401-428 (reached through evaluate / comp_evaluate :208-275): out[i] = party b's int64 share of
+ * [ (x_masked[i] mod 2^32) <= alpha[i] ]. */
+int pm_fss_dif_eval(int b, const int64_t* x_masked, const uint64_t* s0, const uint8_t* bits, const uint64_t* sigma_cw,
+                    const uint64_t* s_cw, const int32_t* leaf, size_t n, size_t stride, int64_t* out, pm_stream_t s);
+/* mask_builder  fss.py:189-204 : r_j = x1_j - x2_j + alpha_j ; x1 or x2 may be NULL (a public 0 operand) */
+int pm_fss_mask_i64(const int64_t* x1, const int64_t* x2, const int64_t* alpha_share, int64_t* r, size_t n, pm_stream_t s);
+/* opening of the masked difference  fss.py:158 : out = (local + peer) mod 2^32 ; `peer` may be peer-mapped (NVLink) */
+int pm_fss_open_mod32_i64(const int64_t* local, const int64_t* peer, int64_t* out, size_t n, pm_stream_t s);
+/* conditions raw 64-bit random words into keygen's randomness (fss.py:346,354,498-505; primitives.py:245-251), in place:
+ * alpha, mask -> [0,2^32); seeds [2][2][n] word 0 -> [0,2^63); alpha0 = (alpha - mask) mod 2^32 (party 0's share of alpha,
+ * party 1 holds mask). */
+int pm_fss_condition_randomness(uint64_t* alpha, uint64_t* mask, uint64_t* seeds, int64_t* alpha0, size_t n, pm_stream_t s);
+/* _pre_pool  syft/frameworks/torch/nn/functional.py:312-390 : x [B,C,H,W] -> [B,C,Ho*Wo,k*k] (zero padding) */
+int pm_pre_pool_i64(const int64_t* x, int B, int C, int H, int W, int k, int stride, int pad, int64_t* out, pm_stream_t s);
+/* t[..., start:start+len] of a [rows, L] tensor made contiguous (max_half_split halves, functional.py:489-508) */
+int pm_slice_lastdim_i64(const int64_t* src, size_t rows, int L, int start, int len, int64_t* dst, pm_stream_t s);
+
 /* ===================================================================== path T : float training */
 /* Layout: activations NHWC; conv weights KRSC ([Cout][kh][kw][Cin]); fp32 ("_f32", parity mode) or
  * bf16 activations with fp32 accumulation ("_bf16", throughput mode). Replaces the ATen CPU ops the

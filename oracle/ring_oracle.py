@@ -247,3 +247,186 @@ def linear_shared(x_sh, w_sh, b_sh, triple_sh, base, pf):
     z = spdz_mul("matmul", x_sh, wt, triple_sh)
     z = truncate(z, base, pf)
     return [z[j] + b_sh[j] for j in range(2)]
+
+
+# --------------------------------------------------------------------------- E12 / E13 (comparison-based ops, protocol="fss")
+def fss_le_shared(x1_sh, x2_sh, fss_key, alpha_sh):
+    """fss.le(x1, x2) -- syft/frameworks/torch/mpc/fss.py:97-185,279-283: shares of [x1 <= x2] (0/1, unscaled).
+    fss_key / alpha_sh: explicit DIF key material for x.numel() instances (oracle/fss_oracle.py layout)."""
+    from . import fss_oracle as F
+
+    shape = x1_sh[0].shape
+    out = F.fss_le([t.reshape(-1).numpy() for t in x1_sh], [t.reshape(-1).numpy() for t in x2_sh], fss_key, alpha_sh)
+    return [torch.from_numpy(o.astype("int64")).reshape(shape) for o in out]
+
+
+def relu_shared(x_sh, fss_key, alpha_sh, triple_sh):
+    """AdditiveSharingTensor.relu, protocol "fss" -- additive_shared.py:922-925: ``zero = self - self;
+    self * (self >= zero)`` with ``>=`` = fss.le(zero, self) (:950-952) and ``*`` an elementwise Beaver mul
+    (no truncation: the comparison result is an unscaled 0/1)."""
+    zero = [s - s for s in x_sh]
+    c = fss_le_shared(zero, x_sh, fss_key, alpha_sh)
+    return spdz_mul("mul", x_sh, c, triple_sh)
+
+
+def pre_pool(x: torch.Tensor, k: int, stride: int, padding: int):
+    """_pre_pool -- nn/functional.py:312-390 (dilation 1), vectorised: [B,C,H,W] -> [B,C,M,k*k], zero padding."""
+    B, C, H, W = x.shape
+    Ho = int(((H + 2 * padding - (k - 1) - 1) / stride) + 1)
+    Wo = int(((W + 2 * padding - (k - 1) - 1) / stride) + 1)
+    if padding:
+        x = torch.nn.functional.pad(x, (padding, padding, padding, padding), "constant")
+        H, W = H + 2 * padding, W + 2 * padding
+    pattern = (torch.arange(k).view(k, 1) * W + torch.arange(k).view(1, k)).reshape(-1)
+    offset = (torch.arange(Ho).view(Ho, 1) * stride * W + torch.arange(Wo).view(1, Wo) * stride).reshape(-1)
+    idx = offset.view(-1, 1) + pattern.view(1, -1)
+    return x.reshape(B, C, -1)[:, :, idx], B, C, Ho, Wo
+
+
+def max_pool2d_shared(x_sh, k, stride, padding, fss_keys, alpha_shs, triples, trace=None):
+    """max_pool2d on shares -- nn/functional.py:420-437,460-525 mode "max" for k*k in (4, 9): the binary-tree
+    ``max_half_split`` (left + (right >= left) * (right - left)), one FSS comparison + one Beaver mul per step.
+    fss_keys/alpha_shs/triples: one entry per step, in execution order."""
+    pre = [pre_pool(s, k, stride, padding) for s in x_sh]
+    im = [p[0] for p in pre]
+    _, B, C, Ho, Wo = pre[0]
+    step = iter(range(len(triples)))
+
+    def select(left, right):
+        i = next(step)
+        if trace is not None:
+            trace.append(tuple(left[0].shape))
+        c = fss_le_shared(left, right, fss_keys[i], alpha_shs[i])          # right >= left
+        diff = [right[j] - left[j] for j in range(2)]
+        prod = spdz_mul("mul", c, diff, triples[i])
+        return [left[j] + prod[j] for j in range(2)]
+
+    def max_half_split(t, half):
+        return select([s[..., :half] for s in t], [s[..., half:] for s in t])
+
+    if im[0].shape[-1] == 4:
+        res = max_half_split(max_half_split(im, 2), 1)
+    elif im[0].shape[-1] == 9:
+        res = max_half_split([s[..., :8] for s in im], 4)
+        res = max_half_split(res, 2)
+        left = max_half_split(res, 1)
+        res = select(left, [s[..., 8:] for s in im])
+    else:
+        raise NotImplementedError("the reference falls back to AST.max for other kernels; ResNet-18 uses 3x3")
+    return [r.reshape(B, C, Ho, Wo).contiguous() for r in res]
+
+
+# --------------------------------------------------------------------------- E1: the whole encrypted forward
+class Tape:
+    """Explicit randomness of one encrypted forward, in consumption order (one FIFO per kind):
+    ``triples``  [(op, [(a0,b0,c0),(a1,b1,c1)])], ``consts`` [[s0, s1]] (sharings of public constants,
+    additive_shared.py:473-487), ``fss`` [(key dict, [alpha0, alpha1])] (oracle/fss_oracle.py layout)."""
+
+    def __init__(self, triples, consts, fss):
+        self.triples, self.consts, self.fss = list(triples), list(consts), list(fss)
+
+    def triple(self, op, x_shape=None, y_shape=None):
+        got_op, tri = self.triples.pop(0)
+        assert got_op == op, (got_op, op)
+        if x_shape is not None:
+            assert tuple(tri[0][0].shape) == tuple(x_shape) and tuple(tri[0][1].shape) == tuple(y_shape), \
+                (tri[0][0].shape, tri[0][1].shape, x_shape, y_shape)
+        return tri
+
+    def const(self):
+        return self.consts.pop(0)
+
+    def fss_keys(self, n):
+        key, alpha = self.fss.pop(0)
+        assert key["leaf"].shape[1] == n, (key["leaf"].shape, n)
+        return key, alpha
+
+    def exhausted(self):
+        return not (self.triples or self.consts or self.fss)
+
+
+def batch_norm_eval_taped(x_sh, mean_sh, var_sh, gamma_sh, beta_sh, tape: Tape, base, pf):
+    """batch_norm (eval, functional.py:44-75) drawing its randomness from the tape in the order the reference's
+    expression evaluation consumes it: iteration 0: const ; iterations 1..79: x*x, v*(xx), const, y*x ; then the two muls."""
+    C = var_sh[0].shape[0]
+    consts, triples = [], []
+    for i in range(80):
+        if i == 0:
+            consts.append(tape.const())
+            triples.append(None)
+        else:
+            t0, t1 = tape.triple("mul", (C,), (C,)), tape.triple("mul", (C,), (C,))
+            consts.append(tape.const())
+            triples.append((t0, t1, tape.triple("mul", (C,), (C,))))
+    B, _, H, W = x_sh[0].shape
+    P = B * H * W
+    tri_norm, tri_affine = tape.triple("mul", (C,), (P, C)), tape.triple("mul", (P, C), (C,))
+    return batch_norm_eval_shared(x_sh, mean_sh, var_sh, gamma_sh, beta_sh, consts, triples, tri_norm, tri_affine, base, pf)
+
+
+def relu_taped(x_sh, tape: Tape):
+    key, alpha = tape.fss_keys(x_sh[0].numel())
+    return relu_shared(x_sh, key, alpha, tape.triple("mul", x_sh[0].shape, x_sh[0].shape))
+
+
+def max_pool2d_taped(x_sh, k, stride, padding, tape: Tape):
+    B, C, H, W = x_sh[0].shape
+    M = ((H + 2 * padding - k) // stride + 1) * ((W + 2 * padding - k) // stride + 1)
+    widths = {4: [2, 1], 9: [4, 2, 1, 1]}[k * k]
+    keys, alphas, tris = [], [], []
+    for w in widths:
+        key, alpha = tape.fss_keys(B * C * M * w)
+        keys.append(key)
+        alphas.append(alpha)
+        tris.append(tape.triple("mul", (B, C, M, w), (B, C, M, w)))
+    return max_pool2d_shared(x_sh, k, stride, padding, keys, alphas, tris)
+
+
+def resnet18_forward_shared(P, x_sh, tape: Tape, base=10, pf=16, input_size=224, taps=None):
+    """inference.py:288-314 on shares: ResNet._forward_impl (torchlib/models.py:466-482) with ``model.pool`` and
+    ``model.relu`` swapped (inference.py:289: the stem runs conv -> bn -> MAX-POOL -> RELU), BasicBlock.forward
+    (:268-284), AvgPool2d(input_size/32), flatten, fc.  P: {state_dict key: [share0, share1]} of the encoded
+    parameters and BN buffers.  taps (optional dict) receives named intermediate shares."""
+
+    def conv(x, name, stride, pad):
+        w = P[name + ".weight"]
+        B, C, H, W = x[0].shape
+        Co, _, kh, kw = w[0].shape
+        Ho = (H + 2 * pad - kh) // stride + 1
+        tri = tape.triple("matmul", (B, Ho * Ho, C * kh * kw), (C * kh * kw, Co))
+        return conv2d_shared(x, w, tri, stride, pad, base, pf)
+
+    def bn(x, name):
+        return batch_norm_eval_taped(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"],
+                                     P[name + ".bias"], tape, base, pf)
+
+    def tap(name, x):
+        if taps is not None:
+            taps[name] = [s.clone() for s in x]
+        return x
+
+    x = tap("conv1", conv(x_sh, "conv1", 2, 3))
+    x = tap("bn1", bn(x, "bn1"))
+    x = tap("pool", max_pool2d_taped(x, 3, 2, 1, tape))
+    x = tap("relu", relu_taped(x, tape))
+    inplanes = 64
+    for li, (planes, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi in range(2):
+            st = stride if bi == 0 else 1
+            pre = f"layer{li}.{bi}"
+            identity = x
+            out = conv(x, pre + ".conv1", st, 1)
+            out = bn(out, pre + ".bn1")
+            out = relu_taped(out, tape)
+            out = conv(out, pre + ".conv2", 1, 1)
+            out = bn(out, pre + ".bn2")
+            if st != 1 or inplanes != planes:
+                identity = bn(conv(x, pre + ".downsample.0", st, 0), pre + ".downsample.1")
+            out = [out[j] + identity[j] for j in range(2)]
+            x = tap(pre, relu_taped(out, tape))
+            inplanes = planes
+    x = avg_pool_shared(x, input_size // 32)
+    x = [s.reshape(s.shape[0], -1) for s in x]
+    B = x[0].shape[0]
+    ncls = P["fc.weight"][0].shape[0]
+    return linear_shared(x, P["fc.weight"], P["fc.bias"], tape.triple("matmul", (B, 512), (512, ncls)), base, pf)

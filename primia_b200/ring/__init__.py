@@ -10,3 +10,5 @@ from .spdz import (  # noqa: F401
 )
 from .tensors import AdditiveSharingTensor, FixedPrecisionTensor  # noqa: F401
 from . import functional  # noqa: F401
+from . import fss  # noqa: F401
+from .resnet import EncryptedResNet18  # noqa: F401

@@ -89,6 +89,42 @@ def avg_pool2d(input: FixedPrecisionTensor, kernel_size, stride=None, padding=0)
     return input._new(input.child.map(lambda s: ops.avgpool(s, kernel_size)))
 
 
+def relu(input: FixedPrecisionTensor, inplace=False):
+    """torch.nn.functional.relu on FPT > AST: AdditiveSharingTensor.relu (additive_shared.py:896-897,922-925)"""
+    return input.relu()
+
+
+def max_pool2d(input: FixedPrecisionTensor, kernel_size=2, stride=2, padding=0, dilation=1, ceil_mode=None,
+               return_indices=None):
+    """functional.py:420-437 -> _pool2d :460-525, mode "max": _pre_pool per party, the max_half_split binary tree
+    (one FSS comparison + one Beaver mul per step, on the AST: no truncation), _post_pool reshape."""
+    from . import fss
+
+    assert dilation == 1
+    x = input.child
+    B, C, H, W = x.shape
+    Ho, Wo = (H + 2 * padding - kernel_size) // stride + 1, (W + 2 * padding - kernel_size) // stride + 1
+    im = x.map(lambda s: fss.pre_pool(s, kernel_size, stride, padding))
+
+    def select(left, right):
+        return left + (right >= left) * (right - left)
+
+    def max_half_split(t, L, half):
+        return select(t.slice_lastdim(0, half), t.slice_lastdim(half, L - half))
+
+    kk = kernel_size * kernel_size
+    if kk == 4:
+        res = max_half_split(max_half_split(im, 4, 2), 2, 1)
+    elif kk == 9:
+        res = select(im.slice_lastdim(0, 4), im.slice_lastdim(4, 4))    # max_half_split(im[..., :8], 4)
+        res = max_half_split(res, 4, 2)
+        left = max_half_split(res, 2, 1)
+        res = select(left, im.slice_lastdim(8, 1))
+    else:
+        raise NotImplementedError("max_pool2d on shares: kernel 2 or 3 (the reference's fast paths, functional.py:501-508)")
+    return input._new(res.reshape(B, C, Ho, Wo))
+
+
 def linear(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias: FixedPrecisionTensor = None):
     """functional.py:10-14 -> native_linear: input.matmul(weight.t()) + bias"""
     wt = weight._new(weight.child.map(lambda s: s.t().contiguous()))

@@ -126,3 +126,78 @@ class EncryptedLinearGraph:
     def online(self):
         self.graph.replay()
         return self.out
+
+
+class EncryptedResNet18:
+    """The reference's encrypted-inference model (inference.py:279-321): every parameter AND buffer of the ResNet-18
+    fix-precision-encoded and secret-shared between model_owner and data_owner (hook.py:738-765 iterates parameters and
+    buffers), evaluated layer by layer on shares.  ``forward`` is ResNet._forward_impl (torchlib/models.py:466-482) with
+    ``model.pool`` and ``model.relu`` swapped as inference.py:289 does (stem: conv -> bn -> max-pool -> relu).
+
+    ``shared`` maps state_dict keys to FixedPrecisionTensor > AdditiveSharingTensor; build it with ``from_state_dict``
+    (encode + share on the GPU) or pass explicit shares (parity tests)."""
+
+    def __init__(self, shared, parties, provider, base=10, precision_fractional=16, input_size=224):
+        self.P, self.parties, self.provider = shared, parties, provider
+        self.base, self.pf, self.input_size = base, precision_fractional, input_size
+        self.taps = None
+
+    @classmethod
+    def from_state_dict(cls, state_dict, parties, provider, base=10, precision_fractional=16, input_size=224, rng=None):
+        """model.fix_precision(**kw).share(*workers, **kw) -- inference.py:280-286"""
+        dev = parties[0].device
+        shared = {}
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue  # an integer counter: never read by the eval forward
+            t = v.detach().to(dev, torch.float32).contiguous()
+            shared[k] = FixedPrecisionTensor.fix_precision(t, base, precision_fractional).share(
+                *parties, crypto_provider=provider, rng=rng)
+        return cls(shared, parties, provider, base, precision_fractional, input_size)
+
+    def share_input(self, x: torch.Tensor, rng=None):
+        """data.fix_precision(**kw).share(*workers, **kw) -- inference.py:307-311"""
+        x = x.to(self.parties[0].device, torch.float32).contiguous()
+        return FixedPrecisionTensor.fix_precision(x, self.base, self.pf).share(*self.parties, crypto_provider=self.provider,
+                                                                               rng=rng)
+
+    def _tap(self, name, x):
+        if self.taps is not None:
+            self.taps[name] = [s.clone() for s in x.child.child]
+        return x
+
+    def _bn(self, x, name):
+        P = self.P
+        return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"])
+
+    def forward(self, x: FixedPrecisionTensor) -> FixedPrecisionTensor:
+        P = self.P
+        x = self._tap("conv1", F.conv2d(x, P["conv1.weight"], None, 2, 3))
+        x = self._tap("bn1", self._bn(x, "bn1"))
+        x = self._tap("pool", F.max_pool2d(x, 3, 2, 1))       # model.relu <- model.pool (inference.py:289)
+        x = self._tap("relu", F.relu(x))                       # model.pool <- model.relu
+        inplanes = 64
+        for li, (planes, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+            for bi in range(2):
+                st = stride if bi == 0 else 1
+                pre = f"layer{li}.{bi}"
+                identity = x
+                out = F.conv2d(x, P[pre + ".conv1.weight"], None, st, 1)
+                out = F.relu(self._bn(out, pre + ".bn1"))
+                out = F.conv2d(out, P[pre + ".conv2.weight"], None, 1, 1)
+                out = self._bn(out, pre + ".bn2")
+                if st != 1 or inplanes != planes:
+                    identity = self._bn(F.conv2d(x, P[pre + ".downsample.0.weight"], None, st, 0), pre + ".downsample.1")
+                out = out + identity
+                x = self._tap(pre, F.relu(out))
+                inplanes = planes
+        x = F.avg_pool2d(x, self.input_size // 32)
+        x = x._new(x.child.reshape(x.shape[0], -1))            # torch.flatten(x, 1)
+        return F.linear(x, P["fc.weight"], P["fc.bias"])
+
+    __call__ = forward
+
+    def predict(self, x: torch.Tensor):
+        """one pass of the loop body of inference.py:292-317: share the image, forward, reconstruct, decode, argmax"""
+        out = self.forward(self.share_input(x)).get().float_prec()
+        return out, out.argmax(dim=1)

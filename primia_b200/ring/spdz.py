@@ -49,8 +49,33 @@ class PrimitiveStorage:
             "mul": defaultdict(list),
             "matmul": defaultdict(list),
         }
+        self._fss = []  # pools of DIF keys (ring/fss.py FSSKeys), consumed from the front
 
-    def get_keys(self, op: str, shapes, n_instances: int = 1, remove: bool = True, **kwargs):
+    def _get_fss_keys(self, n_instances: int, remove: bool):
+        """FSS half of get_keys (primitives.py:52-102): the next ``n_instances`` comparison keys; ``remove`` burns them."""
+        from .fss import OP, FSSKeys
+
+        self._fss = [c for c in self._fss if c.available > 0]
+        avail = sum(c.available for c in self._fss)
+        if avail < n_instances:
+            raise EmptyCryptoPrimitiveStoreError(self, avail if avail else -1, n_instances, op=OP)
+        if self._fss[0].available < n_instances:  # the request spans pools: the reference keeps one concatenated array
+            self._fss = [FSSKeys.cat(self._fss)]
+        head = self._fss[0]
+        win = head.window(n_instances)
+        if remove:
+            head.off += n_instances
+        return win
+
+    def add_fss_keys(self, keys):
+        self._fss.append(keys)
+
+    def fss_available(self):
+        return sum(c.available for c in self._fss)
+
+    def get_keys(self, op: str, shapes=None, n_instances: int = 1, remove: bool = True, **kwargs):
+        if op == "fss_comp":
+            return self._get_fss_keys(n_instances, remove)
         stack = self._stacks[op][_key(shapes)]
         if len(stack) < n_instances:
             raise EmptyCryptoPrimitiveStoreError(self, len(stack) if stack else -1, n_instances, op=op, shapes=_key(shapes))
@@ -65,7 +90,8 @@ class PrimitiveStorage:
         return len(self._stacks[op][_key(shapes)])
 
     def nbytes(self):
-        return sum(t.numel() * 8 for st in self._stacks.values() for lst in st.values() for tri in lst for t in tri)
+        return (sum(t.numel() * 8 for st in self._stacks.values() for lst in st.values() for tri in lst for t in tri)
+                + sum(c.nbytes() for c in self._fss))
 
 
 class Party:
@@ -110,7 +136,23 @@ class TripleProvider:
             out[0][i], out[1][i] = s0, s1
         return out
 
-    def provide_primitives(self, op: str, shapes, parties, n_instances: int = 1, **_):
+    def build_fss_keys(self, n_instances: int):
+        """build_fss_keys / build_separate_fss_keys -- primitives.py:237-253 (DIF.keygen on the provider's GPU)"""
+        from .fss import build_fss_keys
+
+        self.counter += 3
+        return build_fss_keys(n_instances, self.provider.device, self.seed, self.counter - 2)
+
+    def provide_primitives(self, op: str, shapes=None, parties=None, n_instances: int = 1, **_):
+        if op == "fss_comp":
+            keys = self.build_fss_keys(n_instances)
+            for j, p in enumerate(parties):
+                k = keys[j] if p.device == self.provider.device else keys[j].to(p.device)
+                self.generated_bytes += k.nbytes()
+                p.crypto_store.add_fss_keys(k)
+            if any(p.device != self.provider.device for p in parties):
+                torch.cuda.synchronize(self.provider.device)
+            return
         for _i in range(n_instances):
             tri = self.build_triple(op, shapes)
             for j, p in enumerate(parties):

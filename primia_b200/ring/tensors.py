@@ -23,6 +23,9 @@ class ShareRNG:
         return ops.share_gen(q, self.seed, self.counter)
 
 
+DEFAULT_RNG = ShareRNG()  # one stream per process: every fresh sharing draws a new Philox offset
+
+
 class AdditiveSharingTensor:
     """2-party additive sharing over Z_2^64; ``child[j]`` is party j's share on party j's GPU."""
 
@@ -30,13 +33,13 @@ class AdditiveSharingTensor:
         self.child = list(shares)
         self.parties = list(parties)
         self.provider = provider
-        self.rng = rng or ShareRNG()
+        self.rng = rng or DEFAULT_RNG
 
     # -- construction / reconstruction
     @classmethod
     def share_secret(cls, q: torch.Tensor, parties, provider=None, rng=None):
         """additive_shared.py:317-365"""
-        rng = rng or ShareRNG()
+        rng = rng or DEFAULT_RNG
         s0, s1 = rng.share(q)
         shares = [s0.to(parties[0].device), s1.to(parties[1].device)]
         return cls(shares, parties, provider, rng)
@@ -92,6 +95,42 @@ class AdditiveSharingTensor:
 
     def map(self, fn):
         return self._new([fn(s) for s in self.child])
+
+    def numel(self):
+        return self.child[0].numel()
+
+    # -- comparisons, protocol "fss" (additive_shared.py:939-974): shares of an unscaled 0/1
+    def __le__(self, other):
+        from . import fss
+
+        return self._new(fss.le(self.child, other.child, self.parties, self.provider))
+
+    def __ge__(self, other):
+        from . import fss
+
+        return self._new(fss.le(other.child, self.child, self.parties, self.provider))
+
+    def __gt__(self, other):
+        return (other + 1) <= self
+
+    def __lt__(self, other):
+        return (self + 1) <= other
+
+    def relu(self):
+        """additive_shared.py:922-925"""
+        zero = self - self
+        return self * (self >= zero)
+
+    __mul__ = mul
+
+    def slice_lastdim(self, start, length):
+        """t[..., start:start+length] on every share"""
+        from . import fss
+
+        return self._new([fss.slice_lastdim(s, start, length) for s in self.child])
+
+    def reshape(self, *shape):
+        return self._new([s.reshape(*shape) for s in self.child])
 
 
 class FixedPrecisionTensor:
@@ -162,6 +201,10 @@ class FixedPrecisionTensor:
     # precision.py:419-463
     def matmul(self, other):
         return self._new(self.child.matmul(other.child)).truncate(other.precision_fractional)
+
+    def relu(self):
+        """F.relu on an FPT is forwarded to the child (precision.py:864-905 finds no FPT override): no rescale, no truncation"""
+        return self._new(self.child.relu())
 
     def reciprocal(self, method="newton"):
         """precision.py:507-518 -- literally (80 iterations, C = 20)."""

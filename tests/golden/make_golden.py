@@ -14,6 +14,8 @@ Fixtures
   ring_spdz.npz      spdz_mask/spdz_compute/triple_mat_mul (syft/frameworks/torch/mpc/spdz.py:22-122)
   ring_newton.npz    control flow of reciprocal(method="newton") run on exact python ints
                      (syft/frameworks/torch/tensors/interpreters/precision.py:507-518)
+  ring_pool.npz      _pre_pool/_post_pool and the op trace of _pool2d's max branch (nn/functional.py:312-525)
+  fss_dif.npz        DIF keygen / eval / H executed from syft/frameworks/torch/mpc/fss.py (shaloop -> hashlib)
   train_ref.npz      torchlib/models.py resnet18: state_dict keys/shapes, logits, loss, grad digests
 """
 import ast
@@ -277,7 +279,103 @@ def gen_fss():
     np.savez_compressed(os.path.join(HERE, "fss_dif.npz"), **out)
 
 
+def gen_pool():
+    """_pre_pool / _post_pool executed on int64 tensors, and the control flow of _pool2d's max branch (which slices are
+    compared, in which order, with which shapes) recorded by running the reference's own ``_pool2d`` over a stand-in
+    AdditiveSharingTensor that computes on the reconstructed value."""
+    fns = extract("syft/frameworks/torch/nn/functional.py", ["_pre_pool", "_post_pool", "_pool2d"])
+    trace = []
+
+    class Loc:
+        def __init__(self, id):
+            self.id = id
+
+    locs = [Loc("alice"), Loc("bob")]
+
+    class AST:
+        """two additive shares; comparisons and products are evaluated on the reconstructed value and re-shared"""
+
+        def __init__(self, child=None, **kw):
+            self.child = child
+            self.locations = locs
+
+        def get_class_attributes(self):
+            return {}
+
+        @property
+        def shape(self):
+            return self.child["alice"].shape
+
+        def _plain(self):
+            return self.child["alice"] + self.child["bob"]
+
+        def _share(self, v):
+            r = torch.full_like(v, 12345)
+            return AST({"alice": r, "bob": v - r})
+
+        def __getitem__(self, idx):
+            trace.append("slice|" + repr(idx).replace("slice(None, None, None)", ":").replace(" ", ""))
+            return AST({k: v[idx] for k, v in self.child.items()})
+
+        def __add__(self, o):
+            trace.append(f"add|{tuple(self.shape)}")
+            return AST({k: self.child[k] + o.child[k] for k in self.child})
+
+        def __sub__(self, o):
+            trace.append(f"sub|{tuple(self.shape)}")
+            return AST({k: self.child[k] - o.child[k] for k in self.child})
+
+        def __ge__(self, o):
+            trace.append(f"ge|{tuple(self.shape)}")
+            return self._share((self._plain() >= o._plain()).long())
+
+        def __mul__(self, o):
+            trace.append(f"mul|{tuple(self.shape)}")
+            return self._share(self._plain() * o._plain())
+
+    class FPT:
+        def __init__(self, **kw):
+            self.child = None
+
+        def get_class_attributes(self):
+            return {}
+
+        def on(self, t, wrap=False):
+            self.child = t
+            return self
+
+    def remote(f, location=None):
+        def g(*a, return_value=False, return_arity=1, **kw):
+            return f(*a, **kw)
+        return g
+
+    sy = types.SimpleNamespace(AdditiveSharingTensor=AST, FixedPrecisionTensor=FPT)
+    ns = {"torch": torch, "sy": sy, "remote": remote}
+    for s_ in fns.values():
+        exec(s_, ns)
+    g = torch.Generator().manual_seed(44)
+    out = {}
+    cases = [(1, 3, 8, 8, 3, 2, 1), (2, 2, 7, 7, 3, 2, 1), (1, 2, 6, 6, 2, 2, 0)]  # (B, C, H, W, k, stride, pad)
+    out["cases"] = np.array(cases, dtype=np.int64)
+    for i, (B, C, H, W, k, st, pd) in enumerate(cases):
+        x = torch.randint(-1000, 1000, (B, C, H, W), dtype=torch.int64, generator=g)
+        im, *params = ns["_pre_pool"](x, k, st, pd, 1)
+        out[f"x{i}"], out[f"im{i}"] = x.numpy(), im.numpy()
+        out[f"post{i}"] = ns["_post_pool"](im.sum(-1), *params).numpy()
+        x0 = rand_i64(g, (B, C, H, W))
+        fp = FPT().on(AST({"alice": x0, "bob": x - x0}))
+        del trace[:]
+        res = ns["_pool2d"](fp, kernel_size=k, stride=st, padding=pd, dilation=1, mode="max")
+        got = res.child._plain()
+        want = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x.double(), (pd, pd, pd, pd)), k, st).long()
+        assert torch.equal(got, want)
+        out[f"max{i}"] = got.numpy()
+        out[f"trace{i}"] = np.array(list(trace))
+    np.savez_compressed(os.path.join(HERE, "ring_pool.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_pool()
     gen_preconv()
     gen_spdz()
     gen_newton()

@@ -109,3 +109,125 @@ def test_avgpool_and_linear_shapes():
     wrap = (2 ** 64) // 49
     diff = (rec - torch.div(exact, 49, rounding_mode="trunc"))
     assert all(min(abs(int(d)), abs(abs(int(d)) - wrap)) <= 2 for d in diff.flatten())
+
+
+def test_pool_restatement_matches_reference_sources():
+    """_pre_pool/_post_pool outputs and the op order of _pool2d's max branch, executed from the reference (ring_pool.npz)."""
+    import numpy as np
+    from oracle import fss_oracle as F
+
+    g = np.load(os.path.join(GOLDEN, "ring_pool.npz"))
+    rng = np.random.default_rng(3)
+    for i, (B, C, H, W, k, st, pd) in enumerate(g["cases"]):
+        x = torch.from_numpy(g[f"x{i}"])
+        im, *_ = R.pre_pool(x, int(k), int(st), int(pd))
+        assert torch.equal(im, torch.from_numpy(g[f"im{i}"]))
+        ref_trace = [t for t in g[f"trace{i}"] if t.startswith("ge|")]
+        shapes = [eval(t.split("|")[1]) for t in ref_trace]
+        x0 = torch.from_numpy(rng.integers(-2 ** 62, 2 ** 62, x.shape))
+        xs = [x0, x - x0]
+        keys, alphas, tris = [], [], []
+        for shp in shapes:
+            n = int(np.prod(shp))
+            alpha = rng.integers(0, 2 ** 32, n, dtype=np.uint64)
+            keys.append(F.dif_keygen(alpha, rng.integers(0, 2 ** 63, (2, 2, n), dtype=np.uint64)))
+            alphas.append(F.split_alpha(alpha, rng.integers(0, 2 ** 32, n, dtype=np.uint64)))
+            a, b = (torch.from_numpy(rng.integers(-2 ** 63, 2 ** 63 - 1, shp)) for _ in range(2))
+            a0, b0, c0 = (torch.from_numpy(rng.integers(-2 ** 63, 2 ** 63 - 1, shp)) for _ in range(3))
+            tris.append([(a0, b0, c0), (a - a0, b - b0, a * b - c0)])
+        trace = []
+        out = R.max_pool2d_shared(xs, int(k), int(st), int(pd), keys, alphas, tris, trace)
+        assert trace == shapes                                   # same comparisons, same order, same shapes
+        assert torch.equal(out[0] + out[1], torch.from_numpy(g[f"max{i}"]))
+
+
+def test_relu_on_shares_reconstructs():
+    import numpy as np
+    from oracle import fss_oracle as F
+
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.integers(-10 ** 6, 10 ** 6, (2, 3, 4, 4)))
+    x.view(-1)[:3] = torch.tensor([0, 1, -1])
+    x0 = torch.from_numpy(rng.integers(-2 ** 62, 2 ** 62, x.shape))
+    n = x.numel()
+    alpha = rng.integers(0, 2 ** 32, n, dtype=np.uint64)
+    key = F.dif_keygen(alpha, rng.integers(0, 2 ** 63, (2, 2, n), dtype=np.uint64))
+    al = F.split_alpha(alpha, rng.integers(0, 2 ** 32, n, dtype=np.uint64))
+    a, b = (torch.from_numpy(rng.integers(-2 ** 63, 2 ** 63 - 1, x.shape)) for _ in range(2))
+    a0, b0, c0 = (torch.from_numpy(rng.integers(-2 ** 63, 2 ** 63 - 1, x.shape)) for _ in range(3))
+    out = R.relu_shared([x0, x - x0], key, al, [(a0, b0, c0), (a - a0, b - b0, a * b - c0)])
+    assert torch.equal(out[0] + out[1], torch.clamp(x, min=0))
+
+
+class GenTape(R.Tape):
+    """a tape that draws its randomness on demand (numpy), for oracle-only end-to-end checks"""
+
+    def __init__(self, seed=0):
+        import numpy as np
+
+        self.rng = np.random.default_rng(seed)
+        self.n_triples = self.n_consts = self.n_fss = 0
+
+    def _r(self, shape):
+        return torch.from_numpy(self.rng.integers(-2 ** 63, 2 ** 63 - 1, tuple(shape)))
+
+    def triple(self, op, x_shape=None, y_shape=None):
+        self.n_triples += 1
+        a, b = self._r(x_shape), self._r(y_shape)
+        c = torch.matmul(a, b) if op == "matmul" else a * b
+        a0, b0, c0 = self._r(a.shape), self._r(b.shape), self._r(c.shape)
+        return [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+
+    def const(self):
+        raise NotImplementedError  # set by the caller: needs the encoded constant
+
+    def fss_keys(self, n):
+        import numpy as np
+        from oracle import fss_oracle as F
+
+        self.n_fss += n
+        alpha = self.rng.integers(0, 2 ** 32, n, dtype=np.uint64)
+        key = F.dif_keygen(alpha, self.rng.integers(0, 2 ** 63, (2, 2, n), dtype=np.uint64))
+        return key, F.split_alpha(alpha, self.rng.integers(0, 2 ** 32, n, dtype=np.uint64))
+
+
+def test_full_encrypted_forward_oracle_tracks_plaintext_model():
+    """resnet18_forward_shared (the restatement of inference.py:279-321) on a 32x32 image at base 10, pf 4: the decoded
+    logits follow the plaintext model with pool/relu swapped (inference.py:289)."""
+    from oracle import train_oracle as O
+
+    base, pf, size = 10, 4, 32
+    torch.manual_seed(42)
+    model = O.ResNet18(input_size=size)
+    gg = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=gg) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=gg) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.num_features, generator=gg) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.num_features, generator=gg) * 0.1)
+    model.eval()
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(1, 3, size, size, generator=g)
+    tape = GenTape(1)
+    q21 = torch.tensor([21 * base ** pf], dtype=torch.int64)
+
+    def const():
+        tape.n_consts += 1
+        s0 = tape._r((1,))
+        return [s0, q21 - s0]
+
+    tape.const = const
+    sh = lambda q: [(s0 := tape._r(q.shape)), q - s0]
+    P = {k: sh(R.encode(v.float().contiguous(), base, pf)) for k, v in model.state_dict().items()
+         if not k.endswith("num_batches_tracked")}
+    out = R.resnet18_forward_shared(P, sh(R.encode(img, base, pf)), tape, base, pf, size)
+    logits = R.decode(out[0] + out[1], base, pf)
+    with torch.no_grad():
+        model.pool, model.relu = model.relu, model.pool
+        want = model(img)
+    assert (logits - want).abs().max() < 0.15, (logits, want)
+    # protocol accounting: 20 convs + fc matmul triples, 20 BN layers x 239 elementwise triples, 17 ReLUs + 4 pool steps
+    assert tape.n_consts == 20 * 80
+    assert tape.n_triples == 21 + 20 * 239 + 17 + 4
