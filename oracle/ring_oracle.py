@@ -430,3 +430,54 @@ def resnet18_forward_shared(P, x_sh, tape: Tape, base=10, pf=16, input_size=224,
     B = x[0].shape[0]
     ncls = P["fc.weight"][0].shape[0]
     return linear_shared(x, P["fc.weight"], P["fc.bias"], tape.triple("matmul", (B, 512), (512, ncls)), base, pf)
+
+
+class GeneratingTape(Tape):
+    """a tape that draws its randomness on demand (numpy), for oracle-only end-to-end runs: the CPU tests and the CPU
+    baseline leg of bench.py.  ``const_value``: the encoded public constant of the Newton iteration ((C+1) * base**pf)."""
+
+    def __init__(self, seed=0, const_value=0):
+        import numpy as np
+
+        self.rng = np.random.default_rng(seed)
+        self.const_value = const_value
+        self.n_triples = self.n_consts = self.n_fss = 0
+        self.gen_seconds = 0.0  # time spent producing primitives (the offline phase), so callers can time the online part
+
+    def _r(self, shape):
+        return torch.from_numpy(self.rng.integers(-2 ** 63, 2 ** 63 - 1, tuple(shape)))
+
+    def triple(self, op, x_shape=None, y_shape=None):
+        import time
+
+        t0 = time.perf_counter()
+        self.n_triples += 1
+        a, b = self._r(x_shape), self._r(y_shape)
+        c = torch.matmul(a, b) if op == "matmul" else a * b
+        a0, b0, c0 = self._r(a.shape), self._r(b.shape), self._r(c.shape)
+        out = [(a0, b0, c0), (a - a0, b - b0, c - c0)]
+        self.gen_seconds += time.perf_counter() - t0
+        return out
+
+    def const(self):
+        self.n_consts += 1
+        s0 = self._r((1,))
+        return [s0, torch.tensor([self.const_value], dtype=torch.int64) - s0]
+
+    def fss_keys(self, n):
+        import numpy as np
+
+        from . import fss_oracle as F
+
+        import time
+
+        t0 = time.perf_counter()
+        self.n_fss += n
+        alpha = self.rng.integers(0, 2 ** 32, n, dtype=np.uint64)
+        key = F.dif_keygen(alpha, self.rng.integers(0, 2 ** 63, (2, 2, n), dtype=np.uint64))
+        out = key, F.split_alpha(alpha, self.rng.integers(0, 2 ** 32, n, dtype=np.uint64))
+        self.gen_seconds += time.perf_counter() - t0
+        return out
+
+    def exhausted(self):
+        return True

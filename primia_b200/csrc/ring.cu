@@ -372,6 +372,41 @@ __global__ void combine_mul_kernel(int j, const u64* __restrict__ delta, const u
   }
 }
 
+// reciprocal(method="newton") (precision.py:507-518) run to completion for one [C] vector when both share holders live on
+// the same device: thread = channel, both parties' shares in registers, the openings of the 3*(iters-1) Beaver products
+// happen in registers.  Arithmetic per party is exactly spdz_mask / spdz_compute / truncate / __rsub__ / __truediv__.
+// a*,b*,c* : [3*(iters-1)][C] triple shares in consumption order (x*x, v*(xx), y*x per iteration); k* : [iters] shares of
+// the public constant (C+1) encoded (additive_shared.py:473-487).
+__global__ void bn_newton_fused_kernel(const u64* __restrict__ v0, const u64* __restrict__ v1, const u64* __restrict__ a0,
+                                       const u64* __restrict__ b0, const u64* __restrict__ c0, const u64* __restrict__ a1,
+                                       const u64* __restrict__ b1, const u64* __restrict__ c1, const u64* __restrict__ k0,
+                                       const u64* __restrict__ k1, int C, int iters, int64_t div, int64_t Cc,
+                                       u64* __restrict__ x0, u64* __restrict__ x1) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const u64 V0 = v0[ch], V1 = v1[ch];
+  u64 X0 = (u64)((int64_t)(0 - (V0 - k0[0])) / Cc), X1 = (u64)((int64_t)(0 - (V1 - k1[0])) / Cc);
+  auto beaver = [&](u64 p0, u64 p1, u64 q0, u64 q1, int m, u64& z0, u64& z1) {
+    const size_t o = (size_t)m * C + ch;
+    const u64 A0 = a0[o], B0 = b0[o], A1 = a1[o], B1 = b1[o];
+    const u64 d = (p0 - A0) + (p1 - A1), e = (q0 - B0) + (q1 - B1);
+    z0 = (u64)((int64_t)(d * B0 + A0 * e + c0[o] + d * e) / div);
+    z1 = (u64)((int64_t)(d * B1 + A1 * e + c1[o]) / div);
+  };
+  for (int it = 1; it < iters; ++it) {
+    const int m = 3 * (it - 1);
+    u64 xx0, xx1, w0, w1, t0, t1;
+    beaver(X0, X1, X0, X1, m, xx0, xx1);
+    beaver(V0, V1, xx0, xx1, m + 1, w0, w1);
+    const u64 y0 = 0 - (w0 - k0[it]), y1 = 0 - (w1 - k1[it]);
+    beaver(y0, y1, X0, X1, m + 2, t0, t1);
+    X0 = (u64)((int64_t)t0 / Cc);
+    X1 = (u64)((int64_t)t1 / Cc);
+  }
+  x0[ch] = X0;
+  x1[ch] = X1;
+}
+
 __global__ void avgpool_kernel(const int64_t* __restrict__ x, int H, int W, int k, int64_t* __restrict__ out,
                                size_t total) {
   const int Ho = H / k, Wo = W / k;
@@ -518,6 +553,18 @@ int pm_axpby_i64(int64_t alpha, const int64_t* x, int64_t beta, const int64_t* y
   const size_t n = P * C;
   if (n == 0) return PM_OK;
   axpby_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(alpha, x, beta, y, ybcast, n, C, out);
+  PM_LAUNCH_OK();
+}
+
+int pm_bn_newton_fused_i64(const int64_t* v0, const int64_t* v1, const int64_t* a0, const int64_t* b0, const int64_t* c0,
+                           const int64_t* a1, const int64_t* b1, const int64_t* c1, const int64_t* k0, const int64_t* k1,
+                           int C, int iters, int64_t divisor, int64_t newton_c, int64_t* x0, int64_t* x1, pm_stream_t s) {
+  PM_CHECK_ARG(v0 && v1 && k0 && k1 && x0 && x1 && C > 0 && iters >= 1 && divisor != 0 && newton_c != 0);
+  PM_CHECK_ARG(iters == 1 || (a0 && b0 && c0 && a1 && b1 && c1));
+  bn_newton_fused_kernel<<<(C + 63) / 64, 64, 0, S(s)>>>((const u64*)v0, (const u64*)v1, (const u64*)a0, (const u64*)b0,
+                                                          (const u64*)c0, (const u64*)a1, (const u64*)b1, (const u64*)c1,
+                                                          (const u64*)k0, (const u64*)k1, C, iters, divisor, newton_c,
+                                                          (u64*)x0, (u64*)x1);
   PM_LAUNCH_OK();
 }
 

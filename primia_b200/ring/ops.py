@@ -16,7 +16,7 @@ I64 = torch.int64
 __all__ = [
     "encode", "decode", "share_gen", "random_i64", "im2col", "mask", "mask_im2col", "mask_wt", "open_add",
     "combine_matmul", "combine_mul", "matmul", "trunc_div", "trunc_post_conv", "axpby", "avgpool",
-    "nchw_to_pc", "pc_to_nchw", "conv_out_size",
+    "nchw_to_pc", "pc_to_nchw", "conv_out_size", "stack", "bn_newton_fused",
 ]
 
 
@@ -265,3 +265,28 @@ def pc_to_nchw(x, B, C, H, W):
     with torch.cuda.device(x.device):
         call("pm_pc_to_nchw_i64", ptr(x), B, C, H * W, ptr(out), stream())
     return out
+
+
+def stack(tensors):
+    """[n] same-shape tensors -> one contiguous [n, ...] buffer (a no-copy view when they already are consecutive slices of
+    one allocation, as bulk-generated triples are)."""
+    t0 = tensors[0]
+    step = t0.numel() * t0.element_size()
+    if all(t.is_contiguous() and t.data_ptr() == t0.data_ptr() + i * step and t.untyped_storage().data_ptr() ==
+           t0.untyped_storage().data_ptr() for i, t in enumerate(tensors)):
+        return torch.as_strided(t0, (len(tensors), *t0.shape), (t0.numel(), *t0.stride()))
+    return torch.stack([_chk(t) for t in tensors])
+
+
+def bn_newton_fused(v, tri, k, iters: int, divisor: int, newton_c: int):
+    """precision.py:507-518 for both co-resident parties in one launch. v: [v0, v1] ([C]); tri[j] = (a, b, c) each
+    [3*(iters-1), C]; k = (k0, k1) each [iters]."""
+    v0, v1 = _chk(v[0]), _chk(v[1])
+    C = v0.shape[0]
+    x0, x1 = torch.empty_like(v0), torch.empty_like(v1)
+    (a0, b0, c0), (a1, b1, c1) = [[_chk(t) for t in tri[j]] for j in range(2)]
+    assert tuple(a0.shape) == (3 * (iters - 1), C)
+    with torch.cuda.device(v0.device):
+        call("pm_bn_newton_fused_i64", ptr(v0), ptr(v1), ptr(a0), ptr(b0), ptr(c0), ptr(a1), ptr(b1), ptr(c1), ptr(_chk(k[0])),
+             ptr(_chk(k[1])), C, iters, int(divisor), int(newton_c), ptr(x0), ptr(x1), stream())
+    return [x0, x1]

@@ -197,6 +197,22 @@ class EncryptedResNet18:
 
     __call__ = forward
 
+    # ---- offline / online split (triple and key generation is reported separately)
+    def trace(self, x: FixedPrecisionTensor):
+        """run one forward with on-demand primitives and remember which primitives it asked for, in order"""
+        start = len(self.provider.request_log)
+        out = self.forward(x)
+        self.schedule = list(self.provider.request_log[start:])
+        return out
+
+    def preprocess(self, n_images: int = 1):
+        """offline phase: the crypto provider generates and distributes every Beaver triple and FSS key that ``n_images``
+        forward passes will consume (beaver.py:7-63, primitives.py:237-286), in consumption order."""
+        assert getattr(self, "schedule", None), "call trace(x) once first: it records the primitive schedule"
+        for _ in range(n_images):
+            for op, shapes, n in self.schedule:
+                self.provider.provide_primitives(op, shapes, self.parties, n)
+
     def predict(self, x: torch.Tensor):
         """one pass of the loop body of inference.py:292-317: share the image, forward, reconstruct, decode, argmax"""
         out = self.forward(self.share_input(x)).get().float_prec()

@@ -65,6 +65,8 @@ class PrimitiveStorage:
         win = head.window(n_instances)
         if remove:
             head.off += n_instances
+            if head.available == 0:
+                self._fss.pop(0)  # the window keeps the tensors alive until the evaluation that uses it has been issued
         return win
 
     def add_fss_keys(self, keys):
@@ -117,6 +119,7 @@ class TripleProvider:
         self.seed = seed
         self.counter = 0
         self.generated_bytes = 0
+        self.request_log = []  # (op, shapes, n_instances) of every provide_primitives call, in order
 
     def _rand(self, shape):
         self.counter += 1
@@ -136,6 +139,9 @@ class TripleProvider:
             out[0][i], out[1][i] = s0, s1
         return out
 
+    def on_triple(self, op, shapes, tri):
+        """hook: called once per generated triple instance, in store order (tests record the randomness here)"""
+
     def build_fss_keys(self, n_instances: int):
         """build_fss_keys / build_separate_fss_keys -- primitives.py:237-253 (DIF.keygen on the provider's GPU)"""
         from .fss import build_fss_keys
@@ -144,6 +150,7 @@ class TripleProvider:
         return build_fss_keys(n_instances, self.provider.device, self.seed, self.counter - 2)
 
     def provide_primitives(self, op: str, shapes=None, parties=None, n_instances: int = 1, **_):
+        self.request_log.append((op, shapes, n_instances))
         if op == "fss_comp":
             keys = self.build_fss_keys(n_instances)
             for j, p in enumerate(parties):
@@ -153,14 +160,37 @@ class TripleProvider:
             if any(p.device != self.provider.device for p in parties):
                 torch.cuda.synchronize(self.provider.device)
             return
+        if op == "mul" and n_instances > 1 and tuple(shapes[0]) == tuple(shapes[1]):
+            # build_triple with a leading n_instances axis (beaver.py:23-31), split into per-instance views
+            bulk = ((n_instances, *shapes[0]), (n_instances, *shapes[1]))
+            tri = self.build_triple(op, bulk)
+            for j, p in enumerate(parties):
+                moved = tuple(t.to(p.device, non_blocking=True) for t in tri[j])
+                self.generated_bytes += sum(t.numel() * 8 for t in moved)
+                p.crypto_store.add_primitives(op, shapes, [tuple(t[i] for t in moved) for i in range(n_instances)])
+            for i in range(n_instances):
+                self.on_triple(op, shapes, [tuple(t[i] for t in tri[j]) for j in range(2)])
+            n_instances = 0
         for _i in range(n_instances):
             tri = self.build_triple(op, shapes)
+            self.on_triple(op, shapes, tri)
             for j, p in enumerate(parties):
                 moved = tuple(t.to(p.device, non_blocking=True) for t in tri[j])
                 self.generated_bytes += sum(t.numel() * 8 for t in moved)
                 p.crypto_store.add_primitives(op, shapes, [moved])
         if any(p.device != self.provider.device for p in parties):
             torch.cuda.synchronize(self.provider.device)
+
+
+def take_primitives(op: str, shapes, n: int, parties, provider=None):
+    """pop the next ``n`` triples of one kind from every party's store (n consecutive spdz_compute pops, spdz.py:84),
+    asking the provider for the missing ones first as spdz_mul does (spdz.py:156-160)."""
+    have = min(p.crypto_store.count(op, shapes) for p in parties)
+    if have < n:
+        if provider is None or any(p.crypto_store.force_preprocessing for p in parties):
+            raise EmptyCryptoPrimitiveStoreError(parties[0].crypto_store, have, n, op=op, shapes=_key(shapes))
+        provider.provide_primitives(op, shapes, parties, n - have)
+    return [[p.crypto_store.get_keys(op=op, shapes=shapes, remove=True) for _ in range(n)] for p in parties]
 
 
 def _mul_bcast(a, b):

@@ -4,6 +4,8 @@ Mirrors the subset of syft/frameworks/torch/tensors/interpreters/{additive_share
 inference.py:279-321 exercises."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -207,8 +209,13 @@ class FixedPrecisionTensor:
         return self._new(self.child.relu())
 
     def reciprocal(self, method="newton"):
-        """precision.py:507-518 -- literally (80 iterations, C = 20)."""
+        """precision.py:507-518 -- literally (80 iterations, C = 20).  When both share holders are resident on one GPU the
+        whole iteration runs as ONE kernel (pm_bn_newton_fused_i64) with identical per-party arithmetic and the same
+        consumption of triples and constant sharings; otherwise the protocol is issued op by op."""
         assert method == "newton"
+        ast = self.child
+        if (FUSE_NEWTON and len(ast.child[0].shape) == 1 and ast.parties[0].device == ast.parties[1].device):
+            return self._reciprocal_fused(80, 20)
         x = None
         C = 20
         for _ in range(80):
@@ -219,3 +226,20 @@ class FixedPrecisionTensor:
                 y = C + 1 - self
                 x = y / C
         return x
+
+    def _reciprocal_fused(self, iters, C):
+        from .spdz import take_primitives
+
+        ast = self.child
+        n = ast.child[0].shape[0]
+        shapes = ((n,), (n,))
+        tri = take_primitives("mul", shapes, 3 * (iters - 1), ast.parties, ast.provider)
+        dev = ast.parties[0].device
+        q = torch.full((iters,), int((C + 1) * self.scale), dtype=torch.int64, device=dev)
+        k0, k1 = ast.rng.share(q)  # the constant is freshly shared at every iteration (additive_shared.py:473-487)
+        packed = [[ops.stack([t[i] for t in tri[j]]) for i in range(3)] for j in range(2)]
+        x = ops.bn_newton_fused(ast.child, packed, (k0, k1), iters, self.scale, C)
+        return self._new(ast._new(x))
+
+
+FUSE_NEWTON = os.environ.get("PRIMIA_FUSE_NEWTON", "1") != "0"

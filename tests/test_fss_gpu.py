@@ -146,7 +146,8 @@ class ReplayRNG:
             g = torch.Generator().manual_seed(1000 + len(self.log))
             s0 = torch.randint(-(2 ** 63), 2 ** 63 - 1, tuple(q.shape), dtype=torch.int64, generator=g).to(q.device)
         s1 = q - s0
-        self.log.append([s0.cpu(), s1.cpu()])
+        for i in range(q.numel()):  # one log entry per shared constant (the fused Newton kernel shares all 80 at once)
+            self.log.append([s0.reshape(-1)[i:i + 1].cpu(), s1.reshape(-1)[i:i + 1].cpu()])
         return s0, s1
 
 
@@ -158,10 +159,8 @@ def recording_provider(ring, party):
             super().__init__(*a, **k)
             self.triples, self.fss = [], []
 
-        def build_triple(self, op, shapes):
-            tri = super().build_triple(op, shapes)
+        def on_triple(self, op, shapes, tri):
             self.triples.append((op, [tuple(t.cpu() for t in tri[j]) for j in range(2)]))
-            return tri
 
         def build_fss_keys(self, n):
             keys = super().build_fss_keys(n)

@@ -159,38 +159,6 @@ def test_relu_on_shares_reconstructs():
     assert torch.equal(out[0] + out[1], torch.clamp(x, min=0))
 
 
-class GenTape(R.Tape):
-    """a tape that draws its randomness on demand (numpy), for oracle-only end-to-end checks"""
-
-    def __init__(self, seed=0):
-        import numpy as np
-
-        self.rng = np.random.default_rng(seed)
-        self.n_triples = self.n_consts = self.n_fss = 0
-
-    def _r(self, shape):
-        return torch.from_numpy(self.rng.integers(-2 ** 63, 2 ** 63 - 1, tuple(shape)))
-
-    def triple(self, op, x_shape=None, y_shape=None):
-        self.n_triples += 1
-        a, b = self._r(x_shape), self._r(y_shape)
-        c = torch.matmul(a, b) if op == "matmul" else a * b
-        a0, b0, c0 = self._r(a.shape), self._r(b.shape), self._r(c.shape)
-        return [(a0, b0, c0), (a - a0, b - b0, c - c0)]
-
-    def const(self):
-        raise NotImplementedError  # set by the caller: needs the encoded constant
-
-    def fss_keys(self, n):
-        import numpy as np
-        from oracle import fss_oracle as F
-
-        self.n_fss += n
-        alpha = self.rng.integers(0, 2 ** 32, n, dtype=np.uint64)
-        key = F.dif_keygen(alpha, self.rng.integers(0, 2 ** 63, (2, 2, n), dtype=np.uint64))
-        return key, F.split_alpha(alpha, self.rng.integers(0, 2 ** 32, n, dtype=np.uint64))
-
-
 def test_full_encrypted_forward_oracle_tracks_plaintext_model():
     """resnet18_forward_shared (the restatement of inference.py:279-321) on a 32x32 image at base 10, pf 4: the decoded
     logits follow the plaintext model with pool/relu swapped (inference.py:289)."""
@@ -210,15 +178,7 @@ def test_full_encrypted_forward_oracle_tracks_plaintext_model():
     model.eval()
     g = torch.Generator().manual_seed(8)
     img = torch.randn(1, 3, size, size, generator=g)
-    tape = GenTape(1)
-    q21 = torch.tensor([21 * base ** pf], dtype=torch.int64)
-
-    def const():
-        tape.n_consts += 1
-        s0 = tape._r((1,))
-        return [s0, q21 - s0]
-
-    tape.const = const
+    tape = R.GeneratingTape(1, 21 * base ** pf)
     sh = lambda q: [(s0 := tape._r(q.shape)), q - s0]
     P = {k: sh(R.encode(v.float().contiguous(), base, pf)) for k, v in model.state_dict().items()
          if not k.endswith("num_batches_tracked")}

@@ -185,7 +185,10 @@ class ReplayRNG:
         self.s0 = list(s0_list)
 
     def share(self, q):
-        s0 = self.s0.pop(0).to(q.device)
+        if self.s0[0].numel() == q.numel():
+            s0 = self.s0.pop(0).to(q.device)
+        else:  # the fused Newton kernel shares all its constants in one call
+            s0 = torch.cat([self.s0.pop(0).reshape(-1) for _ in range(q.numel())]).reshape(q.shape).to(q.device)
         return s0, q - s0
 
 
@@ -227,6 +230,22 @@ def test_batch_norm_eval_newton_bit_exact(ring):
     out = ring.functional.batch_norm(mk(x_sh), mk(m_sh), mk(v_sh), mk(g_sh), mk(b_sh))
     for j in range(2):
         assert torch.equal(out.child.child[j].cpu(), ref[j])
+    # the op-by-op protocol (parties on different GPUs take this path) produces the same shares as the fused kernel
+    from primia_b200.ring import tensors as T
+    for j, pty in enumerate(parties):
+        for it in range(1, iters):
+            for t in triples[it]:
+                pty.crypto_store.add_primitives("mul", ((C,), (C,)), [tuple(cu(u) for u in t[j])])
+        pty.crypto_store.add_primitives("mul", ((C,), (P, C)), [tuple(cu(u) for u in tri_norm[j])])
+        pty.crypto_store.add_primitives("mul", ((P, C), (C,)), [tuple(cu(u) for u in tri_aff[j])])
+    rng.s0 = list(c_s0)
+    T.FUSE_NEWTON = False
+    try:
+        out2 = ring.functional.batch_norm(mk(x_sh), mk(m_sh), mk(v_sh), mk(g_sh), mk(b_sh))
+    finally:
+        T.FUSE_NEWTON = True
+    for j in range(2):
+        assert torch.equal(out2.child.child[j].cpu(), ref[j])
     # numerically sane at pf=4: decodes to the float batch norm (eps ignored) within fixed-point error
     got = R.decode(ref[0] + ref[1], base, pf)
     xf, mf, vf, gf, bf = (R.decode(t, base, pf) for t in (x, mean, var, gamma, beta))
