@@ -207,7 +207,7 @@ def encrypted_inference_block(steps=3, cpu=True):
     import torchvision
 
     from primia_b200 import _lib, ring
-    from primia_b200.ring.resnet import EncryptedLinearGraph, SharedLinearLayers
+    from primia_b200.ring.resnet import EncryptedInferenceGraph, EncryptedLinearGraph, SharedLinearLayers
 
     dev = "cuda:%d" % torch.cuda.current_device()
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -219,26 +219,26 @@ def encrypted_inference_block(steps=3, cpu=True):
         sd = torchvision.models.resnet18(num_classes=3).state_dict()   # key-compatible with torchlib/models.py resnet18
         net = ring.EncryptedResNet18.from_state_dict(sd, parties, prov, 10, 16, input_size=size)
         himg = (torch.randn(1, 3, size, size) * 0.1).pin_memory()
-        net.trace(net.share_input(himg))                                # warm-up; records the primitive schedule
-        off, on, e2e, launches = [], [], [], 0
+        eg = EncryptedInferenceGraph(net, himg)                         # warm-up, primitive schedule, capture of the online phase
+        off, on, launches = [], [], 0
         hout = torch.zeros(1, 3).pin_memory()
-        for it in range(reps + 1):
+        for it in range(reps + 2):
             torch.cuda.synchronize()
             e = [ev() for _ in range(3)]
             e[0].record()
-            net.preprocess(1)
+            eg.offline()                                                # fresh triples + FSS keys into the static buffers
             e[1].record()
             l0 = _lib.launch_counter
-            out, _pred = net.predict(himg.to(dev, non_blocking=True))   # H2D image, share, forward, reconstruct, decode
+            out, _pred = eg.online(himg.to(dev, non_blocking=True))     # H2D image, encode+share, graph replay (forward, reconstruct, decode)
             hout.copy_(out)                                             # D2H logits
             e[2].record()
             torch.cuda.synchronize()
-            if it:
+            if it >= 2:                                                 # two warm-up images (allocator growth)
                 off.append(e[0].elapsed_time(e[1]))
                 on.append(e[1].elapsed_time(e[2]))
-                launches = _lib.launch_counter - l0
-        gb = prov.generated_bytes / (reps + 2) / 1e9
-        del net, parties, prov
+        launches = eg.kernels_in_graph
+        gb = prov.generated_bytes / (reps + 4) / 1e9
+        del eg, net, parties, prov
         torch.cuda.empty_cache()
         return sum(on) / len(on), sum(off) / len(off), launches, gb
 
@@ -249,7 +249,7 @@ def encrypted_inference_block(steps=3, cpu=True):
            "e2e": {"value": on_ms, "unit": "ms/image", "h2d_bytes_per_step": 3 * 224 * 224 * 4, "d2h_bytes_per_step": 12,
                    "note": "host image -> H2D -> encode+share -> forward on shares -> reconstruct -> decode -> D2H logits"},
            "config": {"workload": "C4: SPDZ 2-party + crypto provider ResNet-18, base 10 pf 16 int64 ring, one 224x224x3 image, "
-                                  "protocol fss, parties time-sharing one GPU, eager launches"}}
+                                  "protocol fss, parties time-sharing one GPU, online phase = one CUDA-graph replay"}}
     # FSS evaluation is the dominant kernel: integer-ALU bound (no memory or tensor roofline applies)
     cmp_per_image = 64 * 56 * 56 * 8 + 64 * 56 * 56 + 4 * 64 * 56 * 56 + 4 * 128 * 28 * 28 + 4 * 256 * 14 * 14 + 4 * 512 * 7 * 7
     out["fss"] = {"comparisons_per_image": cmp_per_image, "sha512_per_image_online": cmp_per_image * 64,

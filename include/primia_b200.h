@@ -96,11 +96,18 @@ int pm_axpby_i64(int64_t alpha, const int64_t* x, int64_t beta, const int64_t* y
 /* FixedPrecisionTensor.reciprocal(method="newton")  precision.py:507-518 as used by batch_norm (nn/functional.py:62-64):
  * x0 = (C+1 - v)/C ; x <- x*(C+1 - v*x*x)/C, iters-1 more times, every product a Beaver multiplication followed by
  * truncate(divisor = base**pf) and "/ C" a per-share truncating divide.  This entry point runs the whole iteration for
- * both share holders when they are resident on the SAME device (the openings stay in registers); v*: [C] shares of the
- * variance, a*,b*,c*: [3*(iters-1)][C] triple shares in consumption order, k*: [iters] shares of encode(C+1). */
-int pm_bn_newton_fused_i64(const int64_t* v0, const int64_t* v1, const int64_t* a0, const int64_t* b0, const int64_t* c0,
-                           const int64_t* a1, const int64_t* b1, const int64_t* c1, const int64_t* k0, const int64_t* k1,
-                           int C, int iters, int64_t divisor, int64_t newton_c, int64_t* x0, int64_t* x1, pm_stream_t s);
+ * both share holders when they are resident on the SAME device (the openings stay in registers), for up to
+ * PM_NEWTON_MAX_JOBS vectors (BatchNorm layers) in one launch.  Per job: v*: [C] shares of the variance, a*,b*,c*:
+ * [3*(iters-1)][C] triple shares in consumption order, k*: [iters] shares of encode(C+1), x*: [C] outputs.
+ * `jobs` is a HOST array (copied into the kernel's parameter space). */
+#define PM_NEWTON_MAX_JOBS 32
+typedef struct {
+  const int64_t *v0, *v1, *a0, *b0, *c0, *a1, *b1, *c1, *k0, *k1;
+  int64_t *x0, *x1;
+  int C;
+} pm_newton_job_t;
+int pm_bn_newton_fused_i64(const pm_newton_job_t* jobs, int n_jobs, int iters, int64_t divisor, int64_t newton_c,
+                           pm_stream_t s);
 /* avg pool k x k, stride k on one share: sum / (k*k) with trunc  functional.py:460-525 + additive_shared.py:720-729 */
 int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t* out, pm_stream_t s);
 /* batch_norm layout shuffles functional.py:52-55,70-73: NCHW [B,C,H,W] <-> [P=B*H*W, C] */

@@ -318,20 +318,20 @@ def max_pool2d_shared(x_sh, k, stride, padding, fss_keys, alpha_shs, triples, tr
 
 # --------------------------------------------------------------------------- E1: the whole encrypted forward
 class Tape:
-    """Explicit randomness of one encrypted forward, in consumption order (one FIFO per kind):
-    ``triples``  [(op, [(a0,b0,c0),(a1,b1,c1)])], ``consts`` [[s0, s1]] (sharings of public constants,
-    additive_shared.py:473-487), ``fss`` [(key dict, [alpha0, alpha1])] (oracle/fss_oracle.py layout)."""
+    """Explicit randomness of one encrypted forward.  ``triples`` [(op, [(a0,b0,c0),(a1,b1,c1)])] are consumed first-in
+    first-out PER (op, operand shapes) -- the reference's crypto store is keyed that way (primitives.py:52-102) -- so only the
+    relative order of same-shaped triples matters; ``consts`` [[s0, s1]] (sharings of public constants,
+    additive_shared.py:473-487) and ``fss`` [(key dict, [alpha0, alpha1])] (oracle/fss_oracle.py layout) are plain FIFOs."""
 
     def __init__(self, triples, consts, fss):
-        self.triples, self.consts, self.fss = list(triples), list(consts), list(fss)
+        self.triples = {}
+        for op, tri in triples:
+            key = (op, tuple(tri[0][0].shape), tuple(tri[0][1].shape))
+            self.triples.setdefault(key, []).append(tri)
+        self.consts, self.fss = list(consts), list(fss)
 
-    def triple(self, op, x_shape=None, y_shape=None):
-        got_op, tri = self.triples.pop(0)
-        assert got_op == op, (got_op, op)
-        if x_shape is not None:
-            assert tuple(tri[0][0].shape) == tuple(x_shape) and tuple(tri[0][1].shape) == tuple(y_shape), \
-                (tri[0][0].shape, tri[0][1].shape, x_shape, y_shape)
-        return tri
+    def triple(self, op, x_shape, y_shape):
+        return self.triples[(op, tuple(x_shape), tuple(y_shape))].pop(0)
 
     def const(self):
         return self.consts.pop(0)
@@ -342,7 +342,7 @@ class Tape:
         return key, alpha
 
     def exhausted(self):
-        return not (self.triples or self.consts or self.fss)
+        return not (any(self.triples.values()) or self.consts or self.fss)
 
 
 def batch_norm_eval_taped(x_sh, mean_sh, var_sh, gamma_sh, beta_sh, tape: Tape, base, pf):

@@ -32,6 +32,13 @@ class WCvt(ctypes.Structure):
                 ("C", ctypes.c_int), ("RS", ctypes.c_int), ("Cpad", ctypes.c_int)]
 
 
+class NewtonJob(ctypes.Structure):
+    """pm_newton_job_t"""
+
+    _fields_ = [(n, ctypes.c_void_p) for n in ("v0", "v1", "a0", "b0", "c0", "a1", "b1", "c1", "k0", "k1", "x0", "x1")] + [
+        ("C", ctypes.c_int)]
+
+
 _SCALARS = {
     "int": ctypes.c_int,
     "size_t": ctypes.c_size_t,

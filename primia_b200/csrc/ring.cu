@@ -372,39 +372,86 @@ __global__ void combine_mul_kernel(int j, const u64* __restrict__ delta, const u
   }
 }
 
-// reciprocal(method="newton") (precision.py:507-518) run to completion for one [C] vector when both share holders live on
+// exact C-style (truncating) int64 division by a positive invariant divisor without the ~100-instruction emulated
+// 64-bit divide: two double-precision quotient estimates, each followed by an exact remainder in wrapping integer
+// arithmetic, then at most two unit corrections.  inv_d = 1.0 / d.
+__device__ __forceinline__ int64_t trunc_div_inv(int64_t x, int64_t d, double inv_d) {
+  int64_t q = __double2ll_rz((double)x * inv_d);
+  int64_t r = (int64_t)((u64)x - (u64)q * (u64)d);           // |r| <= ~2^11 * d: exact despite the wrap
+  const int64_t q2 = __double2ll_rz((double)r * inv_d);
+  q += q2;
+  r -= q2 * d;                                                // now |r| < 2d
+  if (x >= 0) {
+    if (r < 0) { --q; r += d; }
+    if (r < 0) { --q; r += d; }
+    if (r >= d) { ++q; r -= d; }
+    if (r >= d) { ++q; }
+  } else {
+    if (r > 0) { ++q; r -= d; }
+    if (r > 0) { ++q; r -= d; }
+    if (r <= -d) { --q; r += d; }
+    if (r <= -d) { --q; }
+  }
+  return q;
+}
+
+// reciprocal(method="newton") (precision.py:507-518) run to completion for [C] vectors when both share holders live on
 // the same device: thread = channel, both parties' shares in registers, the openings of the 3*(iters-1) Beaver products
 // happen in registers.  Arithmetic per party is exactly spdz_mask / spdz_compute / truncate / __rsub__ / __truediv__.
 // a*,b*,c* : [3*(iters-1)][C] triple shares in consumption order (x*x, v*(xx), y*x per iteration); k* : [iters] shares of
-// the public constant (C+1) encoded (additive_shared.py:473-487).
-__global__ void bn_newton_fused_kernel(const u64* __restrict__ v0, const u64* __restrict__ v1, const u64* __restrict__ a0,
-                                       const u64* __restrict__ b0, const u64* __restrict__ c0, const u64* __restrict__ a1,
-                                       const u64* __restrict__ b1, const u64* __restrict__ c1, const u64* __restrict__ k0,
-                                       const u64* __restrict__ k1, int C, int iters, int64_t div, int64_t Cc,
-                                       u64* __restrict__ x0, u64* __restrict__ x1) {
+// the public constant (C+1) encoded (additive_shared.py:473-487).  blockIdx.y selects the job (one BatchNorm layer each):
+// the inverse square roots depend on the model only, so all layers of a forward pass are issued as one launch.
+struct NewtonJobs {
+  pm_newton_job_t job[PM_NEWTON_MAX_JOBS];
+};
+
+__global__ void __launch_bounds__(64)
+bn_newton_fused_kernel(const __grid_constant__ NewtonJobs jobs, int iters, int64_t div, int64_t Cc) {
+  const pm_newton_job_t& J = jobs.job[blockIdx.y];
+  const int C = J.C;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
-  const u64 V0 = v0[ch], V1 = v1[ch];
-  u64 X0 = (u64)((int64_t)(0 - (V0 - k0[0])) / Cc), X1 = (u64)((int64_t)(0 - (V1 - k1[0])) / Cc);
-  auto beaver = [&](u64 p0, u64 p1, u64 q0, u64 q1, int m, u64& z0, u64& z1) {
-    const size_t o = (size_t)m * C + ch;
-    const u64 A0 = a0[o], B0 = b0[o], A1 = a1[o], B1 = b1[o];
-    const u64 d = (p0 - A0) + (p1 - A1), e = (q0 - B0) + (q1 - B1);
-    z0 = (u64)((int64_t)(d * B0 + A0 * e + c0[o] + d * e) / div);
-    z1 = (u64)((int64_t)(d * B1 + A1 * e + c1[o]) / div);
+  const u64 *a0 = (const u64*)J.a0, *b0 = (const u64*)J.b0, *c0 = (const u64*)J.c0;
+  const u64 *a1 = (const u64*)J.a1, *b1 = (const u64*)J.b1, *c1 = (const u64*)J.c1;
+  const u64 *k0 = (const u64*)J.k0, *k1 = (const u64*)J.k1;
+  const double inv_div = 1.0 / (double)div, inv_c = 1.0 / (double)Cc;
+  const u64 V0 = (u64)J.v0[ch], V1 = (u64)J.v1[ch];
+  u64 X0 = (u64)trunc_div_inv((int64_t)(0 - (V0 - k0[0])), Cc, inv_c);
+  u64 X1 = (u64)trunc_div_inv((int64_t)(0 - (V1 - k1[0])), Cc, inv_c);
+  // operands of one iteration: 3 products x (a0,b0,c0,a1,b1,c1); loaded one iteration ahead (their addresses do not
+  // depend on the data), so the dependent chain below never waits on memory
+  u64 T[3][6], Tn[3][6], K0n = 0, K1n = 0;
+  auto load = [&](int it, u64 (&t)[3][6], u64& kk0, u64& kk1) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const size_t o = (size_t)(3 * (it - 1) + m) * C + ch;
+      t[m][0] = a0[o]; t[m][1] = b0[o]; t[m][2] = c0[o]; t[m][3] = a1[o]; t[m][4] = b1[o]; t[m][5] = c1[o];
+    }
+    kk0 = k0[it]; kk1 = k1[it];
   };
+  auto beaver = [&](u64 p0, u64 p1, u64 q0, u64 q1, const u64 (&t)[6], u64& z0, u64& z1) {
+    const u64 d = (p0 - t[0]) + (p1 - t[3]), e = (q0 - t[1]) + (q1 - t[4]);
+    z0 = (u64)trunc_div_inv((int64_t)(d * t[1] + t[0] * e + t[2] + d * e), div, inv_div);
+    z1 = (u64)trunc_div_inv((int64_t)(d * t[4] + t[3] * e + t[5]), div, inv_div);
+  };
+  if (iters > 1) load(1, Tn, K0n, K1n);
   for (int it = 1; it < iters; ++it) {
-    const int m = 3 * (it - 1);
+    const u64 K0 = K0n, K1 = K1n;
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) T[m][q] = Tn[m][q];
+    if (it + 1 < iters) load(it + 1, Tn, K0n, K1n);
     u64 xx0, xx1, w0, w1, t0, t1;
-    beaver(X0, X1, X0, X1, m, xx0, xx1);
-    beaver(V0, V1, xx0, xx1, m + 1, w0, w1);
-    const u64 y0 = 0 - (w0 - k0[it]), y1 = 0 - (w1 - k1[it]);
-    beaver(y0, y1, X0, X1, m + 2, t0, t1);
-    X0 = (u64)((int64_t)t0 / Cc);
-    X1 = (u64)((int64_t)t1 / Cc);
+    beaver(X0, X1, X0, X1, T[0], xx0, xx1);
+    beaver(V0, V1, xx0, xx1, T[1], w0, w1);
+    const u64 y0 = 0 - (w0 - K0), y1 = 0 - (w1 - K1);
+    beaver(y0, y1, X0, X1, T[2], t0, t1);
+    X0 = (u64)trunc_div_inv((int64_t)t0, Cc, inv_c);
+    X1 = (u64)trunc_div_inv((int64_t)t1, Cc, inv_c);
   }
-  x0[ch] = X0;
-  x1[ch] = X1;
+  J.x0[ch] = (int64_t)X0;
+  J.x1[ch] = (int64_t)X1;
 }
 
 __global__ void avgpool_kernel(const int64_t* __restrict__ x, int H, int W, int k, int64_t* __restrict__ out,
@@ -556,15 +603,19 @@ int pm_axpby_i64(int64_t alpha, const int64_t* x, int64_t beta, const int64_t* y
   PM_LAUNCH_OK();
 }
 
-int pm_bn_newton_fused_i64(const int64_t* v0, const int64_t* v1, const int64_t* a0, const int64_t* b0, const int64_t* c0,
-                           const int64_t* a1, const int64_t* b1, const int64_t* c1, const int64_t* k0, const int64_t* k1,
-                           int C, int iters, int64_t divisor, int64_t newton_c, int64_t* x0, int64_t* x1, pm_stream_t s) {
-  PM_CHECK_ARG(v0 && v1 && k0 && k1 && x0 && x1 && C > 0 && iters >= 1 && divisor != 0 && newton_c != 0);
-  PM_CHECK_ARG(iters == 1 || (a0 && b0 && c0 && a1 && b1 && c1));
-  bn_newton_fused_kernel<<<(C + 63) / 64, 64, 0, S(s)>>>((const u64*)v0, (const u64*)v1, (const u64*)a0, (const u64*)b0,
-                                                          (const u64*)c0, (const u64*)a1, (const u64*)b1, (const u64*)c1,
-                                                          (const u64*)k0, (const u64*)k1, C, iters, divisor, newton_c,
-                                                          (u64*)x0, (u64*)x1);
+int pm_bn_newton_fused_i64(const pm_newton_job_t* jobs, int n_jobs, int iters, int64_t divisor, int64_t newton_c,
+                           pm_stream_t s) {
+  PM_CHECK_ARG(jobs && n_jobs > 0 && n_jobs <= PM_NEWTON_MAX_JOBS && iters >= 1 && divisor > 0 && newton_c > 0);
+  NewtonJobs J;
+  int maxC = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const pm_newton_job_t& j = jobs[i];
+    PM_CHECK_ARG(j.v0 && j.v1 && j.k0 && j.k1 && j.x0 && j.x1 && j.C > 0);
+    PM_CHECK_ARG(iters == 1 || (j.a0 && j.b0 && j.c0 && j.a1 && j.b1 && j.c1));
+    J.job[i] = j;
+    if (j.C > maxC) maxC = j.C;
+  }
+  bn_newton_fused_kernel<<<dim3((maxC + 63) / 64, n_jobs), 64, 0, S(s)>>>(J, iters, divisor, newton_c);
   PM_LAUNCH_OK();
 }
 

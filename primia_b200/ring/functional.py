@@ -72,12 +72,14 @@ def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None,
 
 
 def batch_norm(input: FixedPrecisionTensor, running_mean, running_var, weight, bias, training=False,
-               exponential_average_factor=0.0, eps=1e-5):
-    """functional.py:44-75 (eval branch: eps ignored, inverse sqrt by the 80-step Newton iteration)."""
+               exponential_average_factor=0.0, eps=1e-5, inv_std=None):
+    """functional.py:44-75 (eval branch: eps ignored, inverse sqrt by the 80-step Newton iteration).
+    ``inv_std``: the result of ``running_var.reciprocal(method="newton")`` when the caller has already evaluated it
+    (it depends on the model only; EncryptedResNet18 issues all layers' iterations as one launch)."""
     assert not training, "encrypted inference uses model.eval() (inference.py:288)"
     B, C, H, W = input.shape
     flat = input._new(input.child.map(ops.nchw_to_pc))
-    x = running_var.reciprocal(method="newton")
+    x = inv_std if inv_std is not None else running_var.reciprocal(method="newton")
     normalized = x * (flat - running_mean)
     result = normalized * weight + bias
     return input._new(result.child.map(lambda s: ops.pc_to_nchw(s, B, C, H, W)))

@@ -278,15 +278,33 @@ def stack(tensors):
     return torch.stack([_chk(t) for t in tensors])
 
 
-def bn_newton_fused(v, tri, k, iters: int, divisor: int, newton_c: int):
-    """precision.py:507-518 for both co-resident parties in one launch. v: [v0, v1] ([C]); tri[j] = (a, b, c) each
-    [3*(iters-1), C]; k = (k0, k1) each [iters]."""
-    v0, v1 = _chk(v[0]), _chk(v[1])
-    C = v0.shape[0]
-    x0, x1 = torch.empty_like(v0), torch.empty_like(v1)
-    (a0, b0, c0), (a1, b1, c1) = [[_chk(t) for t in tri[j]] for j in range(2)]
-    assert tuple(a0.shape) == (3 * (iters - 1), C)
-    with torch.cuda.device(v0.device):
-        call("pm_bn_newton_fused_i64", ptr(v0), ptr(v1), ptr(a0), ptr(b0), ptr(c0), ptr(a1), ptr(b1), ptr(c1), ptr(_chk(k[0])),
-             ptr(_chk(k[1])), C, iters, int(divisor), int(newton_c), ptr(x0), ptr(x1), stream())
-    return [x0, x1]
+def bn_newton_fused(jobs, iters: int, divisor: int, newton_c: int):
+    """precision.py:507-518 for both co-resident parties, several vectors (BatchNorm layers) per launch.
+    jobs: list of (v, tri, k) with v = [v0, v1] ([C]); tri[j] = (a, b, c) each [3*(iters-1), C]; k = (k0, k1) each [iters].
+    Returns [[x0, x1], ...]."""
+    from .._lib import NewtonJob, lib
+
+    outs = []
+    dev = jobs[0][0][0].device
+    MAXJ = 32  # PM_NEWTON_MAX_JOBS
+    for base in range(0, len(jobs), MAXJ):
+        chunk = jobs[base:base + MAXJ]
+        arr = (NewtonJob * len(chunk))()
+        keep = []
+        for i, (v, tri, k) in enumerate(chunk):
+            v0, v1 = _chk(v[0]), _chk(v[1])
+            C = v0.shape[0]
+            x0, x1 = torch.empty_like(v0), torch.empty_like(v1)
+            (a0, b0, c0), (a1, b1, c1) = [[_chk(t) for t in tri[j]] for j in range(2)]
+            assert tuple(a0.shape) == (3 * (iters - 1), C), (a0.shape, iters, C)
+            k0, k1 = _chk(k[0]), _chk(k[1])
+            for name, t in zip(("v0", "v1", "a0", "b0", "c0", "a1", "b1", "c1", "k0", "k1", "x0", "x1"),
+                               (v0, v1, a0, b0, c0, a1, b1, c1, k0, k1, x0, x1)):
+                setattr(arr[i], name, t.data_ptr())
+            arr[i].C = C
+            keep.append((v0, v1, a0, b0, c0, a1, b1, c1, k0, k1))
+            outs.append([x0, x1])
+        with torch.cuda.device(dev):
+            call("pm_bn_newton_fused_i64", ctypes.cast(arr, ctypes.c_void_p), len(chunk), iters, int(divisor), int(newton_c),
+                 stream())
+    return outs

@@ -137,15 +137,19 @@ class EncryptedResNet18:
     ``shared`` maps state_dict keys to FixedPrecisionTensor > AdditiveSharingTensor; build it with ``from_state_dict``
     (encode + share on the GPU) or pass explicit shares (parity tests)."""
 
-    def __init__(self, shared, parties, provider, base=10, precision_fractional=16, input_size=224):
+    def __init__(self, shared, parties, provider, base=10, precision_fractional=16, input_size=224, rng=None):
         self.P, self.parties, self.provider = shared, parties, provider
         self.base, self.pf, self.input_size = base, precision_fractional, input_size
         self.taps = None
+        self.rng = rng
 
     @classmethod
     def from_state_dict(cls, state_dict, parties, provider, base=10, precision_fractional=16, input_size=224, rng=None):
         """model.fix_precision(**kw).share(*workers, **kw) -- inference.py:280-286"""
+        from .tensors import ShareRNG
+
         dev = parties[0].device
+        rng = rng or ShareRNG(seed=0xA11CE ^ getattr(provider, "seed", 0))
         shared = {}
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked"):
@@ -153,25 +157,40 @@ class EncryptedResNet18:
             t = v.detach().to(dev, torch.float32).contiguous()
             shared[k] = FixedPrecisionTensor.fix_precision(t, base, precision_fractional).share(
                 *parties, crypto_provider=provider, rng=rng)
-        return cls(shared, parties, provider, base, precision_fractional, input_size)
+        return cls(shared, parties, provider, base, precision_fractional, input_size, rng)
 
     def share_input(self, x: torch.Tensor, rng=None):
         """data.fix_precision(**kw).share(*workers, **kw) -- inference.py:307-311"""
         x = x.to(self.parties[0].device, torch.float32).contiguous()
         return FixedPrecisionTensor.fix_precision(x, self.base, self.pf).share(*self.parties, crypto_provider=self.provider,
-                                                                               rng=rng)
+                                                                               rng=rng or self.rng)
 
     def _tap(self, name, x):
         if self.taps is not None:
             self.taps[name] = [s.clone() for s in x.child.child]
         return x
 
+    BN_ORDER = ["bn1"] + [f"layer{li}.{bi}.{n}" for li in range(1, 5) for bi in range(2)
+                          for n in (("bn1", "bn2", "downsample.1") if (bi == 0 and li > 1) else ("bn1", "bn2"))]
+
+    def _newton_all(self):
+        """inverse standard deviations of all 20 BatchNorm layers (functional.py:62-64 -> precision.py:507-518) in one launch,
+        consuming triples and constant sharings in forward order; only when both parties share a GPU."""
+        from . import tensors as T
+
+        if not T.FUSE_NEWTON or self.parties[0].device != self.parties[1].device:
+            return {}
+        inv = T.reciprocal_newton_batched([self.P[n + ".running_var"] for n in self.BN_ORDER])
+        return dict(zip(self.BN_ORDER, inv))
+
     def _bn(self, x, name):
         P = self.P
-        return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"])
+        return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"],
+                            inv_std=self._inv.get(name))
 
     def forward(self, x: FixedPrecisionTensor) -> FixedPrecisionTensor:
         P = self.P
+        self._inv = self._newton_all()
         x = self._tap("conv1", F.conv2d(x, P["conv1.weight"], None, 2, 3))
         x = self._tap("bn1", self._bn(x, "bn1"))
         x = self._tap("pool", F.max_pool2d(x, 3, 2, 1))       # model.relu <- model.pool (inference.py:289)
@@ -217,3 +236,82 @@ class EncryptedResNet18:
         """one pass of the loop body of inference.py:292-317: share the image, forward, reconstruct, decode, argmax"""
         out = self.forward(self.share_input(x)).get().float_prec()
         return out, out.argmax(dim=1)
+
+
+class EncryptedInferenceGraph:
+    """The ONLINE phase of one encrypted image (share input -> forward on shares -> reconstruct -> decode) captured once in a
+    CUDA graph: ~1.4 k launches of mostly tiny kernels are launch-bound when issued eagerly from Python.  Every primitive the
+    forward consumes (Beaver triples, FSS keys, sharings of the Newton constant) lives in static buffers; ``offline()`` has
+    the crypto provider generate a fresh set and copies it over them, ``online(img)`` is one graph replay.  The crypto-store
+    bookkeeping (peek / pop, primitives.py:52-102) runs on the host at capture time."""
+
+    def __init__(self, net: EncryptedResNet18, example: torch.Tensor):
+        from .spdz import PrimitiveStorage
+
+        self.net = net
+        dev = net.parties[0].device
+        assert net.rng is not None, "build the model with from_state_dict (it owns the share RNG)"
+        x = net.share_input(example)
+        net.trace(x)                                   # warm-up + primitive schedule
+        self.x_static = x
+        net.preprocess(1)
+        self.static_state = [p.crypto_store.export_state() for p in net.parties]
+        self.static_tensors = self._unique(self.static_state)
+        torch.cuda.synchronize(dev)
+        net.rng.mode, net.rng.static = "record", []
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            net.forward(x)                             # consumes the static primitives once; records the constant sharings
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p, st in zip(net.parties, self.static_state):
+            p.crypto_store.import_state(st)
+        net.rng.mode, net.rng.cursor = "replay", 0
+        from .. import _lib
+
+        l0 = _lib.launch_counter
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out_shares = net.forward(x)
+            self.logits = self.out_shares.get().float_prec()
+        self.kernels_in_graph = _lib.launch_counter - l0
+        net.rng.mode = "live"
+        for p in net.parties:
+            p.crypto_store.clear()
+
+    @staticmethod
+    def _unique(states):
+        """one uint8 view per distinct allocation behind the primitives of both parties, in deterministic order"""
+        from .spdz import PrimitiveStorage
+
+        seen, out = set(), []
+        for st in states:
+            for t in PrimitiveStorage.state_tensors(st):
+                stor = t.untyped_storage()
+                if stor.data_ptr() not in seen:
+                    seen.add(stor.data_ptr())
+                    out.append(torch.empty(0, dtype=torch.uint8, device=t.device).set_(stor))
+        return out
+
+    def offline(self):
+        """fresh triples, FSS keys and constant sharings for the next image, written into the static buffers"""
+        net = self.net
+        net.preprocess(1)
+        fresh_state = [p.crypto_store.export_state() for p in net.parties]
+        fresh = self._unique(fresh_state)
+        assert len(fresh) == len(self.static_tensors)
+        for dst, src in zip(self.static_tensors, fresh):
+            dst.copy_(src, non_blocking=True)
+        for p in net.parties:
+            p.crypto_store.clear()
+        net.rng.mode = "live"
+        net.rng.refresh_static()
+
+    def online(self, img: torch.Tensor):
+        """inference.py:307-317 for one image: returns (logits, argmax) -- device tensors owned by the graph"""
+        s = self.net.share_input(img)
+        for dst, src in zip(self.x_static.child.child, s.child.child):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.logits, self.logits.argmax(dim=1)

@@ -84,6 +84,35 @@ class PrimitiveStorage:
         assert n_instances == 1
         return stack.pop(0) if remove else stack[0]
 
+    # ---- static-buffer support for CUDA-graph replay of the online phase (ring/resnet.py EncryptedInferenceGraph)
+    def export_state(self):
+        """the current content, by reference: ({op: {key: [triples]}}, [fss pools])"""
+        return ({op: {k: list(v) for k, v in st.items()} for op, st in self._stacks.items()}, list(self._fss))
+
+    def import_state(self, state):
+        stacks, fss = state
+        for op in self._stacks:
+            self._stacks[op] = defaultdict(list, {k: list(v) for k, v in stacks.get(op, {}).items()})
+        self._fss = list(fss)
+        for c in self._fss:
+            c.off = 0
+
+    def clear(self):
+        self.import_state(({}, []))
+
+    @staticmethod
+    def state_tensors(state):
+        """every tensor of an exported state, in a deterministic order"""
+        stacks, fss = state
+        out = []
+        for op in ("mul", "matmul"):
+            for key, lst in stacks.get(op, {}).items():
+                for tri in lst:
+                    out.extend(tri)
+        for c in fss:
+            out.extend(c.tensors())
+        return out
+
     def add_primitives(self, op: str, shapes, triples):
         """primitives.py:194-213"""
         self._stacks[op][_key(shapes)].extend(triples)

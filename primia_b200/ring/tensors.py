@@ -14,15 +14,36 @@ from .spdz import Party, TripleProvider, spdz_mul
 
 class ShareRNG:
     """Source of the fresh randomness the reference draws when it secret-shares a value
-    (additive_shared.py:336-365).  Tests subclass it to replay explicit shares."""
+    (additive_shared.py:336-365).  Tests subclass it to replay explicit shares.
+
+    ``mode``: "live" draws a new Philox offset per call; "record" additionally keeps (q, s0, s1) of every call as static
+    buffers; "replay" hands those buffers out again in order (a captured CUDA graph reads them; ``refresh_static`` rewrites
+    them with fresh randomness between replays)."""
 
     def __init__(self, seed=0xA11CE):
         self.seed = seed
         self.counter = 0
+        self.mode = "live"
+        self.static, self.cursor = [], 0
 
     def share(self, q: torch.Tensor):
+        if self.mode == "replay":
+            _q, s0, s1 = self.static[self.cursor]
+            self.cursor += 1
+            return s0, s1
         self.counter += 1
-        return ops.share_gen(q, self.seed, self.counter)
+        s0, s1 = ops.share_gen(q, self.seed, self.counter)
+        if self.mode == "record":
+            self.static.append((q, s0, s1))
+        return s0, s1
+
+    def refresh_static(self):
+        for q, s0, s1 in self.static:
+            self.counter += 1
+            n0, n1 = ops.share_gen(q, self.seed, self.counter)
+            s0.copy_(n0)
+            s1.copy_(n1)
+        self.cursor = 0
 
 
 DEFAULT_RNG = ShareRNG()  # one stream per process: every fresh sharing draws a new Philox offset
@@ -228,18 +249,28 @@ class FixedPrecisionTensor:
         return x
 
     def _reciprocal_fused(self, iters, C):
-        from .spdz import take_primitives
+        return reciprocal_newton_batched([self], iters, C)[0]
 
-        ast = self.child
+
+def reciprocal_newton_batched(fpts, iters=80, C=20):
+    """reciprocal(method="newton") of several shared vectors (one per BatchNorm layer) in ONE launch.  Triples and constant
+    sharings are taken from the stores / the share RNG in list order, exactly as the sequential evaluation would."""
+    from .spdz import take_primitives
+
+    jobs = []
+    for f in fpts:
+        ast = f.child
         n = ast.child[0].shape[0]
-        shapes = ((n,), (n,))
-        tri = take_primitives("mul", shapes, 3 * (iters - 1), ast.parties, ast.provider)
+        tri = take_primitives("mul", ((n,), (n,)), 3 * (iters - 1), ast.parties, ast.provider)
         dev = ast.parties[0].device
-        q = torch.full((iters,), int((C + 1) * self.scale), dtype=torch.int64, device=dev)
-        k0, k1 = ast.rng.share(q)  # the constant is freshly shared at every iteration (additive_shared.py:473-487)
+        q = torch.full((iters,), int((C + 1) * f.scale), dtype=torch.int64, device=dev)
+        k = ast.rng.share(q)  # the constant is freshly shared at every iteration (additive_shared.py:473-487)
         packed = [[ops.stack([t[i] for t in tri[j]]) for i in range(3)] for j in range(2)]
-        x = ops.bn_newton_fused(ast.child, packed, (k0, k1), iters, self.scale, C)
-        return self._new(ast._new(x))
+        jobs.append((ast.child, packed, k))
+    scales = {f.scale for f in fpts}
+    assert len(scales) == 1
+    xs = ops.bn_newton_fused(jobs, iters, scales.pop(), C)
+    return [f._new(f.child._new(x)) for f, x in zip(fpts, xs)]
 
 
 FUSE_NEWTON = os.environ.get("PRIMIA_FUSE_NEWTON", "1") != "0"

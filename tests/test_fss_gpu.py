@@ -323,3 +323,55 @@ def test_encrypted_resnet18_forward_bit_exact_vs_oracle(ring):
         model.pool, model.relu = model.relu, model.pool
         want = model(img)
     assert (logits - want).abs().max() < 0.15, (logits, want)
+
+
+def test_encrypted_inference_graph_replay_equals_eager_protocol(ring):
+    """the CUDA-graph online phase (static primitive buffers refreshed offline) produces exactly the shares the eager
+    protocol produces from the same primitives, for successive images with fresh primitives"""
+    import copy
+
+    from oracle import train_oracle as O
+    from primia_b200.ring.resnet import EncryptedInferenceGraph
+    from primia_b200.ring.spdz import PrimitiveStorage
+
+    base, pf, size = 10, 4, 32
+    torch.manual_seed(42)
+    model = O.ResNet18(input_size=size).eval()
+    parties = [ring.Party("model_owner", DEV), ring.Party("data_owner", DEV)]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", DEV), seed=7)
+    net = ring.EncryptedResNet18.from_state_dict(model.state_dict(), parties, prov, base, pf, input_size=size)
+    g = torch.Generator().manual_seed(9)
+    eg = EncryptedInferenceGraph(net, torch.randn(1, 3, size, size, generator=g))
+    model.pool, model.relu = model.relu, model.pool
+    prev = None
+    for it in range(2):
+        img = torch.randn(1, 3, size, size, generator=g)
+        eg.offline()
+        logits, pred = eg.online(img)
+        got = [s.clone() for s in eg.out_shares.child.child]
+        logits = logits.cpu()
+        with torch.no_grad():
+            want = model(img)
+        assert (logits - want).abs().max() < 0.15, (logits, want)
+        assert prev is None or not torch.equal(prev, logits)
+        prev = logits
+        # eager protocol on clones of the very primitives the replay consumed
+        def clone_state(st):
+            stacks, fss = st
+            memo = {}
+            def cl(t):
+                k = (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()))
+                if k not in memo:
+                    memo[k] = t.clone()
+                return memo[k]
+            new_stacks = {op: {k: [tuple(cl(t) for t in tri) for tri in lst] for k, lst in d.items()} for op, d in stacks.items()}
+            new_fss = [ring.fss.FSSKeys(*(cl(t) for t in c.tensors())) for c in fss]
+            return new_stacks, new_fss
+        for p, st in zip(parties, eg.static_state):
+            p.crypto_store.import_state(clone_state(st))
+        net.rng.mode, net.rng.cursor = "replay", 0
+        out = net.forward(eg.x_static)
+        net.rng.mode = "live"
+        for j in range(2):
+            assert torch.equal(out.child.child[j], got[j]), f"graph replay differs from the eager protocol (party {j}, image {it})"
+        assert all(p.crypto_store.nbytes() == 0 for p in parties)
