@@ -221,9 +221,30 @@ int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const
                          const float* gamma, size_t P, int C, double* ws, void* g_out, void* dx, float* dgamma, float* dbeta,
                          pm_stream_t s);
 
+/* bf16 throughput mode, BN followed by ReLU with no residual: the ReLU decision is recomputed from x and the BN constants
+ * ((x - mean) * (invstd * gamma) + beta > 0, the forward's own evaluation) instead of reading the stored activation. */
+int pm_bn_bwd_fused_xmask_bf16(const void* dy, const void* x, const float* mean, const float* invstd, const float* gamma,
+                               const float* beta, size_t P, int C, double* ws, void* dx, float* dgamma, float* dbeta,
+                               pm_stream_t s);
+/* Stem forward in one pass (bf16 mode): BatchNorm2d (batch statistics from `stats`, running stats updated, mean/invstd
+ * written) + ReLU + MaxPool2d(3,2,1) of x [B,H,W,C] -> y [B,Ho,Wo,C]; the full-resolution activation is not materialised.
+ * idx: argmax per output (first strict maximum of the raw conv outputs, sign-adjusted per channel: BN+ReLU is monotonic), or
+ * 255 where the maximum is not positive (no gradient passes the ReLU there). */
+int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H, int W, int C, float eps, float momentum,
+                                const float* gamma, const float* beta, void* y, uint8_t* idx, float* mean, float* invstd,
+                                float* running_mean, float* running_var, pm_stream_t s);
+
+/* Backward of pm_bn_relu_maxpool_fwd_bf16 (H, W even): max-pool backward gathered from (dpool, pool_idx) + BatchNorm backward
+ * as a reduce launch and an apply launch over 2x2 input blocks; sums: [2*C] doubles ZEROED by the caller; dx [B,H,W,C]. */
+int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* x, const float* mean,
+                             const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
+                             float* dbeta, pm_stream_t s);
+
 /* Stem variant: the BN input gradient is MaxPool2d(3,2,1)'s backward of `dpool` [B,Ho,Wo,C], gathered from the stored
  * argmax inside the reduce pass (saves the separate max-pool-backward launch and one pass over the full-resolution
- * gradient); `g_scratch` [B,H,W,C] receives the gathered+masked gradient for the apply pass; x / y_out / dx are [B,H,W,C]. */
+ * gradient); `g_scratch` [B,H,W,C] receives the gathered+masked gradient for the apply pass (NULL: the apply pass gathers
+ * again instead); x / y_out / dx are [B,H,W,C]; y_out may be NULL when `pool_idx` already encodes the ReLU decision (255 marks
+ * of pm_bn_relu_maxpool_fwd_bf16). */
 int pm_bn_bwd_fused_pool_f32(const float* dpool, const uint8_t* pool_idx, int B, int H, int W, const float* y_out, const float* x,
                              const float* mean, const float* invstd, const float* gamma, int C, double* ws, float* g_scratch,
                              float* dx, float* dgamma, float* dbeta, pm_stream_t s);

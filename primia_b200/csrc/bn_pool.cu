@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(BT, 2)
 bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_idx, PoolGeo pg, const T* __restrict__ y_out,
                     const T* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta_mask /* != NULL: ReLU decision recomputed from x (no y_out read) */,
                     size_t P, int C, double invP, double* __restrict__ partial /* [grid][2C] */,
                     double* __restrict__ totals /* [2C] */, unsigned* __restrict__ sync /* [2] */, T* __restrict__ g_out,
                     T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -358,9 +359,14 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
   const size_t rows_per_block = ((P + gridDim.x - 1) / gridDim.x + rpb - 1) / rpb * rpb;
   const size_t row_begin = (size_t)blockIdx.x * rows_per_block;
   const size_t row_end = row_begin + rows_per_block < P ? row_begin + rows_per_block : P;
-  float mu[V], is[V];
+  float mu[V], is[V], msc[V], mbe[V];
 #pragma unroll
-  for (int k = 0; k < V; ++k) { mu[k] = mean[c + k]; is[k] = invstd[c + k]; }
+  for (int k = 0; k < V; ++k) {
+    mu[k] = mean[c + k]; is[k] = invstd[c + k];
+    // the forward's bf16-mode evaluation (bn_apply_kernel): t = (x - mu) * (invstd * gamma) + beta ; y > 0 <=> t > 0
+    msc[k] = beta_mask ? is[k] * gamma[c + k] : 0.f;
+    mbe[k] = beta_mask ? beta_mask[c + k] : 0.f;
+  }
 
   // ---- phase 1: per-block partial sums of g and g * xhat (g = dy masked by the ReLU decision)
   acc_t s0[V], s1[V];
@@ -386,6 +392,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
         for (int k = 0; k < V; ++k) {
           float gg = g[u][k];
           if (y_out) gg = yv[u][k] > 0.f ? gg : 0.f;
+          else if (beta_mask) gg = ((xv[u][k] - mu[k]) * msc[k] + mbe[k]) > 0.f ? gg : 0.f;
           g[u][k] = gg;
           s0[k] += (acc_t)gg;
           s1[k] += (acc_t)(gg * ((xv[u][k] - mu[k]) * is[k]));
@@ -464,13 +471,16 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
   }
   const T* gsrc = g_out ? g_out : dy;   // the masked gradient was materialised in phase 1 when g_out != NULL
   const T* ymask = g_out ? nullptr : y_out;
+  const bool xmask = beta_mask != nullptr && g_out == nullptr && y_out == nullptr;
   for (size_t row = row_begin + r0; row < row_end; row += (size_t)rpb * U) {
     float g[U][V], xv[U][V], yv[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const size_t r = row + (size_t)u * rpb;
       if (r < row_end) {
-        Vec<T>::load(gsrc + r * C + c, g[u]);  // POOL: phase 1 materialised the gathered (and masked) gradient in g_out
+        // POOL: the gathered gradient is either re-read from g_out (materialised in phase 1) or gathered again
+        if (POOL && !g_out) load_pool_grad<T>(dy, pool_idx, pg, r, C, c, g[u]);
+        else Vec<T>::load(gsrc + r * C + c, g[u]);
         Vec<T>::load(x + r * C + c, xv[u]);
         if (ymask) Vec<T>::load(ymask + r * C + c, yv[u]);
       }
@@ -483,6 +493,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
         for (int k = 0; k < V; ++k) {
           float gg = g[u][k];
           if (ymask) gg = yv[u][k] > 0.f ? gg : 0.f;
+          else if (xmask) gg = ((xv[u][k] - mu[k]) * msc[k] + mbe[k]) > 0.f ? gg : 0.f;
           if (sizeof(T) == 4) {
             const double isd = (double)is[k];
             const double xhat = ((double)xv[u][k] - (double)mu[k]) * isd;
@@ -501,7 +512,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
 template <typename T>
 int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma, size_t P,
                    int C, double* ws, T* g_out, T* dx, float* dgamma, float* dbeta, pm_stream_t s,
-                   const uint8_t* pool_idx = nullptr, PoolGeo pg = PoolGeo{0, 0, 0, 0}) {
+                   const uint8_t* pool_idx = nullptr, PoolGeo pg = PoolGeo{0, 0, 0, 0}, const float* beta_mask = nullptr) {
   PM_CHECK_ARG(dy && x && mean && invstd && gamma && ws && dx && P > 0 && chan_ok<T>(C) && ((dgamma == nullptr) == (dbeta == nullptr)));
   PM_CHECK_ARG(g_out != dx);
   const int rpb = BT / (C / Vec<T>::N);
@@ -515,13 +526,16 @@ int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, c
   double* totals = ws + 2;          // [2][2*512] (ping-pong in ATOMIC mode)
   double* partial = totals + 4 * 512;
   const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
+  PM_CHECK_ARG(!(beta_mask && y_out));  // the ReLU decision comes from y_out OR is recomputed from x, not both
   if (pool_idx) {
-    PM_CHECK_ARG(g_out != nullptr);  // scratch for the gathered gradient (written in phase 1, re-read in phase 2)
+    // g_out: optional scratch for the gathered gradient (written in phase 1, re-read in phase 2); NULL = gather twice
     bn_bwd_fused_kernel<T, true, sizeof(T) != 4><<<(int)blocks, BT, smem, S(s)>>>(
-        dy, pool_idx, pg, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+        dy, pool_idx, pg, y_out, x, mean, invstd, gamma, beta_mask, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx,
+        dgamma, dbeta);
   } else {
     bn_bwd_fused_kernel<T, false, sizeof(T) != 4><<<(int)blocks, BT, smem, S(s)>>>(
-        dy, nullptr, pg, y_out, x, mean, invstd, gamma, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx, dgamma, dbeta);
+        dy, nullptr, pg, y_out, x, mean, invstd, gamma, beta_mask, P, C, 1.0 / (double)P, partial, totals, sync, g_out, dx,
+        dgamma, dbeta);
   }
   PM_LAUNCH_OK();
 }
@@ -561,6 +575,214 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int H, int W, int C,
     Vec<T>::store(y + o, best);
 #pragma unroll
     for (int k = 0; k < V; ++k) idx[o + k] = (uint8_t)bi[k];
+  }
+}
+
+// ---- stem forward in one pass (bf16 throughput mode): BatchNorm (batch statistics finalised here) + ReLU + MaxPool2d(3,2,1).
+// The full-resolution activation is never written: one thread = one pooled output x one 16-byte channel group reads its
+// 3x3 window of conv outputs (each element is touched by <= 4 windows: L1/L2 hits).  BN followed by ReLU and the bf16
+// rounding is monotonic per channel (increasing for gamma*invstd >= 0, decreasing otherwise), so the window maximum of the
+// activation is the activation of the window max (min) of the RAW conv output: the 9-tap scan is a packed bf16x2
+// compare-select on sign-adjusted raw values and BN is evaluated once per output instead of once per tap.  The pooled
+// VALUE is exactly what bn_apply -> max-pool produce; the argmax is the first strict maximum of the raw values (ATen breaks
+// ties of the rounded activations by position; both are valid subgradients).  idx = argmax, or 255 when the maximum is
+// not positive: ReLU passes no gradient there, so the backward never needs the activation.
+__global__ void __launch_bounds__(BT)
+bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats, double Pd, float eps,
+                           float momentum, float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ rm,
+                           float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W,
+                           int C, int Ho, int Wo, size_t total, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx) {
+  constexpr int V = 8;
+  extern __shared__ float sp[];  // [3][C]: mu, invstd*gamma, beta
+  const double invPd = 1.0 / Pd;
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const double md = stats[ch] * invPd;
+    double var = stats[C + ch] * invPd - md * md;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)md;
+    const float ve = (float)(var + (double)eps);
+    float is = rsqrtf(ve);
+    is = is * (1.5f - 0.5f * ve * is * is);
+    if (blockIdx.x == 0) {
+      mean_out[ch] = m;
+      invstd_out[ch] = is;
+      if (rm) {
+        const double unbiased = Pd > 1.0 ? var * Pd / (Pd - 1.0) : var;
+        rm[ch] = (float)((1.0 - momentum) * (double)rm[ch] + momentum * md);
+        rv[ch] = (float)((1.0 - momentum) * (double)rv[ch] + momentum * unbiased);
+      }
+    }
+    sp[ch] = m;
+    sp[C + ch] = is * gamma[ch];
+    sp[2 * C + ch] = beta[ch];
+  }
+  __syncthreads();
+  const int CV = C / V;
+  // blockDim * gridDim is a multiple of CV (= C/8 <= 64 | 256): the channel group of a thread never changes
+  const int cv = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CV);
+  float mu[V], sc[V], be[V];
+  uint32_t flip[4];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = sp[cv * V + k]; sc[k] = sp[C + cv * V + k]; be[k] = sp[2 * C + cv * V + k]; }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) flip[q] = (sc[2 * q] < 0.f ? 0x8000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i / CV;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const size_t b = t / Ho;
+    uint32_t best[4], bi[4];
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int iw = ow * 2 - 1 + s2;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + ((b * H + ih) * W + iw) * C + cv * V);
+        const uint32_t v[4] = {raw.x ^ flip[0], raw.y ^ flip[1], raw.z ^ flip[2], raw.w ^ flip[3]};
+        const uint32_t tap2 = (uint32_t)(r * 3 + s2) * 0x10001u;
+        if (first) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { best[q] = v[q]; bi[q] = tap2; }
+          first = false;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v[q]),
+                                           *reinterpret_cast<const __nv_bfloat162*>(&best[q]));
+            best[q] = (v[q] & m) | (best[q] & ~m);
+            bi[q] = (tap2 & m) | (bi[q] & ~m);
+          }
+        }
+      }
+    }
+    float out[V];
+    uint8_t id[V];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t xm = best[q] ^ flip[q];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xm));
+      float a0 = (f.x - mu[2 * q]) * sc[2 * q] + be[2 * q];
+      float a1 = (f.y - mu[2 * q + 1]) * sc[2 * q + 1] + be[2 * q + 1];
+      a0 = a0 > 0.f ? a0 : 0.f;
+      a1 = a1 > 0.f ? a1 : 0.f;
+      out[2 * q] = a0;
+      out[2 * q + 1] = a1;
+      // the decision must be taken on the value as stored (bf16): a tiny positive that rounds to +0 passes no gradient
+      id[2 * q] = __bfloat162float(__float2bfloat16_rn(a0)) > 0.f ? (uint8_t)(bi[q] & 0xFF) : (uint8_t)255;
+      id[2 * q + 1] = __bfloat162float(__float2bfloat16_rn(a1)) > 0.f ? (uint8_t)((bi[q] >> 16) & 0xFF) : (uint8_t)255;
+    }
+    const size_t o = i * V;
+    Vec<__nv_bfloat16>::store(y + o, out);
+    *reinterpret_cast<uint2*>(idx + o) = *reinterpret_cast<const uint2*>(id);
+  }
+}
+
+// ---- stem backward (bf16 throughput mode): max-pool backward gathered from (dpool, idx) + BatchNorm backward, as a
+// reduce launch and an apply launch over 2x2 input blocks.  For MaxPool2d(3,2,1) on an even-sized input the 2x2 block at
+// (2k, 2j) receives gradient from at most four windows -- (k,j), (k,j+1), (k+1,j), (k+1,j+1) -- through nine fixed
+// (window, tap) pairs, so a thread loads four pooled vectors once and serves four input positions; idx == 255 (ReLU closed)
+// never matches a tap.  PHASE 0: s0 += g, s1 += g * xhat (double atomics per block).  PHASE 1: dx = gamma*invstd *
+// (g - mean(g) - xhat * mean(g*xhat)).
+template <int PHASE>
+__global__ void __launch_bounds__(BT)
+stem_pool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
+                        const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, double* __restrict__ sums, double invP, int H, int W, int C, size_t total,
+                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = 8;
+  using bf = __nv_bfloat16;
+  const int CV = C / V, Ho = H / 2, Wo = W / 2;
+  const int cv = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CV);
+  const int c = cv * V;
+  float mu[V], is[V], gi[V], mg[V], mgx[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    mu[k] = mean[c + k];
+    is[k] = invstd[c + k];
+    if (PHASE == 1) {
+      gi[k] = gamma[c + k] * is[k];
+      mg[k] = (float)(sums[c + k] * invP);
+      mgx[k] = (float)(sums[C + c + k] * invP);
+    }
+  }
+  if (PHASE == 1 && dgamma && blockIdx.x == 0 && threadIdx.x < CV) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) { dbeta[c + k] = (float)sums[c + k]; dgamma[c + k] = (float)sums[C + c + k]; }
+  }
+  float s0[V], s1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0.f;
+  // (window offset dk,dj ; tap) pairs feeding each of the four positions of the block: pos = (dy*2 + dx)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i / CV;
+    const int j = (int)(t % Wo); t /= Wo;
+    const int k2 = (int)(t % Ho);
+    const size_t b = t / Ho;
+    float d[4][V];
+    uint8_t id[4][V];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int ok = k2 + (w >> 1), oj = j + (w & 1);
+      if (ok < Ho && oj < Wo) {
+        const size_t o = ((b * Ho + ok) * Wo + oj) * C + c;
+        Vec<bf>::load(dpool + o, d[w]);
+        *reinterpret_cast<uint2*>(id[w]) = *reinterpret_cast<const uint2*>(idx + o);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { d[w][k] = 0.f; id[w][k] = 255; }
+      }
+    }
+    float xv[4][V];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      Vec<bf>::load(x + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c, xv[p]);
+    float g[4][V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      g[0][k] = id[0][k] == 4 ? d[0][k] : 0.f;
+      g[1][k] = (id[0][k] == 5 ? d[0][k] : 0.f) + (id[1][k] == 3 ? d[1][k] : 0.f);
+      g[2][k] = (id[0][k] == 7 ? d[0][k] : 0.f) + (id[2][k] == 1 ? d[2][k] : 0.f);
+      g[3][k] = (id[0][k] == 8 ? d[0][k] : 0.f) + (id[1][k] == 6 ? d[1][k] : 0.f) + (id[2][k] == 2 ? d[2][k] : 0.f) +
+                (id[3][k] == 0 ? d[3][k] : 0.f);
+    }
+    if (PHASE == 0) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          s0[k] += g[p][k];
+          s1[k] += g[p][k] * ((xv[p][k] - mu[k]) * is[k]);
+        }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float o8[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float xhat = (xv[p][k] - mu[k]) * is[k];
+          o8[k] = gi[k] * (g[p][k] - mg[k] - xhat * mgx[k]);
+        }
+        Vec<bf>::store(dx + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c, o8);
+      }
+    }
+  }
+  if (PHASE == 0) {
+    // block reduction over the threads that share a channel group, then one double atomic per channel per block
+    __shared__ float red[2][BT][V + 1];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s0[k]; red[1][threadIdx.x][k] = s1[k]; }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * C; q += BT) {
+      const int which = q / C, ch = q % C, vv = ch / V, kk = ch % V;
+      double acc = 0.0;
+      // threads with (tid % CV) == vv hold this channel (the block's first thread index is a multiple of CV)
+      for (int tdx = vv; tdx < BT; tdx += CV) acc += (double)red[which][tdx][kk];
+      atomicAdd(sums + q, acc);
+    }
   }
 }
 
@@ -773,6 +995,43 @@ int pm_bn_bwd_fused_bf16(const void* dy, const void* y_out, const void* x, const
                          pm_stream_t s) {
   return bn_bwd_fused_t<bf16>((const bf16*)dy, (const bf16*)y_out, (const bf16*)x, mean, invstd, gamma, P, C, ws, (bf16*)g_out,
                               (bf16*)dx, dgamma, dbeta, s);
+}
+
+int pm_bn_bwd_fused_xmask_bf16(const void* dy, const void* x, const float* mean, const float* invstd, const float* gamma,
+                               const float* beta, size_t P, int C, double* ws, void* dx, float* dgamma, float* dbeta,
+                               pm_stream_t s) {
+  PM_CHECK_ARG(beta != nullptr);
+  return bn_bwd_fused_t<bf16>((const bf16*)dy, nullptr, (const bf16*)x, mean, invstd, gamma, P, C, ws, nullptr, (bf16*)dx, dgamma,
+                              dbeta, s, nullptr, PoolGeo{0, 0, 0, 0}, beta);
+}
+
+int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H, int W, int C, float eps, float momentum,
+                                const float* gamma, const float* beta, void* y, uint8_t* idx, float* mean, float* invstd,
+                                float* running_mean, float* running_var, pm_stream_t s) {
+  PM_CHECK_ARG(x && stats && gamma && beta && y && idx && mean && invstd && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
+  PM_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * Ho * Wo * (C / 8);
+  PM_CHECK_ARG(BT % (C / 8) == 0);
+  bn_relu_maxpool_fwd_kernel<<<pm_grid(total, BT, 1, 16), BT, 3 * C * sizeof(float), S(s)>>>(
+      (const bf16*)x, stats, (double)B * H * W, eps, momentum, mean, invstd, running_mean, running_var, gamma, beta, H, W, C, Ho, Wo,
+      total, (bf16*)y, idx);
+  PM_LAUNCH_OK();
+}
+
+int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* x, const float* mean,
+                             const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
+                             float* dbeta, pm_stream_t s) {
+  PM_CHECK_ARG(dpool && pool_idx && x && mean && invstd && gamma && sums && dx && B > 0 && H > 0 && W > 0);
+  PM_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && BT % (C / 8) == 0 && ((dgamma == nullptr) == (dbeta == nullptr)));
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  const int grid = pm_grid(total, BT, 1, 8);
+  const double invP = 1.0 / ((double)B * H * W);
+  stem_pool_bn_bwd_kernel<0><<<grid, BT, 0, S(s)>>>((const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd, gamma, sums, invP, H,
+                                                    W, C, total, nullptr, nullptr, nullptr);
+  stem_pool_bn_bwd_kernel<1><<<grid, BT, 0, S(s)>>>((const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd, gamma, sums, invP, H,
+                                                    W, C, total, (bf16*)dx, dgamma, dbeta);
+  PM_LAUNCH_OK();
 }
 
 int pm_bn_bwd_fused_pool_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* y_out, const void* x,

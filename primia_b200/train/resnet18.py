@@ -64,6 +64,10 @@ class ResNet18Engine:
         self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
         self.fuse_bn_bwd = True  # BN backward as one launch with a grid barrier
         self.overlap_wgrad = mode == "bf16"
+        # bf16 throughput mode: the stem's BN + ReLU + max-pool run as one pass (the 112x112 activation is never written) and
+        # BN backward recomputes the ReLU decision from x instead of reading the stored activation where no residual is added
+        self.fuse_stem_pool = mode == "bf16"
+        self.bn_xmask = mode == "bf16"
         self._side = None
         self._build_graph()
         self._alloc()
@@ -346,6 +350,12 @@ class ResNet18Engine:
 
     def _bn_bwd(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
         C = self.bns[bn]
+        if self.fuse_bn_bwd and self.bn_xmask and self.mode == "bf16" and y_out is not None and g_out is None and self.training:
+            # BN -> ReLU with no residual: the mask is recomputed from x (two fewer passes over an activation-sized tensor)
+            call("pm_bn_bwd_fused_xmask_bf16", ptr(dy), ptr(x), ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]),
+                 ptr(self.p[bn + ".weight"]), ptr(self.p[bn + ".bias"]), P, C, ptr(self.bn_bwd_ws), ptr(dx),
+                 ptr(self.g[bn + ".weight"]), ptr(self.g[bn + ".bias"]), stream())
+            return
         if self.fuse_bn_bwd:
             call("pm_bn_bwd_fused" + self.sfx, ptr(dy), ptr(y_out) if y_out is not None else None, ptr(x), ptr(self.bn_mean[bn]),
                  ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".weight"]), P, C, ptr(self.bn_bwd_ws), ptr(g_out) if g_out is not None else None,
@@ -387,9 +397,19 @@ class ResNet18Engine:
             c1 = self.convs["conv1"]
             self._conv_fwd(c1 if self.mode == "f32" else self.c1_gemm, self.x0, self.act["conv1"],
                            self._stat_slot(bn_ids["bn1"]) if fuse else None)
-            self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
-            call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
-                 ptr(self.pool_idx), stream())
+            self._stem_pool_fused = bool(self.mode == "bf16" and self.training and self.fuse_stem_pool and c1.Ho % 2 == 0
+                                         and c1.Wo % 2 == 0)
+            if self._stem_pool_fused:
+                if not fuse:
+                    call("pm_bn_stats_bf16", ptr(self.act["conv1"]), c1.P, 64, ptr(self._stat_slot(bn_ids["bn1"])), stream())
+                call("pm_bn_relu_maxpool_fwd_bf16", ptr(self.act["conv1"]), ptr(self._stat_slot(bn_ids["bn1"])), self.B, c1.Ho,
+                     c1.Wo, 64, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM), ptr(self.p["bn1.weight"]),
+                     ptr(self.p["bn1.bias"]), ptr(self.act["p1"]), ptr(self.pool_idx), ptr(self.bn_mean["bn1"]),
+                     ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.running_mean"]), ptr(self.p["bn1.running_var"]), stream())
+            else:
+                self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
+                call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
+                     ptr(self.pool_idx), stream())
             xin = self.act["p1"]
             for pre, ca, cb, ds in self.blocks:
                 ia, ib = bn_ids[pre + ".bn1"], bn_ids[pre + ".bn2"]
@@ -460,7 +480,14 @@ class ResNet18Engine:
                 d_out = d_xin
             c1 = self.convs["conv1"]
             dc1 = self._gbuf(("dc1",), self.act["conv1"])
-            if self.fuse_bn_bwd:
+            if getattr(self, "_stem_pool_fused", False):
+                # the argmax table already encodes the ReLU decision (255 = no gradient): neither the 112x112 activation nor a
+                # full-resolution gradient is ever materialised; reduce + apply launches over 2x2 input blocks
+                call("pm_stem_pool_bn_bwd_bf16", ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["conv1"]),
+                     ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
+                     ptr(self._stat_slot(len(self.bns) + bn_ids["bn1"])), ptr(dc1), ptr(self.g["bn1.weight"]),
+                     ptr(self.g["bn1.bias"]), stream())
+            elif self.fuse_bn_bwd:
                 # max-pool backward is gathered inside the stem's BN backward (no full-resolution gradient round trip)
                 call("pm_bn_bwd_fused_pool" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["a1"]),
                      ptr(self.act["conv1"]), ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
