@@ -174,6 +174,10 @@ int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void*
 /* NB: the bf16 wgrad ACCUMULATES into dw (fp32 red.add over pixel splits): the caller zeroes dw (the engine clears the whole
  * flat gradient buffer once per step). */
 int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, void* ws, pm_stream_t s);
+/* diagnostics for the halo-strip 3x3 kernel (conv_halo.cu): enable != 0 makes the next launches record per-CTA wait / busy
+ * cycle counters; out_host (may be NULL) receives the [160][8] int64 counters of the last profiled launch, then the event
+ * count and up to 256 (code, clock) pairs of CTA 0's trace: 160*8 + 1 + 512 int64 in all. */
+int pm_halo_prof(int enable, int64_t* out_host);
 
 /* BatchNorm2d (training) -- F.batch_norm, models.py:261,264,382 ; P = B*H*W rows of C channels.
  * stats: [2*C] doubles (sum, sumsq), zeroed by the caller. */

@@ -452,6 +452,9 @@ int tc_wgrad_splits(const pm_conv_t* p, int BN) {
 int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, cudaStream_t st);
 int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
 int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
+// halo-strip variant for 3x3 / stride 1 / pad 1 (conv_halo.cu), same return convention
+int pm_halo_conv(const pm_conv_t* p, const void* src, const void* wmat, void* dst, int accumulate, double* stats, int flip,
+                 cudaStream_t st);
 static bool use_tma() {
   const char* e = getenv("PRIMIA_NO_TMA");
   return !(e && e[0] == '1');
@@ -462,6 +465,9 @@ extern "C" {
 int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, double* stats, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && x && w && y);
   if (use_tma()) {
+    const int rh = pm_halo_conv(p, x, w, y, 0, stats, 0, S(s));
+    if (rh == 2) return pm_set_err(__FILE__, __LINE__, "halo conv fwd setup failed");
+    if (rh == 0) PM_LAUNCH_OK();
     const int r = pm_tma_conv_fwd(p, x, w, y, stats, S(s));  // statistics fused into the epilogue
     if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv fwd setup failed");
     if (r == 0) PM_LAUNCH_OK();
@@ -474,6 +480,9 @@ int pm_conv_fwd_bf16(const pm_conv_t* p, const void* x, const void* w, void* y, 
 int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && dy && wt && dx && p->C % 64 == 0);
   if (use_tma()) {
+    const int rh = pm_halo_conv(p, dy, wt, dx, accumulate, nullptr, 1, S(s));
+    if (rh == 2) return pm_set_err(__FILE__, __LINE__, "halo conv dgrad setup failed");
+    if (rh == 0) PM_LAUNCH_OK();
     const int r = pm_tma_conv_dgrad(p, dy, wt, dx, accumulate, S(s));
     if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv dgrad setup failed");
     if (r == 0) PM_LAUNCH_OK();

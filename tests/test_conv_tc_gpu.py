@@ -19,6 +19,11 @@ CASES = [  # B, H, C, K, R, stride, pad
     (1, 14, 512, 512, 3, 1, 1),
     (5, 12, 64, 64, 3, 1, 1),       # 128-pixel tiles straddle image boundaries (144 px / image)
     (2, 10, 128, 128, 3, 2, 1),
+    (2, 56, 64, 64, 3, 1, 1),       # layer1 geometry (resident-weight halo kernel, 256-pixel tiles across image boundaries)
+    (3, 28, 128, 128, 3, 1, 1),     # layer2
+    (3, 14, 256, 256, 3, 1, 1),     # layer3 (two n-tiles share a strip)
+    (5, 7, 512, 512, 3, 1, 1),      # layer4 (8-pixel padded rows, 8 channel blocks)
+    (70, 14, 128, 128, 3, 1, 1),    # enough tiles for the 256-pixel variant with streamed weights, >1 tile per CTA
 ]
 
 
@@ -38,12 +43,15 @@ def bf(t):
     return t.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("no_tma", ["0", "1"])  # 0: TMA im2col producer where eligible; 1: cp.async gather everywhere
+# "halo": halo-strip kernel for 3x3/s1 + im2col-TMA producer elsewhere (the default); "tma": im2col-TMA producer wherever
+# eligible; "cpasync": cp.async gather everywhere
+@pytest.mark.parametrize("variant", ["halo", "tma", "cpasync"])
 @pytest.mark.parametrize("case", CASES)
-def test_fwd_dgrad_wgrad_bf16(case, no_tma, monkeypatch):
+def test_fwd_dgrad_wgrad_bf16(case, variant, monkeypatch):
     from primia_b200._lib import call, ptr, stream
 
-    monkeypatch.setenv("PRIMIA_NO_TMA", no_tma)
+    monkeypatch.setenv("PRIMIA_NO_TMA", "1" if variant == "cpasync" else "0")
+    monkeypatch.setenv("PRIMIA_NO_HALO", "0" if variant == "halo" else "1")
 
     B, H, C, K, R, s, p = case
     g = torch.Generator().manual_seed(sum(case))
@@ -109,3 +117,32 @@ def test_stem_im2col_plus_dense_gemm_matches_conv7x7():
     torch.cuda.synchronize()
     ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), None, 2, 3)
     assert rel(y.float().permute(0, 3, 1, 2), ref) < 4e-3
+
+
+def test_halo_conv_non_square_and_odd_sizes():
+    """Halo-strip kernel on H != W, odd widths and a batch that leaves a ragged last tile; accumulate on top of a gradient."""
+    from primia_b200._lib import ConvDesc, call, ptr, stream
+
+    g = torch.Generator().manual_seed(11)
+    for (B, H, W, C, K) in [(3, 9, 13, 64, 64), (2, 5, 31, 128, 64), (7, 3, 3, 64, 128), (1, 1, 1, 64, 64)]:
+        d = ConvDesc(B, H, W, C, K, 3, 3, 1, 1, H, W)
+        x = bf(torch.randn(B, H, W, C, generator=g))
+        w = bf(torch.randn(K, 3, 3, C, generator=g) * 0.1)
+        dy = bf(torch.randn(B, H, W, K, generator=g))
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = w.float().permute(0, 3, 1, 2)
+        yr = F.conv2d(xr, wr, None, 1, 1)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        xd, wd_, dyd = x.to(DEV), w.to(DEV), dy.to(DEV)
+        y = torch.full((B, H, W, K), 7.0, dtype=torch.bfloat16, device=DEV)
+        stats = torch.zeros(2 * K, dtype=torch.float64, device=DEV)
+        call("pm_conv_fwd_bf16", ctypes.byref(d), ptr(xd), ptr(wd_), ptr(y), ptr(stats), stream())
+        torch.cuda.synchronize()
+        assert rel(y.float().permute(0, 3, 1, 2), yr.detach()) < 4e-3, (B, H, W, C, K)
+        yf = y.double().reshape(-1, K)
+        assert rel(stats[:K], yf.sum(0)) < 1e-6 and rel(stats[K:], (yf * yf).sum(0)) < 1e-6
+        wt = w.permute(3, 1, 2, 0).contiguous().to(DEV)
+        dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+        call("pm_conv_dgrad_bf16", ctypes.byref(d), ptr(dyd), ptr(wt), ptr(dx), 0, stream())
+        torch.cuda.synchronize()
+        assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 4e-3, (B, H, W, C, K)
