@@ -174,6 +174,14 @@ int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void*
 /* NB: the bf16 wgrad ACCUMULATES into dw (fp32 red.add over pixel splits): the caller zeroes dw (the engine clears the whole
  * flat gradient buffer once per step). */
 int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, void* ws, pm_stream_t s);
+/* ResNet stem (conv 7x7 / stride 2 / pad 3, 3 -> 64; models.py:379,468) as a direct tcgen05 implicit GEMM over the fp32 NCHW
+ * batch -- no im2col matrix (conv_stem.cu).  w192: bf16 [64][192] produced by pm_stem_prep_w_bf16 from the fp32 KRSC master
+ * [64][7][7][3].  fwd: y bf16 NHWC [B,Ho,Wo,64], optional fused BatchNorm statistics stats[128] (sum, sum of squares; doubles,
+ * accumulated).  wgrad: dw fp32 KRSC [64][7][7][3] += sum_pix dy x (fp32 atomics: the caller zeroes dw). */
+int pm_stem_prep_w_bf16(const float* w_krsc, void* w192, pm_stream_t s);
+int pm_stem_conv_fwd_bf16(const float* x_nchw, const void* w192, int B, int H, int W, void* y, double* stats, pm_stream_t s);
+int pm_stem_conv_wgrad_bf16(const float* x_nchw, const void* dy, int B, int H, int W, float* dw_krsc, pm_stream_t s);
+
 /* diagnostics for the halo-strip 3x3 kernel (conv_halo.cu): enable != 0 makes the next launches record per-CTA wait / busy
  * cycle counters; out_host (may be NULL) receives the [160][8] int64 counters of the last profiled launch, then the event
  * count and up to 256 (code, clock) pairs of CTA 0's trace: 160*8 + 1 + 512 int64 in all. */

@@ -17,7 +17,8 @@
 //   warp 1 : tcgen05.mma issuer (M = 128 per instruction, MT/128 accumulators in TMEM, double-buffered across tiles);
 //   warp 2 : weight-tile producer ({64 k, BN} boxes, BSTAGES ring) -- or the whole weight matrix once when it fits (RB);
 //   warps 4.. : epilogue, 4 warps per 128-row accumulator: tcgen05.ld -> bf16 store (+ accumulate) and, for the forward,
-//            the BatchNorm batch statistics (sum, sum of squares of the bf16-rounded outputs) via a shuffle transpose-reduce.
+//            the BatchNorm batch statistics (sum, sum of squares of the bf16-rounded outputs); rows are staged through a per-warp
+//            shared-memory scratch so that global stores are 64-byte contiguous per row (tc_ptx.cuh: epilogue_chunk32).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
@@ -38,6 +39,7 @@ struct HGeo {
 // [cta][8]: 0 kernel, 1 mma wait strip, 2 mma wait weights, 3 mma wait tmem-empty, 4 epilogue wait tmem-full, 5 epilogue busy,
 //           6 strip producer wait empty, 7 weight producer wait empty   (clock64 ticks, summed over the CTA's tiles)
 __device__ long long halo_prof[160 * 8];
+__device__ long long halo_epi_prof[160 * 4];  // warp 4: tcgen05.ld+wait, epilogue_chunk32, (unused), chunks
 // CTA 0 event trace: [2*i] = event code, [2*i+1] = clock64 ; codes: 1 mma tile begin (after tmem-empty), 2 mma strip ready,
 // 3 mma tile issued, 4 epi(warp 4) accumulator ready, 5 epi done, 6 strip producer: slot free, 7 strip producer: rows issued
 __device__ long long halo_trace[2 * 256];
@@ -45,25 +47,6 @@ __device__ int halo_trace_n;
 #define TRACE(code) if (g.prof && blockIdx.x == 0) { const int _i = atomicAdd(&halo_trace_n, 1); if (_i < 256) { halo_trace[2 * _i] = (code); halo_trace[2 * _i + 1] = clock64(); } }
 #define PROF_T(var) const long long var = g.prof ? clock64() : 0
 #define PROF_ADD(acc, t0) if (g.prof) acc += clock64() - (t0)
-
-template <int OFF>
-__device__ __forceinline__ void red_step(float (&x)[32], int lane) {
-  const bool up = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float send = up ? x[i] : x[i + OFF];
-    const float keep = up ? x[i + OFF] : x[i];
-    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-  }
-}
-// lane L holds 32 column values of row L  ->  x[0] of lane L = sum over the 32 rows of column L   (31 shuffles)
-__device__ __forceinline__ void col_sums32(float (&x)[32], int lane) {
-  red_step<16>(x, lane);
-  red_step<8>(x, lane);
-  red_step<4>(x, lane);
-  red_step<2>(x, lane);
-  red_step<1>(x, lane);
-}
 
 constexpr int SSTAGES = 2;
 constexpr int BSTAGES = 4;
@@ -88,10 +71,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tfull0 = bempty0 + 8 * BSTAGES, tempty0 = tfull0 + 16, bres = tempty0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SSTAGES + 2 * BSTAGES + 5);
   float* cta_stats = reinterpret_cast<float*>(bars + 2 * SSTAGES + 2 * BSTAGES + 6);  // [2][N]
+  uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + 2 * g.N);              // [4 * NH warps][2048]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   PROF_T(t_kernel);
-  long long pw0 = 0, pw1 = 0, pw2 = 0;
+  long long pw0 = 0, pw1 = 0, pw2 = 0, pe0 = 0, pe1 = 0, pe3 = 0;
   const int cblocks = g.Cin / 64;
   const int nkb = 9 * cblocks;
   const int ntn = g.N / BN;
@@ -249,10 +233,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (4 warps per 128-row accumulator)
     const int j = (warp - 4) >> 2, quad = warp & 3;
+    uint8_t* epi_scr = epi_scr_all + (warp - 4) * 2048;
+    float st[BN / 32][4];  // BatchNorm partial sums of this warp's rows, per 32-column chunk, kept across tiles
+#pragma unroll
+    for (int cc = 0; cc < BN / 32; ++cc)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st[cc][k] = 0.f;
+    int st_n0 = -1;
     int lt = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int as = lt & 1;
       const int n0 = (tile % ntn) * BN;
+      if (do_stats && n0 != st_n0) {  // the column range changes between this CTA's tiles only if gridDim % ntn != 0
+        if (st_n0 >= 0) {
+#pragma unroll
+          for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, cta_stats + st_n0 + cc * 32, cta_stats + g.N + st_n0 + cc * 32);
+        }
+        st_n0 = n0;
+      }
       const int q = (tile / ntn) * MT + j * 128 + quad * 32 + lane;
       const int Rr = q / g.Wp, w = q - Rr * g.Wp;
       const int img = Rr / g.Hp, h = Rr - img * g.Hp;
@@ -264,57 +262,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       PROF_T(t1);
       tc_fence_after();
       const uint32_t tsrc = tmem_base + as * ACC_COLS + j * BN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t v[32];
+        PROF_T(e0);
         tmem_ld32_nowait(tsrc + cc * 32, v);
         tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qd * 8 + e]);
-            uint4* op = reinterpret_cast<uint4*>(out + cc * 32 + qd * 8);
-            if (accumulate) {
-              const uint4 old = *op;
-              const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = __bfloat1622float2(oh[e]);
-                f[2 * e] += t.x; f[2 * e + 1] += t.y;
-              }
-            }
-            uint4 pk;
-            __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-            *op = pk;
-          }
-        }
-        if (do_stats) {
-          // BatchNorm batch statistics of the bf16-rounded outputs (what a separate pass would read back from HBM)
-          float x1[32], x2[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float t = valid ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[e]))) : 0.f;
-            x1[e] = t;
-            x2[e] = t * t;
-          }
-          col_sums32(x1, lane);
-          col_sums32(x2, lane);
-          atomicAdd(&cta_stats[n0 + cc * 32 + lane], x1[0]);
-          atomicAdd(&cta_stats[g.N + n0 + cc * 32 + lane], x2[0]);
-        }
+        PROF_ADD(pe0, e0);
+        PROF_T(e1);
+        epilogue_chunk32(v, valid, out + cc * 32, accumulate != 0, do_stats, epi_scr, lane, st[cc]);
+        PROF_ADD(pe1, e1);
+        ++pe3;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);  // this warp is done reading the accumulator stage
       PROF_ADD(pw1, t1);
     }
+    if (do_stats && st_n0 >= 0) {
+#pragma unroll
+      for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, cta_stats + st_n0 + cc * 32, cta_stats + g.N + st_n0 + cc * 32);
+    }
     if (g.prof && tid == 128) {
       halo_prof[blockIdx.x * 8 + 4] = pw0;
       halo_prof[blockIdx.x * 8 + 5] = pw1;
+      halo_epi_prof[blockIdx.x * 4 + 0] = pe0;
+      halo_epi_prof[blockIdx.x * 4 + 1] = pe1;
+      halo_epi_prof[blockIdx.x * 4 + 3] = pe3;
     }
   }
   __syncthreads();
@@ -373,7 +347,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* 
   const int max_rows = (g.Wp - 1 + MT + 2 * g.Wp + 1) / g.Wp + 1;
   g.strip_bytes = (max_rows * g.Wp * 128 + 1023) / 1024 * 1024;
   g.b_bytes = RB ? 9 * (g.Cin / 64) * BN * 128 : BSTAGES * BN * 128;
-  const int smem = SSTAGES * g.strip_bytes + g.b_bytes + 256 + 2 * g.N * 4 + 1024;
+  const int smem = SSTAGES * g.strip_bytes + g.b_bytes + 256 + 2 * g.N * 4 + (MT / 32) * 2048 + 1024;
   if (smem > 227 * 1024) return 1;
   auto kern = conv_halo_kernel<MT, BN, FLIP, RB>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;
@@ -393,7 +367,7 @@ extern "C" int pm_halo_prof(int enable, int64_t* out_host /* [160*8 + 1 + 512] o
     int n = 0;
     if (cudaMemcpyFromSymbol(&n, halo::halo_trace_n, sizeof(int)) != cudaSuccess) return 1;
     out_host[160 * 8] = n < 256 ? n : 256;
-    if (cudaMemcpyFromSymbol(out_host + 160 * 8 + 1, halo::halo_trace, sizeof(long long) * 512) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(out_host + 160 * 8 + 1, halo::halo_epi_prof, sizeof(long long) * 512) != cudaSuccess) return 1;
   }
   if (enable) {
     const int zero = 0;

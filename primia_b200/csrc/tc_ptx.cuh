@@ -112,4 +112,89 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- epilogue of one [32 rows x 32 columns] accumulator chunk held as tcgen05.ld 32x32b registers (lane = row).
+// Writing each lane's row straight to global memory costs one 16-byte store per 128-byte line and lane (32 LSU wavefronts per
+// instruction): the epilogue, not the MMA, then paces N = 64 layers.  Instead the warp stages the bf16 rows in a 2 KB
+// shared-memory scratch (64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3: conflict-free for the row-wise writes,
+// the 4-lanes-per-row reads and the column reads) and (1) stores 8 rows x 64 contiguous bytes per instruction, (2) optionally
+// adds into the existing bf16 values (dgrad accumulate), (3) optionally accumulates the per-column sum / sum of squares of the
+// ROUNDED values (BatchNorm batch statistics) into per-lane registers, flushed with stats_flush32.
+//   valid: this lane's row exists ; out: its global address at the chunk's first column (ignored when !valid).
+__device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], bool valid, __nv_bfloat16* out, bool accumulate,
+                                                 bool do_stats, uint8_t* scr /* 2048 B, this warp's */, int lane,
+                                                 float (&st)[4] /* this lane's running partial sums (see stats_flush32) */) {
+  {
+    const uint32_t swz = (uint32_t)(lane >> 1) & 3u;
+    uint8_t* my = scr + lane * 64;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pk;
+      __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+      if (!valid) pk = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(my + (((uint32_t)q ^ swz) << 4)) = pk;
+    }
+  }
+  __syncwarp();
+  {
+    // 4 lanes per row, 8 rows per instruction: all shuffles, then all shared-memory reads, then the (predicated) global
+    // accesses -- independent instruction streams instead of four dependent shuffle -> load -> store chains
+    const int sub = lane & 3, r0 = lane >> 2;
+    const unsigned long long mine = valid ? (unsigned long long)(uintptr_t)out : 0ull;
+    unsigned long long p[4];
+    uint4 nv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __shfl_sync(0xffffffffu, mine, i * 8 + r0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + r0;
+      nv[i] = *reinterpret_cast<const uint4*>(scr + r * 64 + ((((uint32_t)sub) ^ ((uint32_t)(r >> 1) & 3u)) << 4));
+    }
+    if (accumulate) {
+      uint4 old[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) old[i] = p[i] ? *(reinterpret_cast<const uint4*>((uintptr_t)p[i]) + sub) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old[i]);
+        __nv_bfloat162* nh = reinterpret_cast<__nv_bfloat162*>(&nv[i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(nh[e]), b = __bfloat1622float2(oh[e]);
+          nh[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (p[i]) *(reinterpret_cast<uint4*>((uintptr_t)p[i]) + sub) = nv[i];
+  }
+  if (do_stats) {
+    // lane = (column pair cp, row parity): partial sums of its 16 rows stay in registers across tiles (shared-memory float
+    // atomics are CAS loops: ~1000 clk per chunk when 8 warps hit the same 64 addresses)
+    const int cp = lane & 15, par = lane >> 4;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = 2 * i + par;
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(scr + r * 64 + ((((uint32_t)(cp >> 2)) ^ ((uint32_t)(r >> 1) & 3u)) << 4) + (cp & 3) * 4);
+      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+      st[0] += x0; st[1] += x1;
+      st[2] = fmaf(x0, x0, st[2]); st[3] = fmaf(x1, x1, st[3]);
+    }
+  }
+  __syncwarp();  // the scratch is reused by the next chunk
+}
+// adds the warp's partial sums of one 32-column chunk into s1[32] / s2[32] (shared memory) and clears them
+__device__ __forceinline__ void stats_flush32(float (&st)[4], int lane, float* s1, float* s2) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] += __shfl_xor_sync(0xffffffffu, st[k], 16);
+  if (lane < 16) {
+    atomicAdd(s1 + 2 * lane, st[0]); atomicAdd(s1 + 2 * lane + 1, st[1]);
+    atomicAdd(s2 + 2 * lane, st[2]); atomicAdd(s2 + 2 * lane + 1, st[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] = 0.f;
+}
+
 }  // namespace tcx

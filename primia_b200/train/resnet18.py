@@ -16,6 +16,7 @@ There is no PyTorch fallback: every arithmetic op is a C-ABI call.
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -68,6 +69,10 @@ class ResNet18Engine:
         # BN backward recomputes the ReLU decision from x instead of reading the stored activation where no residual is added
         self.fuse_stem_pool = mode == "bf16"
         self.bn_xmask = mode == "bf16"
+        # bf16 stem as a direct implicit GEMM over the fp32 NCHW input (conv_stem.cu): no im2col matrix.  The im2col + dense
+        # GEMM route stays for other channel counts and as the cross-check (PRIMIA_NO_DIRECT_STEM=1).
+        self.direct_stem = mode == "bf16" and in_channels == 3 and os.environ.get("PRIMIA_NO_DIRECT_STEM", "0") != "1"
+        self._x_in = None
         self._side = None
         self._build_graph()
         self._alloc()
@@ -152,7 +157,11 @@ class ResNet18Engine:
         if self.mode == "f32":
             self.x0 = A(B, self.size, self.size, self.cin)
         else:
-            self.x0 = A(B, c1.Ho, c1.Wo, self.stem_kpad)  # im2col of the input
+            if self.direct_stem:
+                self.x0 = None
+                self.w_stem = torch.zeros((64, 192), dtype=torch.bfloat16, device=dev)  # k = (r*3 + c)*8 + s
+            else:
+                self.x0 = A(B, c1.Ho, c1.Wo, self.stem_kpad)  # im2col of the input
             self.dw_stem = torch.zeros((64, self.stem_kpad), dtype=f32, device=dev)
         self.act = {}   # forward tensors
         self.grad = {}  # backward tensors
@@ -377,12 +386,18 @@ class ResNet18Engine:
         x_nchw = x_nchw.contiguous()
         if self.mode == "f32":
             call("pm_nchw_to_nhwc_f32", ptr(x_nchw), self.B, self.cin, self.size, self.size, ptr(self.x0), stream())
+        elif self.direct_stem:
+            if x_nchw.dtype != torch.float32:
+                raise PrimiaError("the stem kernel reads the fp32 NCHW batch the reference's loader produces")
+            self._x_in = x_nchw  # read in place by the stem forward and (later) its weight gradient
         else:
             call("pm_im2col_stem_bf16", ptr(x_nchw), self.B, self.cin, self.size, self.size, 7, 2, 3, self.stem_kpad, ptr(self.x0),
                  stream())
 
     def refresh_bf16_weights(self):
         call("pm_krsc_to_bf16_batched", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_tiles, stream())
+        if self.direct_stem:
+            call("pm_stem_prep_w_bf16", ptr(self.p["conv1.weight"]), ptr(self.w_stem), stream())
 
     def forward(self, x_nchw=None):
         with torch.cuda.device(self.device):
@@ -395,8 +410,14 @@ class ResNet18Engine:
             bn_ids = {bn: i for i, bn in enumerate(self.bns)}
             fuse = self.mode == "bf16" and self.training and self.fuse_stats
             c1 = self.convs["conv1"]
-            self._conv_fwd(c1 if self.mode == "f32" else self.c1_gemm, self.x0, self.act["conv1"],
-                           self._stat_slot(bn_ids["bn1"]) if fuse else None)
+            if self.direct_stem:
+                e0 = self._prof_begin()
+                call("pm_stem_conv_fwd_bf16", ptr(self._x_in), ptr(self.w_stem), self.B, self.size, self.size, ptr(self.act["conv1"]),
+                     ptr(self._stat_slot(bn_ids["bn1"])) if fuse else None, stream())
+                self._prof_end(e0)
+            else:
+                self._conv_fwd(c1 if self.mode == "f32" else self.c1_gemm, self.x0, self.act["conv1"],
+                               self._stat_slot(bn_ids["bn1"]) if fuse else None)
             self._stem_pool_fused = bool(self.mode == "bf16" and self.training and self.fuse_stem_pool and c1.Ho % 2 == 0
                                          and c1.Wo % 2 == 0)
             if self._stem_pool_fused:
@@ -500,18 +521,24 @@ class ResNet18Engine:
             if self.mode == "f32":
                 self._conv_wgrad(c1, self.x0, dc1)
             else:
+                def stem_wgrad():
+                    if self.direct_stem:  # accumulates straight into the (cleared) KRSC gradient
+                        call("pm_stem_conv_wgrad_bf16", ptr(self._x_in), ptr(dc1), self.B, self.size, self.size,
+                             ptr(self.g["conv1.weight"]), stream())
+                    else:
+                        call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
+                        self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
+
                 if self._side is not None and self._prof is None:
                     ev = torch.cuda.Event()
                     ev.record()
                     self._side.wait_event(ev)
                     with torch.cuda.stream(self._side):
-                        call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
-                        self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
+                        stem_wgrad()
                 else:
                     e0 = self._prof_begin()
-                    call("pm_conv_wgrad_bf16", ctypes.byref(self.c1_gemm.desc), ptr(self.x0), ptr(dc1), ptr(self.dw_stem), None, stream())
+                    stem_wgrad()
                     self._prof_end(e0)
-                    self.g["conv1.weight"].view(64, -1).copy_(self.dw_stem[:, : 7 * 7 * self.cin])
             if self._side is not None:
                 torch.cuda.current_stream().wait_stream(self._side)  # join: the optimizer needs every weight gradient
         return self.loss

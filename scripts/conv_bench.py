@@ -66,6 +66,10 @@ for name, H, C, K in LAYERS:
         call("pm_halo_prof", 0, buf.ctypes.data_as(ctypes.c_void_p))
         pr = buf[:160 * 8].reshape(160, 8)[:148]
         pr = pr[pr[:, 0] > 0]
+        ep = buf[160 * 8 + 1:160 * 8 + 1 + 128 * 4].reshape(128, 4)
+        ep = ep[ep[:, 3] > 0]
+        if len(ep):
+            print(f"{'':24s} {op} epilogue (warp 4) per chunk: tcgen05.ld+wait {ep[:, 0].sum() / ep[:, 3].sum():.0f} clk, stage+store(+stats) {ep[:, 1].sum() / ep[:, 3].sum():.0f} clk, chunks/CTA {ep[:, 3].mean():.1f}")
         ntr = int(buf[160 * 8])
         tr = buf[160 * 8 + 1:160 * 8 + 1 + 2 * ntr].reshape(ntr, 2)
         t0 = tr[tr[:, 0] == 0][0, 1] if (tr[:, 0] == 0).any() else tr[:, 1].min()

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(192, 1) rate(const __grid_constant__ CUtensorM
       const uint64_t adesc = make_desc(a_s + ta * 17408 + ((mode & 1) ? 384 : 0), 16, 1024);
       const uint64_t bdesc = make_desc(b_s + tb * N * 128, 16, 1024);
 #pragma unroll
+      if (mode & 1024) { const long long tt = clock64(); while (clock64() - tt < 256) { } continue; }
       for (int k = 0; k < 4; ++k) {
         const uint32_t acc = 1;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(adesc + (uint64_t)(k * 2)), "l"(bdesc + (uint64_t)(k * 2)), "r"(idesc), "r"(acc) : "memory");
@@ -116,7 +117,9 @@ __global__ void __launch_bounds__(192, 1) rate(const __grid_constant__ CUtensorM
     if (tid == 64) out[blockIdx.x * 2 + 297] = polls;
   } else if (warp >= 2 && (mode & 16)) {
     uint32_t sink = 0;
+    long long nld = 0;
     while (!*stop) {
+      ++nld;
       uint32_t v[32];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(192, 1) rate(const __grid_constant__ CUtensorM
       sink += v[0] + v[31];
     }
     if (sink == 0x12345678) out[0] = sink;
+    if (tid == 64) out[blockIdx.x * 2 + 297] = nld;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -141,11 +145,9 @@ void run(int grid, long long* d_out, const CUtensorMap& tm) {
   const int smem = 4 * 17408 + 2 * N * 128 + 4 * 16384 + 1024 + 128;
   cudaFuncSetAttribute(rate<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4096;
-  for (int cfg = 0; cfg < 10; ++cfg) {
-    const int mode = 64;
-    const int delays[10] = {0, 50, 100, 200, 400, 800, 100, 200, 400, 800};
-    const int groups[10] = {2, 2, 2, 2, 2, 2, 1, 1, 1, 1};  // iterations (of 4 MMAs) between delays
-    const int delay = delays[cfg], group = groups[cfg];
+  for (int cfg = 0; cfg < 2; ++cfg) {
+    const int mode = cfg == 0 ? 64 + 16 : 64 + 16 + 1024;   // tcgen05.ld loop in 4 warps, with / without the MMA stream
+    const int delay = 0, group = 2;
     cudaMemset(d_out, 0, sizeof(long long) * 4 * 148);
     rate<N><<<grid, 192, smem>>>(tm, iters, mode, d_out, delay, group);
     rate<N><<<grid, 192, smem>>>(tm, iters, mode, d_out, delay, group);
@@ -157,7 +159,7 @@ void run(int grid, long long* d_out, const CUtensorMap& tm) {
     for (int i = 0; i < grid; ++i) { issue += h[2 * i]; total += h[2 * i + 1]; }
     issue /= grid; total /= grid;
     const double per = total / (iters * 4.0), floor_clk = 128.0 * N / 256.0;
-    printf("N=%3d grid=%3d random=%d fence=%d commit=%d tmem_ld=%d tma=%d: issue %.1f clk/MMA, complete %.1f clk/MMA, floor %.0f -> %.1f %% of peak (tma loads/CTA %lld = %.1f B/clk) delay %d clk every %d MMAs -> ideal if hidden %.1f, if exposed %.1f\n", N, grid, (mode >> 6) & 1, (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, (mode >> 5) & 1, issue / (iters * 4.0), per, floor_clk, 100.0 * floor_clk / per, h[296], h[296] * 16384.0 / total, delay, group * 4, floor_clk, floor_clk + delay / (group * 4.0));
+    printf("N=%3d grid=%3d random=%d fence=%d commit=%d tmem_ld=%d tma=%d: issue %.1f clk/MMA, complete %.1f clk/MMA, floor %.0f -> %.1f %% of peak (tma loads/CTA %lld = %.1f B/clk) no_mma=%d: tcgen05.ld.32x32b.x32+wait per warp: %lld in %.0f clk = %.1f clk each\n", N, grid, (mode >> 6) & 1, (mode >> 2) & 1, (mode >> 3) & 1, (mode >> 4) & 1, (mode >> 5) & 1, issue / (iters * 4.0), per, floor_clk, 100.0 * floor_clk / per, h[296], h[296] * 16384.0 / total, (mode >> 10) & 1, h[297], total, total / (double)(h[297] ? h[297] : 1));
   }
 }
 

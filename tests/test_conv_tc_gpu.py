@@ -146,3 +146,36 @@ def test_halo_conv_non_square_and_odd_sizes():
         call("pm_conv_dgrad_bf16", ctypes.byref(d), ptr(dyd), ptr(wt), ptr(dx), 0, stream())
         torch.cuda.synchronize()
         assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 4e-3, (B, H, W, C, K)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 40, 40), (2, 224, 224), (1, 18, 300), (5, 7, 9)])
+def test_direct_stem_conv_fwd_and_wgrad(B, H, W):
+    """conv 7x7 / s2 / p3, 3 -> 64 straight from the fp32 NCHW batch (no im2col matrix): forward + fused BN statistics and
+    the weight gradient vs F.conv2d on the same bf16-rounded operands.  W = 300 gives two 128-pixel tiles per output row."""
+    from primia_b200._lib import call, ptr, stream
+
+    g = torch.Generator().manual_seed(B * 1000 + H + W)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    dy = bf(torch.randn(B, Ho, Wo, 64, generator=g))
+    xr = x.bfloat16().float().requires_grad_(False)
+    wr = w.bfloat16().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 2, 3)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    xd = x.to(DEV)
+    w_krsc = w.permute(0, 2, 3, 1).contiguous().to(DEV)           # fp32 master, KRSC
+    w192 = torch.empty(64, 192, dtype=torch.bfloat16, device=DEV)
+    call("pm_stem_prep_w_bf16", ptr(w_krsc), ptr(w192), stream())
+    y = torch.full((B, Ho, Wo, 64), 3.0, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(128, dtype=torch.float64, device=DEV)
+    call("pm_stem_conv_fwd_bf16", ptr(xd), ptr(w192), B, H, W, ptr(y), ptr(stats), stream())
+    torch.cuda.synchronize()
+    assert rel(y.float().permute(0, 3, 1, 2), yr.detach()) < 4e-3, "stem fwd"
+    yf = y.double().reshape(-1, 64)
+    assert rel(stats[:64], yf.sum(0)) < 1e-6 and rel(stats[64:], (yf * yf).sum(0)) < 1e-6, "fused BN statistics"
+    dyd = dy.to(DEV)
+    dw = torch.zeros(64, 7, 7, 3, dtype=torch.float32, device=DEV)
+    call("pm_stem_conv_wgrad_bf16", ptr(xd), ptr(dyd), B, H, W, ptr(dw), stream())
+    torch.cuda.synchronize()
+    assert rel(dw.permute(0, 3, 1, 2), wr.grad) < 1e-3, "stem wgrad"
