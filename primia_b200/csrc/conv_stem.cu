@@ -3,16 +3,19 @@
 //
 // Why: the im2col + dense-GEMM route writes and re-reads a [B*Ho*Wo, 192] bf16 matrix (308 MB at B = 64, three passes per
 // step).  Here producer warps build each [128 output pixels x 192 k] operand tile directly in shared memory, in the
-// SWIZZLE_128B image the tensor core expects, from a bf16 copy of the 7 input rows the tile needs.
+// SWIZZLE_128B image the tensor core expects, from the fp32 input patch (3 channels x 7 rows x 264 pixels) that TMA drops into
+// shared memory (tiled boxes straight over the NCHW tensor, out-of-image pixels zero-filled by the hardware).
 //
 // k order: k = (r*3 + c)*8 + s with s in 0..7 (s = 7 is a zero weight), 21 groups of 8 = 168, padded to 192 = 3 blocks of 64.
 // A 16-byte operand chunk (8 consecutive k) is then 8 CONSECUTIVE input pixels of one (channel, row): for output pixel m the
-// chunk of group (r, c) is x[c][2*oh-3+r][2*m-3 .. 2*m+4] -- four aligned 32-bit shared-memory loads and one 128-bit store.
+// chunk of group (r, c) is x[c][2*oh-3+r][2*m-3 .. 2*m+4] -- four aligned 64-bit shared-memory loads, four packed fp32->bf16
+// conversions and one 128-bit store.
 //
 // Tile = one output row segment of 128 pixels (b, oh, ow0).  Persistent CTA, 640 threads:
 //   warp 0      : MMA issuer (11 k-steps of M=128, N=64, K=16 per tile; accumulators double-buffered in TMEM)
 //   warp 1      : loads the [64][192] weight matrix once (TMA)            [wgrad: streams the dy tiles]
-//   warps 4-11  : producers: global fp32 rows -> bf16 patch -> swizzled operand tile (double-buffered)
+//   warp 2      : input patches: two TMA boxes {136 px, 7 rows, 3 ch} per tile (pixels 0..135 and 128..263), double-buffered
+//   warps 4-11  : producers: fp32 patch -> swizzled bf16 operand tile (double-buffered)
 //   warps 12-19 : epilogue, one [32 rows x 32 columns] chunk per warp: tcgen05.ld -> bf16 NHWC store + BatchNorm batch
 //                 statistics   [wgrad: final fp32 atomics]
 // The weight-gradient variant reuses the same operand image MN-major (M = k, K = pixels): D[192(+64 pad)][64] accumulates
@@ -26,15 +29,14 @@ using namespace tcx;
 typedef __nv_bfloat16 bf16;
 
 constexpr int NTHR = 640;
-constexpr int PW = 264;                 // patch row: 2*128 + 8 input pixels
+constexpr int PBW = 136;                // one patch box: 136 input pixels (pixels 2m .. 2m+7 of 64 output pixels, + slack)
 constexpr int PROWS = 21;               // (c, r) rows
-constexpr int PATCH_BYTES = 11264;      // 21 * 264 * 2 = 11088, rounded
+constexpr int PBOX_TX = PROWS * PBW * 4;             // bytes one box delivers (11424)
+constexpr int PBOX_BYTES = 11520;                    // box stride in shared memory (TMA destinations are 128-byte aligned)
+constexpr int PATCH_BYTES = 2 * PBOX_BYTES;          // both boxes of one tile
 constexpr int BLK = 16384;              // one 64-wide k block of the operand tile: 128 rows x 128 B
-constexpr int NLD = (PROWS * PW + 255) / 256;  // patch elements per producer thread (22)
 
 struct SGeo { int B, H, W, Ho, Wo, tiles_per_row, ntiles; };
-
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // the (b, oh, ow0) of a tile
 __device__ __forceinline__ void tile_coords(const SGeo& g, int tile, int& b, int& oh, int& ow0) {
@@ -44,40 +46,28 @@ __device__ __forceinline__ void tile_coords(const SGeo& g, int tile, int& b, int
   oh = row - b * g.Ho;
 }
 
-// producer: issue the global loads of one tile's input patch into registers (zero outside the image)
-__device__ __forceinline__ void patch_load(const float* __restrict__ x, const SGeo& g, int tile, int pt, float (&v)[NLD]) {
-  int b, oh, ow0;
-  tile_coords(g, tile, b, oh, ow0);
-  const int iw0 = 2 * ow0 - 3, ih0 = 2 * oh - 3;
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int e = pt + 256 * i;
-    const int row = e / PW, j = e - row * PW;
-    const int c = row / 7, r = row - c * 7;
-    const int ih = ih0 + r, iw = iw0 + j;
-    const bool ok = row < PROWS && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
-    v[i] = ok ? __ldg(x + (((size_t)b * 3 + c) * g.H + ih) * g.W + iw) : 0.f;
-  }
-}
-__device__ __forceinline__ void patch_store(uint8_t* patch, int pt, const float (&v)[NLD]) {
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int e = pt + 256 * i;
-    if (e < PROWS * PW) reinterpret_cast<bf16*>(patch)[e] = __float2bfloat16_rn(v[i]);
-  }
-}
-// producer: operand tile from the patch.  Thread -> pixel m = pt & 127, chunk groups kc = pt >> 7, +2, ... < 21.
+// producer: operand tile from the fp32 patch.  Thread -> pixel m = pt & 127, chunk groups kc = pt >> 7, +2, ... < 21.
+// Pixels m < 64 read box 0, m >= 64 box 1 (which starts 128 input pixels further right).
 template <bool WGRAD>
 __device__ __forceinline__ void build_tile(const uint8_t* patch, uint8_t* a_tile, int pt, int valid_pixels) {
   const int m = pt & 127;
   const bool zero = WGRAD && m >= valid_pixels;  // wgrad: pixels past the row end must not meet the next row's dy
   const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)(m & 7);
+  // the box starts at input pixel 2*ow0 - 4 (TMA needs a 16-byte aligned start: coordinate % 4 == 0 for fp32), so tap s of
+  // pixel m is patch pixel 2m + 1 + s: one 32-bit, three 64-bit and one 32-bit load
+  const uint8_t* base = patch + (m >> 6) * PBOX_BYTES + (m & 63) * 8 + 4;
 #pragma unroll
   for (int kc = pt >> 7; kc < PROWS; kc += 2) {
     const int r = kc / 3, c = kc - r * 3;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + (c * 7 + r) * (PW * 2) + m * 4);
+    const uint8_t* src = base + (c * 7 + r) * (PBW * 4);
+    const float e0 = *reinterpret_cast<const float*>(src);
+    const float2 f1 = *reinterpret_cast<const float2*>(src + 4), f2 = *reinterpret_cast<const float2*>(src + 12),
+                 f3 = *reinterpret_cast<const float2*>(src + 20);
+    const float e7 = *reinterpret_cast<const float*>(src + 28);
     uint4 q;
-    q.x = src[0]; q.y = src[1]; q.z = src[2]; q.w = src[3];
+    __nv_bfloat162* qh = reinterpret_cast<__nv_bfloat162*>(&q);
+    qh[0] = __floats2bfloat162_rn(e0, f1.x); qh[1] = __floats2bfloat162_rn(f1.y, f2.x);
+    qh[2] = __floats2bfloat162_rn(f2.y, f3.x); qh[3] = __floats2bfloat162_rn(f3.y, e7);
     if (zero) q = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(a_tile + (kc >> 3) * BLK + row_off + ((((uint32_t)kc & 7u) ^ sw) << 4)) = q;
   }
@@ -85,8 +75,9 @@ __device__ __forceinline__ void build_tile(const uint8_t* patch, uint8_t* a_tile
 
 template <bool WGRAD>
 __global__ void __launch_bounds__(NTHR, 1)
-stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; wgrad: dy [P][64] */, const float* __restrict__ x,
-            SGeo g, bf16* __restrict__ y, double* __restrict__ stats, float* __restrict__ dw) {
+stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; wgrad: dy [P][64] */,
+            const __grid_constant__ CUtensorMap tmX /* x fp32 NCHW as {W, H, 3, B}, box {136, 7, 3, 1} */, SGeo g, bf16* __restrict__ y,
+            double* __restrict__ stats, float* __restrict__ dw) {
   constexpr int NBLK = WGRAD ? 4 : 3;            // wgrad pads M to 256 = 4 blocks (the 4th stays zero)
   constexpr int A_BYTES = NBLK * BLK;
   constexpr int W_BYTES = WGRAD ? 2 * BLK : 3 * 8192;  // wgrad: two dy tiles [128 px][64] ; fwd: 3 blocks [64 n][64 k]
@@ -95,12 +86,12 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_buf = smem;                        // [2][A_BYTES]
   uint8_t* w_buf = smem + 2 * A_BYTES;          // weights / dy tiles
-  uint8_t* patch = w_buf + W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(patch + PATCH_BYTES);
+  uint8_t* patch = w_buf + W_BYTES;             // [2][PATCH_BYTES] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(patch + 2 * PATCH_BYTES);
   const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 16, tfull0 = afull0 + 32, tempty0 = afull0 + 48, wfull0 = afull0 + 64,
-                 wempty0 = afull0 + 80;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* cta_stats = reinterpret_cast<float*>(bars + 14);  // [2][64] (16-byte aligned: the scratch follows)
+                 wempty0 = afull0 + 80, pfull0 = afull0 + 96, pempty0 = afull0 + 112;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* cta_stats = reinterpret_cast<float*>(bars + 18);  // [2][64] (16-byte aligned: the scratch follows)
   uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + 128);  // [8 warps][2048]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,9 +103,12 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
       mbar_init(tempty0 + 8 * i, 8);
       mbar_init(wfull0 + 8 * i, 1);
       mbar_init(wempty0 + 8 * i, 1);
+      mbar_init(pfull0 + 8 * i, 1);
+      mbar_init(pempty0 + 8 * i, 8);   // one arrival per producer warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
   // the operand tiles start as zeros: chunk groups 21..23 (and wgrad's 4th block) are never written again
   for (int i = tid; i < 2 * A_BYTES / 16; i += NTHR) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
@@ -197,25 +191,39 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
         __syncwarp();
       }
     }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ input patches (TMA, zero fill outside the image)
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      int b, oh, ow0;
+      tile_coords(g, tile, b, oh, ow0);
+      const int buf = it & 1;
+      mbar_wait(pempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        const uint32_t dst = smem_u32(patch) + buf * PATCH_BYTES, full = pfull0 + 8 * buf;
+        mbar_expect_tx(full, 2 * PBOX_TX);
+        tma_load_4d(dst, &tmX, full, 2 * ow0 - 4, 2 * oh - 3, 0, b);
+        tma_load_4d(dst + PBOX_BYTES, &tmX, full, 2 * ow0 - 4 + 128, 2 * oh - 3, 0, b);
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------ producers
     const int pt = tid - 128;
-    float v[NLD];
-    if (my_tiles > 0) patch_load(x, g, blockIdx.x, pt, v);
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int buf = it & 1;
-      producer_bar();               // every producer has finished reading the previous patch
-      patch_store(patch, pt, v);
-      producer_bar();
-      if (it + 1 < my_tiles) patch_load(x, g, tile + gridDim.x, pt, v);  // next tile's rows: in flight during the build
       int b, oh, ow0;
       tile_coords(g, tile, b, oh, ow0);
+      mbar_wait(pfull0 + 8 * buf, (it >> 1) & 1);
       mbar_wait(aempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);
-      build_tile<WGRAD>(patch, a_buf + buf * A_BYTES, pt, g.Wo - ow0);
+      build_tile<WGRAD>(patch + buf * PATCH_BYTES, a_buf + buf * A_BYTES, pt, g.Wo - ow0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(afull0 + 8 * buf);
+      if (lane == 0) {
+        mbar_arrive(afull0 + 8 * buf);
+        mbar_arrive(pempty0 + 8 * buf);
+      }
     }
   } else if (warp >= 12) {
     // ------------------------------------------------------------ epilogue
@@ -310,6 +318,15 @@ static bool map_dense(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// x fp32 NCHW [B][3][H][W] -> box {136 pixels, 7 rows, 3 channels, 1 image}, no swizzle, zero fill out of bounds
+static bool map_input(CUtensorMap* tm, const void* x, int B, int H, int W) {
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+  cuuint32_t box[4] = {PBW, 7, 3, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static SGeo geo(int B, int H, int W) {
   SGeo g;
   g.B = B; g.H = H; g.W = W;
@@ -320,7 +337,7 @@ static SGeo geo(int B, int H, int W) {
   return g;
 }
 template <bool WGRAD>
-constexpr int smem_bytes() { return 2 * (WGRAD ? 4 : 3) * BLK + (WGRAD ? 2 * BLK : 3 * 8192) + PATCH_BYTES + 14 * 8 + 128 * 4 + 8 * 2048 + 1024; }
+constexpr int smem_bytes() { return 2 * (WGRAD ? 4 : 3) * BLK + (WGRAD ? 2 * BLK : 3 * 8192) + 2 * PATCH_BYTES + 18 * 8 + 128 * 4 + 8 * 2048 + 1024; }
 
 }  // namespace stem
 
@@ -334,25 +351,27 @@ int pm_stem_prep_w_bf16(const float* w_krsc, void* w192, pm_stream_t s) {
 
 int pm_stem_conv_fwd_bf16(const float* x_nchw, const void* w192, int B, int H, int W, void* y, double* stats, pm_stream_t s) {
   using namespace stem;
-  PM_CHECK_ARG(x_nchw && w192 && y && B > 0 && H >= 7 && W >= 7);
+  PM_CHECK_ARG(x_nchw && w192 && y && B > 0 && H >= 7 && W >= 7 && W % 4 == 0 && ((uintptr_t)x_nchw & 15) == 0);
   if (!load_driver()) return pm_set_err(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable");
   const SGeo g = geo(B, H, W);
-  CUtensorMap tm;
+  CUtensorMap tm, tmx;
+  if (!map_input(&tmx, x_nchw, B, H, W)) return pm_set_err(__FILE__, __LINE__, "stem input tensor map failed");
   if (!map_dense(&tm, w192, 64, 192, 64)) return pm_set_err(__FILE__, __LINE__, "stem weight tensor map failed");
   PM_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false>()));
-  stem_kernel<false><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<false>(), S(s)>>>(tm, x_nchw, g, (bf16*)y, stats, nullptr);
+  stem_kernel<false><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<false>(), S(s)>>>(tm, tmx, g, (bf16*)y, stats, nullptr);
   PM_LAUNCH_OK();
 }
 
 int pm_stem_conv_wgrad_bf16(const float* x_nchw, const void* dy, int B, int H, int W, float* dw_krsc, pm_stream_t s) {
   using namespace stem;
-  PM_CHECK_ARG(x_nchw && dy && dw_krsc && B > 0 && H >= 7 && W >= 7);
+  PM_CHECK_ARG(x_nchw && dy && dw_krsc && B > 0 && H >= 7 && W >= 7 && W % 4 == 0 && ((uintptr_t)x_nchw & 15) == 0);
   if (!load_driver()) return pm_set_err(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable");
   const SGeo g = geo(B, H, W);
-  CUtensorMap tm;
+  CUtensorMap tm, tmx;
+  if (!map_input(&tmx, x_nchw, B, H, W)) return pm_set_err(__FILE__, __LINE__, "stem input tensor map failed");
   if (!map_dense(&tm, dy, (uint64_t)B * g.Ho * g.Wo, 64, 128)) return pm_set_err(__FILE__, __LINE__, "stem dy tensor map failed");
   PM_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true>()));
-  stem_kernel<true><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<true>(), S(s)>>>(tm, x_nchw, g, nullptr, nullptr, dw_krsc);
+  stem_kernel<true><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<true>(), S(s)>>>(tm, tmx, g, nullptr, nullptr, dw_krsc);
   PM_LAUNCH_OK();
 }
 

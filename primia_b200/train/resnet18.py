@@ -71,7 +71,8 @@ class ResNet18Engine:
         self.bn_xmask = mode == "bf16"
         # bf16 stem as a direct implicit GEMM over the fp32 NCHW input (conv_stem.cu): no im2col matrix.  The im2col + dense
         # GEMM route stays for other channel counts and as the cross-check (PRIMIA_NO_DIRECT_STEM=1).
-        self.direct_stem = mode == "bf16" and in_channels == 3 and os.environ.get("PRIMIA_NO_DIRECT_STEM", "0") != "1"
+        self.direct_stem = (mode == "bf16" and in_channels == 3 and input_size % 4 == 0
+                            and os.environ.get("PRIMIA_NO_DIRECT_STEM", "0") != "1")
         self._x_in = None
         self._side = None
         self._build_graph()

@@ -148,7 +148,7 @@ def test_halo_conv_non_square_and_odd_sizes():
         assert rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 4e-3, (B, H, W, C, K)
 
 
-@pytest.mark.parametrize("B,H,W", [(3, 40, 40), (2, 224, 224), (1, 18, 300), (5, 7, 9)])
+@pytest.mark.parametrize("B,H,W", [(3, 40, 40), (2, 224, 224), (1, 18, 300), (5, 8, 12)])
 def test_direct_stem_conv_fwd_and_wgrad(B, H, W):
     """conv 7x7 / s2 / p3, 3 -> 64 straight from the fp32 NCHW batch (no im2col matrix): forward + fused BN statistics and
     the weight gradient vs F.conv2d on the same bf16-rounded operands.  W = 300 gives two 128-pixel tiles per output row."""
