@@ -307,6 +307,8 @@ typedef struct {
 } pm_wcvt_t;
 /* max_tiles = max over entries of RS * ceil(K/32) * ceil(Cpad/32) (grid.x; smaller entries exit early) */
 int pm_krsc_to_bf16_batched(const pm_wcvt_t* table, int n, int max_tiles, pm_stream_t s);
+/* same, one block per existing tile: total_tiles = sum over entries of RS * ceil(K/32) * ceil(Cpad/32) */
+int pm_krsc_to_bf16_batched_exact(const pm_wcvt_t* table, int n, int total_tiles, pm_stream_t s);
 /* stem im2col for the bf16 path: x NCHW fp32 [B,Cin,H,W] -> [B,Ho,Wo,Kpad] bf16 with k = (r*S+s)*Cin + c (zeros for
  * k >= R*S*Cin), so that the 7x7/stride-2 stem becomes a dense 1x1 problem for the TMA-fed tensor-core kernels */
 int pm_im2col_stem_bf16(const float* x, int B, int Cin, int H, int W, int R, int stride, int pad, int Kpad, void* out,

@@ -3,6 +3,7 @@
 // double accumulation for the statistics (the CPU reference accumulates in double too), grids sized as a
 // multiple of the SM count.  T = float (parity mode) or __nv_bfloat16 (throughput mode).
 #include "common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -509,6 +510,160 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ pool_i
   }
 }
 
+// ---- bf16 (throughput-mode) BatchNorm backward, same one-launch protocol as the ATOMIC variant above (per-block sums ->
+// double atomics into the ping-pong totals -> ONE grid barrier -> apply) but written for memory-level parallelism: four rows
+// per thread are in flight as raw 16-byte vectors (the generic kernel keeps two rows as 8 floats each and sits on its
+// 128-register cap), per-channel constants of the apply phase are folded into dx = A*g + B*x + C.
+// MASK: 0 none (BN without ReLU: the downsample branch), 1 ReLU decision from y_out, 2 recomputed from x as the forward did.
+__device__ __forceinline__ void bf8_unpack(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return t;
+}
+
+template <int MASK, bool GOUT>
+__global__ void __launch_bounds__(BT, 2)
+bn_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y_out, const __nv_bfloat16* __restrict__ x,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, size_t P, int C, double invP, double* __restrict__ totals,
+                   unsigned* __restrict__ sync, __nv_bfloat16* __restrict__ g_out, __nv_bfloat16* __restrict__ dx,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = 8, U = 4, CMAX = 512;
+  extern __shared__ double dyn[];  // phase 1: float [2][BT*V] block reduction ; phase 2: float [3][C] constants
+  float* red = reinterpret_cast<float*>(dyn);
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  const size_t rows_per_block = ((P + gridDim.x - 1) / gridDim.x + rpb - 1) / rpb * rpb;
+  const size_t row_begin = (size_t)blockIdx.x * rows_per_block;
+  const size_t row_end = row_begin + rows_per_block < P ? row_begin + rows_per_block : P;
+  float mu[V], is[V], msc[V], mbe[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    mu[k] = mean[c + k]; is[k] = invstd[c + k];
+    msc[k] = MASK == 2 ? is[k] * gamma[c + k] : 0.f;  // the forward: t = (x - mu) * (invstd * gamma) + beta ; y > 0 <=> t > 0
+    mbe[k] = MASK == 2 ? beta[c + k] : 0.f;
+  }
+  // ---- phase 1
+  float s0[V], s1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0.f;
+  for (size_t row = row_begin + r0; row < row_end; row += (size_t)rpb * U) {
+    uint4 G[U], X[U], Y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        G[u] = *reinterpret_cast<const uint4*>(dy + r * C + c);
+        X[u] = *reinterpret_cast<const uint4*>(x + r * C + c);
+        if (MASK == 1) Y[u] = *reinterpret_cast<const uint4*>(y_out + r * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        float g[V], xv[V], yv[V];
+        bf8_unpack(G[u], g);
+        bf8_unpack(X[u], xv);
+        if (MASK == 1) bf8_unpack(Y[u], yv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = g[k];
+          if (MASK == 1) gg = yv[k] > 0.f ? gg : 0.f;
+          if (MASK == 2) gg = ((xv[k] - mu[k]) * msc[k] + mbe[k]) > 0.f ? gg : 0.f;
+          g[k] = gg;
+          s0[k] += gg;
+          s1[k] = fmaf(gg, (xv[k] - mu[k]) * is[k], s1[k]);
+        }
+        if (GOUT) *reinterpret_cast<uint4*>(g_out + r * C + c) = bf8_pack(g);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[threadIdx.x * V + k] = s0[k]; red[BT * V + threadIdx.x * V + k] = s1[k]; }
+  __syncthreads();
+  const unsigned parity = (*(volatile unsigned*)(sync + 1)) & 1u;  // barrier generation before this launch's barrier
+  double* tot = totals + (size_t)parity * 2 * CMAX;
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const int vv = ch / V, ii = ch % V;
+    double t0 = 0.0, t1 = 0.0;
+    for (int r = 0; r < rpb; ++r) { t0 += (double)red[(r * vr + vv) * V + ii]; t1 += (double)red[BT * V + (r * vr + vv) * V + ii]; }
+    atomicAdd(tot + ch, t0);
+    atomicAdd(tot + CMAX + ch, t1);
+  }
+  if (blockIdx.x == 0)  // clear the other-parity buffer for the next launch (its readers finished a launch ago)
+    for (int i = threadIdx.x; i < 2 * CMAX; i += BT) totals[(size_t)(parity ^ 1u) * 2 * CMAX + i] = 0.0;
+  grid_barrier(sync, sync + 1);
+  if (dgamma && blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < C; ch += BT) {
+      dbeta[ch] = (float)__ldcg(tot + ch);
+      dgamma[ch] = (float)__ldcg(tot + CMAX + ch);
+    }
+  }
+  // ---- phase 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat)) = A*g + B*x + Cc per channel
+  float* cA = red;
+  float* cB = red + C;
+  float* cC = red + 2 * C;
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const float mg = (float)(__ldcg(tot + ch) * invP), mgx = (float)(__ldcg(tot + CMAX + ch) * invP);
+    const float isc = invstd[ch], a = gamma[ch] * isc;
+    cA[ch] = a;
+    cB[ch] = -a * mgx * isc;
+    cC[ch] = a * (mgx * isc * mean[ch] - mg);
+  }
+  __syncthreads();
+  float A[V], Bc[V], Cc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { A[k] = cA[c + k]; Bc[k] = cB[c + k]; Cc[k] = cC[c + k]; }
+  const __nv_bfloat16* gsrc = GOUT ? g_out : dy;  // the masked gradient was materialised in phase 1 when GOUT
+  for (size_t row = row_begin + r0; row < row_end; row += (size_t)rpb * U) {
+    uint4 G[U], X[U], Y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        G[u] = *reinterpret_cast<const uint4*>(gsrc + r * C + c);
+        X[u] = *reinterpret_cast<const uint4*>(x + r * C + c);
+        if (MASK == 1 && !GOUT) Y[u] = *reinterpret_cast<const uint4*>(y_out + r * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + (size_t)u * rpb;
+      if (r < row_end) {
+        float g[V], xv[V], yv[V];
+        bf8_unpack(G[u], g);
+        bf8_unpack(X[u], xv);
+        if (MASK == 1 && !GOUT) bf8_unpack(Y[u], yv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = g[k];
+          if (MASK == 1 && !GOUT) gg = yv[k] > 0.f ? gg : 0.f;
+          if (MASK == 2) gg = ((xv[k] - mu[k]) * msc[k] + mbe[k]) > 0.f ? gg : 0.f;
+          g[k] = fmaf(A[k], gg, fmaf(Bc[k], xv[k], Cc[k]));
+        }
+        *reinterpret_cast<uint4*>(dx + r * C + c) = bf8_pack(g);
+      }
+    }
+  }
+}
+
+static bool bn_bwd_generic() {  // PRIMIA_BN_BWD_GENERIC=1: the generic two-rows-in-flight kernel also in bf16 mode (cross-check)
+  const char* e = getenv("PRIMIA_BN_BWD_GENERIC");
+  return e && e[0] == '1';
+}
+
 template <typename T>
 int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, const float* invstd, const float* gamma, size_t P,
                    int C, double* ws, T* g_out, T* dx, float* dgamma, float* dbeta, pm_stream_t s,
@@ -527,6 +682,24 @@ int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, c
   double* partial = totals + 4 * 512;
   const size_t smem = 2 * BT * Vec<T>::N * sizeof(double);
   PM_CHECK_ARG(!(beta_mask && y_out));  // the ReLU decision comes from y_out OR is recomputed from x, not both
+  if constexpr (sizeof(T) == 2) {
+    if (!pool_idx && !bn_bwd_generic()) {
+      typedef __nv_bfloat16 b16;
+      const b16* d = (const b16*)dy; const b16* yo = (const b16*)y_out; const b16* xx = (const b16*)x;
+      b16* go = (b16*)g_out; b16* dxx = (b16*)dx;
+      const size_t sm = 2 * BT * 8 * sizeof(float);
+      const double invP = 1.0 / (double)P;
+#define PM_BNB(MASK, GO) bn_bwd_bf16_kernel<MASK, GO><<<(int)blocks, BT, sm, S(s)>>>(d, yo, xx, mean, invstd, gamma, beta_mask, P, C, invP, totals, sync, go, dxx, dgamma, dbeta)
+      if (beta_mask && !g_out) PM_BNB(2, false);
+      else if (beta_mask) PM_BNB(2, true);
+      else if (y_out && g_out) PM_BNB(1, true);
+      else if (y_out) PM_BNB(1, false);
+      else if (g_out) PM_BNB(0, true);
+      else PM_BNB(0, false);
+#undef PM_BNB
+      PM_LAUNCH_OK();
+    }
+  }
   if (pool_idx) {
     // g_out: optional scratch for the gathered gradient (written in phase 1, re-read in phase 2); NULL = gather twice
     bn_bwd_fused_kernel<T, true, sizeof(T) != 4><<<(int)blocks, BT, smem, S(s)>>>(

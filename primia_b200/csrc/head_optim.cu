@@ -70,16 +70,26 @@ __global__ void head_bwd_kernel(const float* __restrict__ feat, const float* __r
   if (f < F) {
     float dw[MAXC], wcol[MAXC];
     for (int j = 0; j < ncls; ++j) { dw[j] = 0.f; wcol[j] = W[(size_t)j * F + f]; }
-    for (int b = 0; b < B; ++b) {
-      const float* dl = ws + (size_t)b * (ncls + 1);
-      const float x = feat[(size_t)b * F + f];
-      float df = 0.f;
-      for (int j = 0; j < ncls; ++j) {
-        const float g = dl[j] * inv;
-        dw[j] = fmaf(g, x, dw[j]);
-        df = fmaf(g, wcol[j], df);
+    // rows in batches of 8: the 8 feature loads are issued together (the loop was one dependent ~600-cycle load per row);
+    // the accumulation order over b is unchanged
+    for (int b0 = 0; b0 < B; b0 += 8) {
+      float xs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xs[u] = b0 + u < B ? feat[(size_t)(b0 + u) * F + f] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u;
+        if (b < B) {
+          const float* dl = ws + (size_t)b * (ncls + 1);
+          float df = 0.f;
+          for (int j = 0; j < ncls; ++j) {
+            const float g = dl[j] * inv;
+            dw[j] = fmaf(g, xs[u], dw[j]);
+            df = fmaf(g, wcol[j], df);
+          }
+          dfeat[(size_t)b * F + f] = df;
+        }
       }
-      dfeat[(size_t)b * F + f] = df;
     }
     for (int j = 0; j < ncls; ++j) dW[(size_t)j * F + f] = dw[j];
   }
@@ -188,6 +198,66 @@ krsc_to_bf16_batched_kernel(const pm_wcvt_t* __restrict__ table) {
   }
 }
 
+// Same conversion with an EXACT grid: blockIdx.x enumerates the tiles of all entries back to back (the rectangular
+// (max_tiles, n) grid above launches ~4x more blocks than there are tiles, and retiring empty blocks costs more than the
+// conversion itself).  Warp 0 finds the entry with a ballot over the per-entry tile counts.
+__global__ void __launch_bounds__(256)
+krsc_to_bf16_exact_kernel(const pm_wcvt_t* __restrict__ table, int n) {
+  __shared__ float tile[32][33];
+  __shared__ int s_entry, s_local;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int base = 0, found = 0;
+    for (int e0 = 0; e0 < n && !found; e0 += 32) {
+      int nt = 0;
+      if (e0 + lane < n) {
+        const pm_wcvt_t e = table[e0 + lane];
+        nt = e.RS * ((e.K + 31) / 32) * ((e.Cpad + 31) / 32);
+      }
+      int incl = nt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, base + incl > (int)blockIdx.x);
+      if (hit) {
+        const int l = __ffs(hit) - 1;
+        const int excl = __shfl_sync(0xffffffffu, incl - nt, l);
+        if (lane == 0) { s_entry = e0 + l; s_local = (int)blockIdx.x - base - excl; }
+        found = 1;
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (!found && lane == 0) s_entry = -1;
+  }
+  __syncthreads();
+  if (s_entry < 0) return;
+  const pm_wcvt_t e = table[s_entry];
+  const int bx = s_local;
+  const int tk = (e.K + 31) / 32, tc = (e.Cpad + 31) / 32;
+  const int rs = bx / (tk * tc);
+  const int rem = bx - rs * tk * tc;
+  const int k0 = (rem / tc) * 32, c0 = (rem % tc) * 32;
+  __nv_bfloat16* wf = (__nv_bfloat16*)e.w_fwd;
+  __nv_bfloat16* wd = (__nv_bfloat16*)e.w_dgrad;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (k < e.K && c < e.C) v = e.w[((size_t)k * e.RS + rs) * e.C + c];
+    tile[i][tx] = v;
+    if (k < e.K && c < e.Cpad) wf[((size_t)k * e.RS + rs) * e.Cpad + c] = __float2bfloat16_rn(v);
+  }
+  if (wd) {
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, k = k0 + tx;
+      if (c < e.C && k < e.K) wd[((size_t)c * e.RS + rs) * e.K + k] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
 // one block per (image, output row): the R input rows it needs are staged in shared memory (coalesced), then every
 // thread assembles 16-byte chunks (8 consecutive k = (r*S+s)*Cin + c) of the im2col rows.  blockDim = 10 pixels x
 // (Kpad/8) chunks: a thread always produces the same chunk index, so its 8 smem offsets live in registers.
@@ -250,7 +320,7 @@ int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const
   PM_CHECK_ARG((labels != nullptr) != (soft != nullptr));
   PM_CUDA(cudaMemsetAsync(ws + (size_t)B * (ncls + 1), 0, sizeof(float), S(s)));
   head_fwd_kernel<<<B, 128, 0, S(s)>>>(feat, W, bias, labels, soft, class_w, F, ncls, logits, ws);
-  head_bwd_kernel<<<(F + 127) / 128, 128, 0, S(s)>>>(feat, W, B, F, ncls, ws, loss, dfeat, dW, db);
+  head_bwd_kernel<<<(F + 63) / 64, 64, 0, S(s)>>>(feat, W, B, F, ncls, ws, loss, dfeat, dW, db);  // thread 32 of block 0 writes the loss
   PM_LAUNCH_OK();
 }
 
@@ -313,6 +383,12 @@ int pm_krsc_to_bf16_batched(const pm_wcvt_t* table, int n, int max_tiles, pm_str
   PM_CHECK_ARG(table && n > 0 && n <= 65535 && max_tiles > 0);
   dim3 grid(max_tiles, n);  // max_tiles = max over entries of RS * ceil(K/32) * ceil(Cpad/32)
   krsc_to_bf16_batched_kernel<<<grid, 256, 0, S(s)>>>(table);
+  PM_LAUNCH_OK();
+}
+
+int pm_krsc_to_bf16_batched_exact(const pm_wcvt_t* table, int n, int total_tiles, pm_stream_t s) {
+  PM_CHECK_ARG(table && n > 0 && total_tiles > 0);
+  krsc_to_bf16_exact_kernel<<<total_tiles, 256, 0, S(s)>>>(table, n);
   PM_LAUNCH_OK();
 }
 

@@ -213,6 +213,7 @@ class ResNet18Engine:
             arr = (WCvt * len(entries))(*entries)
             self.wcvt_n = len(entries)
             self.wcvt_tiles = max(e.RS * ((e.K + 31) // 32) * ((e.Cpad + 31) // 32) for e in entries)
+            self.wcvt_total = sum(e.RS * ((e.K + 31) // 32) * ((e.Cpad + 31) // 32) for e in entries)
             self.wcvt_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
 
     def _lib_size(self, fn, conv):
@@ -396,7 +397,7 @@ class ResNet18Engine:
                  stream())
 
     def refresh_bf16_weights(self):
-        call("pm_krsc_to_bf16_batched", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_tiles, stream())
+        call("pm_krsc_to_bf16_batched_exact", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_total, stream())
         if self.direct_stem:
             call("pm_stem_prep_w_bf16", ptr(self.p["conv1.weight"]), ptr(self.w_stem), stream())
 
