@@ -371,13 +371,19 @@ def run_ours(args):
     conv_ms, launches = eng.profile_conv_time(xs[0], ys[0], steps=2)
     pk = peaks()
     achieved = GFLOP_PER_IMAGE * B / conv_ms  # GFLOP / ms == TFLOP/s
-    roof = {"bound": "tensor", "kernel": "tma::conv_tma_kernel + dgrad_s2_tma_kernel + wgrad_tma_kernel (tcgen05/TMEM implicit GEMM fed by im2col "
-                                         "TMA: 20 fwd + 19 dgrad + 20 wgrad launches per step)",
+    roof = {"bound": "tensor", "kernel": "conv family, tcgen05/TMEM implicit GEMMs: halo::conv_halo_kernel (3x3/s1 fwd + dgrad, one TMA strip "
+                                         "serves all 9 taps), stem::stem_kernel (7x7/s2 fwd + wgrad straight from the fp32 NCHW batch), "
+                                         "tma::conv_tma_kernel / dgrad_s2_tma_kernel (1x1 and stride-2), tma::wgrad_tma_kernel: "
+                                         "20 fwd + 19 dgrad + 20 wgrad launches per step",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
             "traffic": 1.479e9 if args.mode == "bf16" and B == 64 else None,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step, ncu pass "
                             "profiles/r01_step_dram_traffic_ncu.csv (write-back of the outputs is not attributed to the kernel by ncu)",
-            "conv_ms_per_step": conv_ms, "step_share": conv_ms / (ms / args.steps),
+            "conv_ms_per_step": conv_ms, "conv_ms_by_kind": getattr(eng, "conv_ms_by_kind", None),
+            "step_share": conv_ms / (ms / args.steps),
+            "timing": "CUDA events on the launching stream around each of the 59 conv launches of an eager step (a spin kernel queued "
+                      "before each bracket keeps host launch latency out of it); in the timed CUDA-graph step the 20 wgrad launches run "
+                      "on a side stream, so step_share is an upper bound of the family's share of the critical path",
             "algorithmic": f"{GFLOP_PER_IMAGE} GFLOP/image x {B} images per step", "peak_source": pk["source"] + ", sustained bf16 GEMM"}
     if args.mode != "bf16":
         roof["note"] = "fp32 parity mode runs on the FP32 pipe; fraction is still quoted against the bf16 tensor peak"

@@ -531,6 +531,74 @@ __device__ __forceinline__ uint4 bf8_pack(const float (&v)[8]) {
   return t;
 }
 
+// bf16 BatchNorm forward apply (training; mean / invstd finalised from the batch statistics in the prologue exactly as
+// bn_apply_kernel<T, true> does): y = act((x - mu) * (invstd * gamma) + beta (+ residual)), four raw 16-byte rows in flight.
+__global__ void __launch_bounds__(BT, 2)
+bn_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats, double Pd, float eps, float momentum,
+                   float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ rm, float* __restrict__ rv,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, int relu,
+                   size_t P, int C, __nv_bfloat16* __restrict__ y) {
+  constexpr int V = 8, U = 4;
+  extern __shared__ float sp[];  // [3][C]: mu, invstd*gamma, beta
+  const double invPd = 1.0 / Pd;
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const double md = stats[ch] * invPd;
+    double var = stats[C + ch] * invPd - md * md;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)md;
+    const float ve = (float)(var + (double)eps);
+    float is = rsqrtf(ve);
+    is = is * (1.5f - 0.5f * ve * is * is);
+    if (blockIdx.x == 0) {
+      mean_out[ch] = m;
+      invstd_out[ch] = is;
+      if (rm) {
+        const double unbiased = Pd > 1.0 ? var * Pd / (Pd - 1.0) : var;
+        rm[ch] = (float)((1.0 - momentum) * (double)rm[ch] + momentum * md);
+        rv[ch] = (float)((1.0 - momentum) * (double)rv[ch] + momentum * unbiased);
+      }
+    }
+    sp[ch] = m;
+    sp[C + ch] = is * gamma[ch];
+    sp[2 * C + ch] = beta[ch];
+  }
+  __syncthreads();
+  const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
+  const int c = v * V;
+  float mu[V], sc[V], be[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = sp[c + k]; sc[k] = sp[C + c + k]; be[k] = sp[2 * C + c + k]; }
+  const size_t stride = (size_t)gridDim.x * rpb;
+  for (size_t row = (size_t)blockIdx.x * rpb + r0; row < P; row += stride * U) {
+    uint4 X[U], R[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+        X[u] = *reinterpret_cast<const uint4*>(x + r * C + c);
+        if (res) R[u] = *reinterpret_cast<const uint4*>(res + r * C + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t r = row + u * stride;
+      if (r < P) {
+        float xv[V], rvv[V];
+        bf8_unpack(X[u], xv);
+        if (res) bf8_unpack(R[u], rvv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float t = (xv[k] - mu[k]) * sc[k] + be[k];
+          if (res) t += rvv[k];
+          if (relu) t = t > 0.f ? t : 0.f;
+          xv[k] = t;
+        }
+        *reinterpret_cast<uint4*>(y + r * C + c) = bf8_pack(xv);
+      }
+    }
+  }
+}
+
 template <int MASK, bool GOUT>
 __global__ void __launch_bounds__(BT, 2)
 bn_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y_out, const __nv_bfloat16* __restrict__ x,
@@ -804,32 +872,32 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __
     const int ow = (int)(t % Wo); t /= Wo;
     const int oh = (int)(t % Ho);
     const size_t b = t / Ho;
-    uint32_t best[4], bi[4];
-    bool first = true;
+    // all nine taps are loaded before the first compare (nine independent 16-byte loads in flight per thread); a tap outside
+    // the image is -inf after the sign adjustment, so it never wins a strict comparison and the scan order -- hence the
+    // "first strict maximum" tie rule -- is unchanged
+    uint4 raw[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = oh * 2 - 1 + r;
-      if (ih < 0 || ih >= H) continue;
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
         const int iw = ow * 2 - 1 + s2;
-        if (iw < 0 || iw >= W) continue;
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + ((b * H + ih) * W + iw) * C + cv * V);
-        const uint32_t v[4] = {raw.x ^ flip[0], raw.y ^ flip[1], raw.z ^ flip[2], raw.w ^ flip[3]};
-        const uint32_t tap2 = (uint32_t)(r * 3 + s2) * 0x10001u;
-        if (first) {
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        raw[r * 3 + s2] = ok ? *reinterpret_cast<const uint4*>(x + ((b * H + ih) * W + iw) * C + cv * V)
+                             : make_uint4(0xFF80FF80u ^ flip[0], 0xFF80FF80u ^ flip[1], 0xFF80FF80u ^ flip[2], 0xFF80FF80u ^ flip[3]);
+      }
+    }
+    uint32_t best[4] = {raw[0].x ^ flip[0], raw[0].y ^ flip[1], raw[0].z ^ flip[2], raw[0].w ^ flip[3]};
+    uint32_t bi[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { best[q] = v[q]; bi[q] = tap2; }
-          first = false;
-        } else {
+    for (int tp = 1; tp < 9; ++tp) {
+      const uint32_t v[4] = {raw[tp].x ^ flip[0], raw[tp].y ^ flip[1], raw[tp].z ^ flip[2], raw[tp].w ^ flip[3]};
+      const uint32_t tap2 = (uint32_t)tp * 0x10001u;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v[q]),
-                                           *reinterpret_cast<const __nv_bfloat162*>(&best[q]));
-            best[q] = (v[q] & m) | (best[q] & ~m);
-            bi[q] = (tap2 & m) | (bi[q] & ~m);
-          }
-        }
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v[q]), *reinterpret_cast<const __nv_bfloat162*>(&best[q]));
+        best[q] = (v[q] & m) | (best[q] & ~m);
+        bi[q] = (tap2 & m) | (bi[q] & ~m);
       }
     }
     float out[V];
@@ -861,86 +929,110 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __
 // never matches a tap.  PHASE 0: s0 += g, s1 += g * xhat (double atomics per block).  PHASE 1: dx = gamma*invstd *
 // (g - mean(g) - xhat * mean(g*xhat)).
 template <int PHASE>
-__global__ void __launch_bounds__(BT)
+__global__ void __launch_bounds__(BT, 2)
 stem_pool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
                         const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, double* __restrict__ sums, double invP, int H, int W, int C, size_t total,
                         __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  // The twelve vectors of one 2x2 block stay RAW (16-byte bf16 / 8-byte index words, 40 registers) and are unpacked one
+  // channel pair at a time: two resident blocks per SM instead of one, every load of the block issued before the first use.
   constexpr int V = 8;
-  using bf = __nv_bfloat16;
   const int CV = C / V, Ho = H / 2, Wo = W / 2;
   const int cv = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CV);
   const int c = cv * V;
-  float mu[V], is[V], gi[V], mg[V], mgx[V];
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    mu[k] = mean[c + k];
-    is[k] = invstd[c + k];
+  __shared__ float cst[5][64 * 8];  // per-channel constants (C <= 512): mu, is, and for the apply phase A, B, Cc
+  for (int ch = threadIdx.x; ch < C; ch += BT) {
+    const float m = mean[ch], isd = invstd[ch];
+    cst[0][ch] = m;
+    cst[1][ch] = isd;
     if (PHASE == 1) {
-      gi[k] = gamma[c + k] * is[k];
-      mg[k] = (float)(sums[c + k] * invP);
-      mgx[k] = (float)(sums[C + c + k] * invP);
+      // dx = gamma*invstd * (g - mean(g) - xhat * mean(g*xhat)) = A*g + B*x + Cc
+      const float a = gamma[ch] * isd;
+      const float mg = (float)(sums[ch] * invP), mgx = (float)(sums[C + ch] * invP);
+      cst[2][ch] = a;
+      cst[3][ch] = -a * mgx * isd;
+      cst[4][ch] = a * (mgx * isd * m - mg);
     }
   }
-  if (PHASE == 1 && dgamma && blockIdx.x == 0 && threadIdx.x < CV) {
-#pragma unroll
-    for (int k = 0; k < V; ++k) { dbeta[c + k] = (float)sums[c + k]; dgamma[c + k] = (float)sums[C + c + k]; }
-  }
+  if (PHASE == 1 && dgamma && blockIdx.x == 0)
+    for (int ch = threadIdx.x; ch < C; ch += BT) { dbeta[ch] = (float)sums[ch]; dgamma[ch] = (float)sums[C + ch]; }
+  __syncthreads();
   float s0[V], s1[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0.f;
-  // (window offset dk,dj ; tap) pairs feeding each of the four positions of the block: pos = (dy*2 + dx)
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t t = i / CV;
     const int j = (int)(t % Wo); t /= Wo;
     const int k2 = (int)(t % Ho);
     const size_t b = t / Ho;
-    float d[4][V];
-    uint8_t id[4][V];
+    uint4 D[4], X[4];
+    uint2 I[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int ok = k2 + (w >> 1), oj = j + (w & 1);
+      D[w] = make_uint4(0, 0, 0, 0);
+      I[w] = make_uint2(0xffffffffu, 0xffffffffu);
       if (ok < Ho && oj < Wo) {
         const size_t o = ((b * Ho + ok) * Wo + oj) * C + c;
-        Vec<bf>::load(dpool + o, d[w]);
-        *reinterpret_cast<uint2*>(id[w]) = *reinterpret_cast<const uint2*>(idx + o);
-      } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) { d[w][k] = 0.f; id[w][k] = 255; }
+        D[w] = *reinterpret_cast<const uint4*>(dpool + o);
+        I[w] = *reinterpret_cast<const uint2*>(idx + o);
       }
     }
-    float xv[4][V];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-      Vec<bf>::load(x + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c, xv[p]);
-    float g[4][V];
+      X[p] = *reinterpret_cast<const uint4*>(x + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c);
+    uint4 O[4];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      g[0][k] = id[0][k] == 4 ? d[0][k] : 0.f;
-      g[1][k] = (id[0][k] == 5 ? d[0][k] : 0.f) + (id[1][k] == 3 ? d[1][k] : 0.f);
-      g[2][k] = (id[0][k] == 7 ? d[0][k] : 0.f) + (id[2][k] == 1 ? d[2][k] : 0.f);
-      g[3][k] = (id[0][k] == 8 ? d[0][k] : 0.f) + (id[1][k] == 6 ? d[1][k] : 0.f) + (id[2][k] == 2 ? d[2][k] : 0.f) +
-                (id[3][k] == 0 ? d[3][k] : 0.f);
+    for (int kk = 0; kk < 4; ++kk) {  // channel pair (2kk, 2kk+1)
+      float2 d[4], xv[4];
+      uint32_t id[4];  // the two index bytes of this pair
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t dw = kk == 0 ? D[w].x : kk == 1 ? D[w].y : kk == 2 ? D[w].z : D[w].w;
+        const uint32_t xw = kk == 0 ? X[w].x : kk == 1 ? X[w].y : kk == 2 ? X[w].z : X[w].w;
+        d[w] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw));
+        xv[w] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
+        const uint32_t iw = kk < 2 ? I[w].x : I[w].y;
+        id[w] = (iw >> ((kk & 1) * 16)) & 0xffffu;
+      }
+      float g[4][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t i0 = (id[0] >> (8 * h)) & 0xffu, i1 = (id[1] >> (8 * h)) & 0xffu, i2 = (id[2] >> (8 * h)) & 0xffu,
+                       i3 = (id[3] >> (8 * h)) & 0xffu;
+        const float d0 = h ? d[0].y : d[0].x, d1 = h ? d[1].y : d[1].x, d2 = h ? d[2].y : d[2].x, d3 = h ? d[3].y : d[3].x;
+        g[0][h] = i0 == 4 ? d0 : 0.f;
+        g[1][h] = (i0 == 5 ? d0 : 0.f) + (i1 == 3 ? d1 : 0.f);
+        g[2][h] = (i0 == 7 ? d0 : 0.f) + (i2 == 1 ? d2 : 0.f);
+        g[3][h] = (i0 == 8 ? d0 : 0.f) + (i1 == 6 ? d1 : 0.f) + (i2 == 2 ? d2 : 0.f) + (i3 == 0 ? d3 : 0.f);
+      }
+      if (PHASE == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = c + 2 * kk + h;
+          const float m = cst[0][ch], isd = cst[1][ch];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xx = h ? xv[p].y : xv[p].x;
+            s0[2 * kk + h] += g[p][h];
+            s1[2 * kk + h] = fmaf(g[p][h], (xx - m) * isd, s1[2 * kk + h]);
+          }
+        }
+      } else {
+        const int ch = c + 2 * kk;
+        const float a0 = cst[2][ch], b0 = cst[3][ch], c0 = cst[4][ch], a1 = cst[2][ch + 1], b1 = cst[3][ch + 1], c1 = cst[4][ch + 1];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(fmaf(a0, g[p][0], fmaf(b0, xv[p].x, c0)), fmaf(a1, g[p][1], fmaf(b1, xv[p].y, c1)));
+          const uint32_t ow = *reinterpret_cast<const uint32_t*>(&o2);
+          if (kk == 0) O[p].x = ow; else if (kk == 1) O[p].y = ow; else if (kk == 2) O[p].z = ow; else O[p].w = ow;
+        }
+      }
     }
-    if (PHASE == 0) {
+    if (PHASE == 1) {
 #pragma unroll
       for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          s0[k] += g[p][k];
-          s1[k] += g[p][k] * ((xv[p][k] - mu[k]) * is[k]);
-        }
-    } else {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float o8[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float xhat = (xv[p][k] - mu[k]) * is[k];
-          o8[k] = gi[k] * (g[p][k] - mg[k] - xhat * mgx[k]);
-        }
-        Vec<bf>::store(dx + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c, o8);
-      }
+        *reinterpret_cast<uint4*>(dx + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c) = O[p];
     }
   }
   if (PHASE == 0) {
@@ -1062,6 +1154,16 @@ int bn_fwd_fused_t(const T* x, const double* stats, size_t P, int C, float eps, 
                    const float* beta, const T* res, int relu, T* y, float* mean, float* invstd, float* rm, float* rv,
                    pm_stream_t s) {
   PM_CHECK_ARG(x && stats && gamma && beta && y && mean && invstd && P > 0 && chan_ok<T>(C) && ((rm == nullptr) == (rv == nullptr)));
+  if constexpr (sizeof(T) == 2) {
+    if (!bn_bwd_generic()) {
+      typedef __nv_bfloat16 b16;
+      int grid = row_grid<T>(P, C, 8);
+      if (grid > 2 * pm_num_sms()) grid = 2 * pm_num_sms();
+      bn_fwd_bf16_kernel<<<grid, BT, 3 * C * sizeof(float), S(s)>>>((const b16*)x, stats, (double)P, eps, momentum, mean, invstd, rm, rv, gamma,
+                                                                    beta, (const b16*)res, relu, P, C, (b16*)y);
+      PM_LAUNCH_OK();
+    }
+  }
   bn_apply_kernel<T, true><<<row_grid<T>(P, C, 4), BT, 4 * C * sizeof(float), S(s)>>>(x, nullptr, nullptr, stats, (double)P, eps, momentum, mean, invstd,
                                                                   rm, rv, gamma, beta, res, relu, P, C, y);
   PM_LAUNCH_OK();

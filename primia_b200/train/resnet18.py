@@ -281,26 +281,30 @@ class ResNet18Engine:
         return out
 
     # ------------------------------------------------------------------ kernels
-    def _prof_begin(self):
+    def _prof_begin(self, tag="conv"):
+        """Profiling pass only: CUDA-event bracket around ONE conv launch.  The launch takes the host longer (ctypes call, two
+        tensor-map encodes) than the kernel takes the GPU, so a ~100 us spin kernel is queued first: the host runs ahead and the
+        events bracket device time, not launch latency."""
         if self._prof is None:
             return None
+        torch.cuda._sleep(200000)
         e = torch.cuda.Event(enable_timing=True)
         e.record()
-        return e
+        return (e, tag)
 
     def _prof_end(self, e0):
         if e0 is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            self._prof.append((e0, e1))
+            self._prof.append((e0[0], e1, e0[1]))
 
     def _conv_fwd(self, c, x, y, stats=None):
-        e0 = self._prof_begin()
+        e0 = self._prof_begin("fwd")
         self._conv_fwd_impl(c, x, y, stats)
         self._prof_end(e0)
 
     def _conv_dgrad(self, c, dy, dx, accumulate):
-        e0 = self._prof_begin()
+        e0 = self._prof_begin("dgrad")
         self._conv_dgrad_impl(c, dy, dx, accumulate)
         self._prof_end(e0)
 
@@ -309,7 +313,7 @@ class ResNet18Engine:
         so in bf16 mode they are issued on a side stream and overlap the BN / dgrad chain (the tensor-core wgrad CTAs
         co-reside with the memory-bound BN kernels).  Each conv has its own dy buffer, so there is no reuse hazard."""
         if self._side is None or self._prof is not None:
-            e0 = self._prof_begin()
+            e0 = self._prof_begin("wgrad")
             self._conv_wgrad_impl(c, x, dy)
             self._prof_end(e0)
             return
@@ -413,7 +417,7 @@ class ResNet18Engine:
             fuse = self.mode == "bf16" and self.training and self.fuse_stats
             c1 = self.convs["conv1"]
             if self.direct_stem:
-                e0 = self._prof_begin()
+                e0 = self._prof_begin("fwd")
                 call("pm_stem_conv_fwd_bf16", ptr(self._x_in), ptr(self.w_stem), self.B, self.size, self.size, ptr(self.act["conv1"]),
                      ptr(self._stat_slot(bn_ids["bn1"])) if fuse else None, stream())
                 self._prof_end(e0)
@@ -538,7 +542,7 @@ class ResNet18Engine:
                     with torch.cuda.stream(self._side):
                         stem_wgrad()
                 else:
-                    e0 = self._prof_begin()
+                    e0 = self._prof_begin("wgrad")
                     stem_wgrad()
                     self._prof_end(e0)
             if self._side is not None:
@@ -623,7 +627,10 @@ class ResNet18Engine:
                 self._train_step_eager(x_nchw, target)
             torch.cuda.synchronize(self.device)
             launches = (_lib.launch_counter - n0) // steps + 1
-            ms = sum(a.elapsed_time(b) for a, b in self._prof) / steps
+            ms = sum(a.elapsed_time(b) for a, b, _ in self._prof) / steps
+            self.conv_ms_by_kind = {}
+            for a, b, tag in self._prof:
+                self.conv_ms_by_kind[tag] = self.conv_ms_by_kind.get(tag, 0.0) + a.elapsed_time(b) / steps
             self._prof = None
             self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
         return ms, launches
