@@ -468,7 +468,8 @@ class ResNet18Engine:
             target = target.contiguous()
             if self.mode == "bf16":
                 self.grads.zero_()  # the tensor-core wgrad accumulates (split over pixels) into a cleared buffer
-                self.dw_stem.zero_()
+                if not self.direct_stem:
+                    self.dw_stem.zero_()
                 if self.overlap_wgrad and self._side is None:
                     self._side = torch.cuda.Stream(self.device)
             call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
