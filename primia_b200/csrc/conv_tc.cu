@@ -455,6 +455,8 @@ int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* 
 // halo-strip variant for 3x3 / stride 1 / pad 1 (conv_halo.cu), same return convention
 int pm_halo_conv(const pm_conv_t* p, const void* src, const void* wmat, void* dst, int accumulate, double* stats, int flip,
                  cudaStream_t st);
+// persistent stride-2 data gradient (conv_s2.cu), same return convention
+int pm_s2p_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
 static bool use_tma() {
   const char* e = getenv("PRIMIA_NO_TMA");
   return !(e && e[0] == '1');
@@ -483,6 +485,9 @@ int pm_conv_dgrad_bf16(const pm_conv_t* p, const void* dy, const void* wt, void*
     const int rh = pm_halo_conv(p, dy, wt, dx, accumulate, nullptr, 1, S(s));
     if (rh == 2) return pm_set_err(__FILE__, __LINE__, "halo conv dgrad setup failed");
     if (rh == 0) PM_LAUNCH_OK();
+    const int rs = pm_s2p_conv_dgrad(p, dy, wt, dx, accumulate, S(s));
+    if (rs == 2) return pm_set_err(__FILE__, __LINE__, "stride-2 conv dgrad setup failed");
+    if (rs == 0) PM_LAUNCH_OK();
     const int r = pm_tma_conv_dgrad(p, dy, wt, dx, accumulate, S(s));
     if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv dgrad setup failed");
     if (r == 0) PM_LAUNCH_OK();

@@ -43,7 +43,7 @@ def bf(t):
     return t.to(torch.bfloat16)
 
 
-# "halo": halo-strip kernel for 3x3/s1 + im2col-TMA producer elsewhere (the default); "tma": im2col-TMA producer wherever
+# "halo": halo-strip kernel for 3x3/s1, persistent stride-2 dgrad, im2col-TMA producer elsewhere (the default); "tma": im2col-TMA producer wherever
 # eligible; "cpasync": cp.async gather everywhere
 @pytest.mark.parametrize("variant", ["halo", "tma", "cpasync"])
 @pytest.mark.parametrize("case", CASES)
@@ -52,6 +52,7 @@ def test_fwd_dgrad_wgrad_bf16(case, variant, monkeypatch):
 
     monkeypatch.setenv("PRIMIA_NO_TMA", "1" if variant == "cpasync" else "0")
     monkeypatch.setenv("PRIMIA_NO_HALO", "0" if variant == "halo" else "1")
+    monkeypatch.setenv("PRIMIA_NO_S2P", "0" if variant == "halo" else "1")  # persistent stride-2 dgrad rides with "halo"
 
     B, H, C, K, R, s, p = case
     g = torch.Generator().manual_seed(sum(case))
