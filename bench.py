@@ -376,9 +376,10 @@ def run_ours(args):
                                          "tma::conv_tma_kernel / dgrad_s2_tma_kernel (1x1 and stride-2), tma::wgrad_tma_kernel: "
                                          "20 fwd + 19 dgrad + 20 wgrad launches per step",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "traffic": 1.479e9 if args.mode == "bf16" and B == 64 else None,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the conv launches of one step, ncu pass "
-                            "profiles/r01_step_dram_traffic_ncu.csv (write-back of the outputs is not attributed to the kernel by ncu)",
+            "traffic": 1.320e9 if args.mode == "bf16" and B == 64 else None,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 59 conv launches of one step, ncu pass "
+                            "profiles/r01b_launch_summary.csv (1.274 GB read + 0.046 GB written; write-back of the outputs is not "
+                            "attributed to the producing kernel by ncu); algorithmic operand + output bytes ~1.6 GB",
             "conv_ms_per_step": conv_ms, "conv_ms_by_kind": getattr(eng, "conv_ms_by_kind", None),
             "step_share": conv_ms / (ms / args.steps),
             "timing": "CUDA events on the launching stream around each of the 59 conv launches of an eager step (a spin kernel queued "

@@ -540,6 +540,7 @@ bn_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict
                    size_t P, int C, __nv_bfloat16* __restrict__ y) {
   constexpr int V = 8, U = 4;
   extern __shared__ float sp[];  // [3][C]: mu, invstd*gamma, beta
+  pm_pdl_sync();
   const double invPd = 1.0 / Pd;
   for (int ch = threadIdx.x; ch < C; ch += BT) {
     const double md = stats[ch] * invPd;
@@ -609,6 +610,7 @@ bn_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   constexpr int V = 8, U = 4, CMAX = 512;
   extern __shared__ double dyn[];  // phase 1: float [2][BT*V] block reduction ; phase 2: float [3][C] constants
   float* red = reinterpret_cast<float*>(dyn);
+  pm_pdl_sync();
   const int vr = C / V, v = threadIdx.x % vr, rpb = BT / vr, r0 = threadIdx.x / vr;
   const int c = v * V;
   const size_t rows_per_block = ((P + gridDim.x - 1) / gridDim.x + rpb - 1) / rpb * rpb;
@@ -757,7 +759,7 @@ int bn_bwd_fused_t(const T* dy, const T* y_out, const T* x, const float* mean, c
       b16* go = (b16*)g_out; b16* dxx = (b16*)dx;
       const size_t sm = 2 * BT * 8 * sizeof(float);
       const double invP = 1.0 / (double)P;
-#define PM_BNB(MASK, GO) bn_bwd_bf16_kernel<MASK, GO><<<(int)blocks, BT, sm, S(s)>>>(d, yo, xx, mean, invstd, gamma, beta_mask, P, C, invP, totals, sync, go, dxx, dgamma, dbeta)
+#define PM_BNB(MASK, GO) PM_CUDA(pm_launch(bn_bwd_bf16_kernel<MASK, GO>, dim3((unsigned)blocks), dim3(BT), sm, S(s), d, yo, xx, mean, invstd, gamma, beta_mask, P, C, invP, totals, sync, go, dxx, dgamma, dbeta))
       if (beta_mask && !g_out) PM_BNB(2, false);
       else if (beta_mask) PM_BNB(2, true);
       else if (y_out && g_out) PM_BNB(1, true);
@@ -835,6 +837,7 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __
                            int C, int Ho, int Wo, size_t total, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx) {
   constexpr int V = 8;
   extern __shared__ float sp[];  // [3][C]: mu, invstd*gamma, beta
+  pm_pdl_sync();
   const double invPd = 1.0 / Pd;
   for (int ch = threadIdx.x; ch < C; ch += BT) {
     const double md = stats[ch] * invPd;
@@ -941,6 +944,7 @@ stem_pool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* 
   const int cv = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CV);
   const int c = cv * V;
   __shared__ float cst[5][64 * 8];  // per-channel constants (C <= 512): mu, is, and for the apply phase A, B, Cc
+  pm_pdl_sync();
   for (int ch = threadIdx.x; ch < C; ch += BT) {
     const float m = mean[ch], isd = invstd[ch];
     cst[0][ch] = m;
@@ -1159,8 +1163,8 @@ int bn_fwd_fused_t(const T* x, const double* stats, size_t P, int C, float eps, 
       typedef __nv_bfloat16 b16;
       int grid = row_grid<T>(P, C, 8);
       if (grid > 2 * pm_num_sms()) grid = 2 * pm_num_sms();
-      bn_fwd_bf16_kernel<<<grid, BT, 3 * C * sizeof(float), S(s)>>>((const b16*)x, stats, (double)P, eps, momentum, mean, invstd, rm, rv, gamma,
-                                                                    beta, (const b16*)res, relu, P, C, (b16*)y);
+      PM_CUDA(pm_launch(bn_fwd_bf16_kernel, dim3(grid), dim3(BT), 3 * C * sizeof(float), S(s), (const b16*)x, stats, (double)P, eps, momentum,
+                        mean, invstd, rm, rv, gamma, beta, (const b16*)res, relu, P, C, (b16*)y));
       PM_LAUNCH_OK();
     }
   }
@@ -1288,9 +1292,9 @@ int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const size_t total = (size_t)B * Ho * Wo * (C / 8);
   PM_CHECK_ARG(BT % (C / 8) == 0);
-  bn_relu_maxpool_fwd_kernel<<<pm_grid(total, BT, 1, 16), BT, 3 * C * sizeof(float), S(s)>>>(
-      (const bf16*)x, stats, (double)B * H * W, eps, momentum, mean, invstd, running_mean, running_var, gamma, beta, H, W, C, Ho, Wo,
-      total, (bf16*)y, idx);
+  PM_CUDA(pm_launch(bn_relu_maxpool_fwd_kernel, dim3(pm_grid(total, BT, 1, 16)), dim3(BT), 3 * C * sizeof(float), S(s), (const bf16*)x, stats,
+                    (double)B * H * W, eps, momentum, mean, invstd, running_mean, running_var, gamma, beta, H, W, C, Ho, Wo, total,
+                    (bf16*)y, idx));
   PM_LAUNCH_OK();
 }
 
@@ -1302,10 +1306,10 @@ int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, int B, 
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
   const int grid = pm_grid(total, BT, 1, 8);
   const double invP = 1.0 / ((double)B * H * W);
-  stem_pool_bn_bwd_kernel<0><<<grid, BT, 0, S(s)>>>((const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd, gamma, sums, invP, H,
-                                                    W, C, total, nullptr, nullptr, nullptr);
-  stem_pool_bn_bwd_kernel<1><<<grid, BT, 0, S(s)>>>((const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd, gamma, sums, invP, H,
-                                                    W, C, total, (bf16*)dx, dgamma, dbeta);
+  PM_CUDA(pm_launch(stem_pool_bn_bwd_kernel<0>, dim3(grid), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd,
+                    gamma, sums, invP, H, W, C, total, (bf16*)nullptr, (float*)nullptr, (float*)nullptr));
+  PM_CUDA(pm_launch(stem_pool_bn_bwd_kernel<1>, dim3(grid), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd,
+                    gamma, sums, invP, H, W, C, total, (bf16*)dx, dgamma, dbeta));
   PM_LAUNCH_OK();
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/primia_b200.h"
 
 extern char g_pm_err[512];
@@ -47,6 +48,42 @@ static inline int pm_num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---- programmatic dependent launch (PDL).  A kernel launched through pm_launch() may be scheduled while its predecessor in
+// the stream is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block
+// in pm_pdl_sync() until the predecessor grid has completed and flushed.  Rules kept by every kernel that uses it:
+//   * pm_pdl_sync() is executed by every thread, unconditionally, before the first global-memory access (read OR write);
+//   * nothing before it touches global memory.
+// Transitivity (kernel C after B after A also sees A's results) holds because B cannot complete before its own wait returned.
+// Launched without the attribute (PRIMIA_PDL=0, or a plain <<<>>> launch) both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pm_pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+static inline bool pm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PRIMIA_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // grid sized as a multiple of the SM count for grid-stride kernels

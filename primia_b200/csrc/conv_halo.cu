@@ -107,6 +107,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pm_pdl_sync();  // everything above is CTA-local; the first global access (TMA, stores) is below
 
   if (warp == 0) {
     // ------------------------------------------------------------ strip producer: one TMA per padded row
@@ -353,7 +354,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* 
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;
   const int ntiles = ((g.V + MT - 1) / MT) * (g.N / BN);
   dim3 grid(std::min(pm_num_sms(), ntiles));
-  kern<<<grid, 128 + MT, smem, st>>>(tmA, tmB, g, (bf16*)dst, accumulate, stats);
+  if (pm_launch(kern, grid, dim3(128 + MT), (size_t)smem, st, tmA, tmB, g, (bf16*)dst, accumulate, stats) != cudaSuccess) return 2;
   return 0;
 }
 

@@ -71,6 +71,7 @@ dgrad_s2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pm_pdl_sync();  // CTA-local prologue above, first global access below
 
   // per work item: class (ca, cb), taps r = r_first + 2*ri (nr of them), s = s_first + 2*si (ns of them)
 #define S2P_DECODE(tile)                                                                                     \
@@ -249,12 +250,14 @@ int pm_s2p_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* 
     if (!map_dense(&tmB, wt, p->C, Ktot, 128)) return 2;
     if (cudaFuncSetAttribute(dgrad_s2_kernel<128, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128)) != cudaSuccess) return 2;
     const int ntiles = 4 * ((Mc + 127) / 128) * (p->C / 128);
-    dgrad_s2_kernel<128, STAGES><<<std::min(pm_num_sms(), ntiles), NTHR, smem_bytes(128), st>>>(tmA, tmB, g, (bf16*)dx, accumulate);
+    if (pm_launch(dgrad_s2_kernel<128, STAGES>, dim3(std::min(pm_num_sms(), ntiles)), dim3(NTHR), (size_t)smem_bytes(128), st, tmA, tmB, g,
+                  (bf16*)dx, accumulate) != cudaSuccess) return 2;
   } else {
     if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
     if (cudaFuncSetAttribute(dgrad_s2_kernel<64, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64)) != cudaSuccess) return 2;
     const int ntiles = 4 * ((Mc + 127) / 128) * (p->C / 64);
-    dgrad_s2_kernel<64, STAGES><<<std::min(pm_num_sms(), ntiles), NTHR, smem_bytes(64), st>>>(tmA, tmB, g, (bf16*)dx, accumulate);
+    if (pm_launch(dgrad_s2_kernel<64, STAGES>, dim3(std::min(pm_num_sms(), ntiles)), dim3(NTHR), (size_t)smem_bytes(64), st, tmA, tmB, g,
+                  (bf16*)dx, accumulate) != cudaSuccess) return 2;
   }
   return 0;
 }

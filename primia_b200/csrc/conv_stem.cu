@@ -119,6 +119,7 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pm_pdl_sync();  // the prologue above only touched shared memory / TMEM
   const int my_tiles = (int)blockIdx.x < g.ntiles ? (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 1) {
@@ -358,7 +359,8 @@ int pm_stem_conv_fwd_bf16(const float* x_nchw, const void* w192, int B, int H, i
   if (!map_input(&tmx, x_nchw, B, H, W)) return pm_set_err(__FILE__, __LINE__, "stem input tensor map failed");
   if (!map_dense(&tm, w192, 64, 192, 64)) return pm_set_err(__FILE__, __LINE__, "stem weight tensor map failed");
   PM_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false>()));
-  stem_kernel<false><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<false>(), S(s)>>>(tm, tmx, g, (bf16*)y, stats, nullptr);
+  PM_CUDA(pm_launch(stem_kernel<false>, dim3(std::min(pm_num_sms(), g.ntiles)), dim3(NTHR), (size_t)smem_bytes<false>(), S(s), tm, tmx, g,
+                    (bf16*)y, stats, (float*)nullptr));
   PM_LAUNCH_OK();
 }
 
@@ -371,7 +373,8 @@ int pm_stem_conv_wgrad_bf16(const float* x_nchw, const void* dy, int B, int H, i
   if (!map_input(&tmx, x_nchw, B, H, W)) return pm_set_err(__FILE__, __LINE__, "stem input tensor map failed");
   if (!map_dense(&tm, dy, (uint64_t)B * g.Ho * g.Wo, 64, 128)) return pm_set_err(__FILE__, __LINE__, "stem dy tensor map failed");
   PM_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true>()));
-  stem_kernel<true><<<std::min(pm_num_sms(), g.ntiles), NTHR, smem_bytes<true>(), S(s)>>>(tm, tmx, g, nullptr, nullptr, dw_krsc);
+  PM_CUDA(pm_launch(stem_kernel<true>, dim3(std::min(pm_num_sms(), g.ntiles)), dim3(NTHR), (size_t)smem_bytes<true>(), S(s), tm, tmx, g,
+                    (bf16*)nullptr, (double*)nullptr, dw_krsc));
   PM_LAUNCH_OK();
 }
 

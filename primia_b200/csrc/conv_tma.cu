@@ -163,6 +163,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pm_pdl_sync();  // programmatic dependent launch (common.cuh): CTA-local prologue above, first global access below
 
   if (tid == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -592,17 +593,17 @@ int pm_tma_conv_fwd(const pm_conv_t* p, const void* x, const void* w, void* y, d
     if (!map_dense(&tmB, w, p->K, Ktot, 128)) return 2;
     if (!set_smem(conv_tma_kernel<128, FSTAGES, false, false>, smem_conv(128, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 128)));
-    conv_tma_kernel<128, FSTAGES, false, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+    if (pm_launch(conv_tma_kernel<128, FSTAGES, false, false>, grid, dim3(NTHREADS), (size_t)smem_conv(128, FSTAGES), st, tmA, tmB, geo(p), (bf16*)y, 0, stats) != cudaSuccess) return 2;
   } else if (p->K == 64 && Ktot * 64 * 2 <= RB_MAX_BYTES) {
     if (!map_dense(&tmB, w, p->K, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, RSTAGES, false, true>, smem_conv_rb(RSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), (M + 127) / 128));
-    conv_tma_kernel<64, RSTAGES, false, true><<<grid, NTHREADS, smem_conv_rb(RSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+    if (pm_launch(conv_tma_kernel<64, RSTAGES, false, true>, grid, dim3(NTHREADS), (size_t)smem_conv_rb(RSTAGES), st, tmA, tmB, geo(p), (bf16*)y, 0, stats) != cudaSuccess) return 2;
   } else {
     if (!map_dense(&tmB, w, p->K, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, FSTAGES, false, false>, smem_conv(64, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->K / 64)));
-    conv_tma_kernel<64, FSTAGES, false, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)y, 0, stats);
+    if (pm_launch(conv_tma_kernel<64, FSTAGES, false, false>, grid, dim3(NTHREADS), (size_t)smem_conv(64, FSTAGES), st, tmA, tmB, geo(p), (bf16*)y, 0, stats) != cudaSuccess) return 2;
   }
   return 0;
 }
@@ -641,17 +642,17 @@ int pm_tma_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* 
     if (!map_dense(&tmB, wt, p->C, Ktot, 128)) return 2;
     if (!set_smem(conv_tma_kernel<128, FSTAGES, true, false>, smem_conv(128, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 128)));
-    conv_tma_kernel<128, FSTAGES, true, false><<<grid, NTHREADS, smem_conv(128, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+    if (pm_launch(conv_tma_kernel<128, FSTAGES, true, false>, grid, dim3(NTHREADS), (size_t)smem_conv(128, FSTAGES), st, tmA, tmB, geo(p), (bf16*)dx, accumulate, (double*)nullptr) != cudaSuccess) return 2;
   } else if (p->C == 64 && Ktot * 64 * 2 <= RB_MAX_BYTES) {
     if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, RSTAGES, true, true>, smem_conv_rb(RSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), (M + 127) / 128));
-    conv_tma_kernel<64, RSTAGES, true, true><<<grid, NTHREADS, smem_conv_rb(RSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+    if (pm_launch(conv_tma_kernel<64, RSTAGES, true, true>, grid, dim3(NTHREADS), (size_t)smem_conv_rb(RSTAGES), st, tmA, tmB, geo(p), (bf16*)dx, accumulate, (double*)nullptr) != cudaSuccess) return 2;
   } else {
     if (!map_dense(&tmB, wt, p->C, Ktot, 64)) return 2;
     if (!set_smem(conv_tma_kernel<64, FSTAGES, true, false>, smem_conv(64, FSTAGES))) return 2;
     dim3 grid(std::min(pm_num_sms(), ((M + 127) / 128) * (p->C / 64)));
-    conv_tma_kernel<64, FSTAGES, true, false><<<grid, NTHREADS, smem_conv(64, FSTAGES), st>>>(tmA, tmB, geo(p), (bf16*)dx, accumulate, nullptr);
+    if (pm_launch(conv_tma_kernel<64, FSTAGES, true, false>, grid, dim3(NTHREADS), (size_t)smem_conv(64, FSTAGES), st, tmA, tmB, geo(p), (bf16*)dx, accumulate, (double*)nullptr) != cudaSuccess) return 2;
   }
   return 0;
 }

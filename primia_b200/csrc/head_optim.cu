@@ -111,6 +111,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   // torch.optim.Adam (single-tensor path): grad += wd*p ; m = b1*m + (1-b1)*grad ; v = b2*v + (1-b2)*grad^2 ;
   // denom = sqrt(v)/sqrt(bias_correction2) + eps ; p -= (lr/bias_correction1) * m/denom
   const float step = lr / bc1;
+  pm_pdl_sync();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = fmaf(wd, pi, g[i]);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(256)
 krsc_to_bf16_exact_kernel(const pm_wcvt_t* __restrict__ table, int n) {
   __shared__ float tile[32][33];
   __shared__ int s_entry, s_local;
+  pm_pdl_sync();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     int base = 0, found = 0;
@@ -337,8 +339,8 @@ int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, flo
   if (n == 0) return PM_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<pm_grid(n, 256, 1, 16), 256, 0, S(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                       (float)sqrt(bc2));
+  PM_CUDA(pm_launch(adam_kernel, dim3(pm_grid(n, 256, 1, 16)), dim3(256), 0, S(s), p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                    (float)bc1, (float)sqrt(bc2)));
   PM_LAUNCH_OK();
 }
 
@@ -388,7 +390,7 @@ int pm_krsc_to_bf16_batched(const pm_wcvt_t* table, int n, int max_tiles, pm_str
 
 int pm_krsc_to_bf16_batched_exact(const pm_wcvt_t* table, int n, int total_tiles, pm_stream_t s) {
   PM_CHECK_ARG(table && n > 0 && total_tiles > 0);
-  krsc_to_bf16_exact_kernel<<<total_tiles, 256, 0, S(s)>>>(table, n);
+  PM_CUDA(pm_launch(krsc_to_bf16_exact_kernel, dim3(total_tiles), dim3(256), 0, S(s), table, n));
   PM_LAUNCH_OK();
 }
 
