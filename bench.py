@@ -147,7 +147,7 @@ def run_reference(args):
                                    "omits PySyft per-op msgpack round-trips => lower bound on the reference's time"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -410,9 +410,31 @@ def run_ours(args):
                 line["encrypted_inference"] = encrypted_inference_block()
             except Exception as exc:  # the headline must still print
                 line["encrypted_inference"] = {"error": repr(exc)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else this process or its libraries print (NCCL's version
+    banner, warnings) is routed to stderr by pointing fd 1 at fd 2 for the duration of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -427,6 +449,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     run_ours(args)
