@@ -457,6 +457,8 @@ int pm_halo_conv(const pm_conv_t* p, const void* src, const void* wmat, void* ds
                  cudaStream_t st);
 // persistent stride-2 data gradient (conv_s2.cu), same return convention
 int pm_s2p_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
+// experimental halo-strip weight gradient (wgrad_halo.cu; only when PRIMIA_HALO_WGRAD=1), same return convention
+int pm_halo_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
 static bool use_tma() {
   const char* e = getenv("PRIMIA_NO_TMA");
   return !(e && e[0] == '1');
@@ -500,6 +502,9 @@ int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float*
   PM_CHECK_ARG(tc_ok(p) && x && dy && dw);
   (void)ws;
   if (use_tma()) {
+    const int rh = pm_halo_conv_wgrad(p, x, dy, dw, S(s));
+    if (rh == 2) return pm_set_err(__FILE__, __LINE__, "halo conv wgrad setup failed");
+    if (rh == 0) PM_LAUNCH_OK();
     const int r = pm_tma_conv_wgrad(p, x, dy, dw, S(s));
     if (r == 2) return pm_set_err(__FILE__, __LINE__, "TMA conv wgrad setup failed");
     if (r == 0) PM_LAUNCH_OK();

@@ -180,3 +180,24 @@ def test_direct_stem_conv_fwd_and_wgrad(B, H, W):
     call("pm_stem_conv_wgrad_bf16", ptr(xd), ptr(dyd), B, H, W, ptr(dw), stream())
     torch.cuda.synchronize()
     assert rel(dw.permute(0, 3, 1, 2), wr.grad) < 1e-3, "stem wgrad"
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PRIMIA_TEST_HALO_WGRAD") != "1",
+                    reason="experimental halo-strip weight gradient (wgrad_halo.cu): opt-in, PRIMIA_TEST_HALO_WGRAD=1")
+@pytest.mark.parametrize("B,H,W,C,K", [(3, 28, 28, 128, 128), (5, 14, 14, 256, 256), (9, 7, 7, 512, 256), (2, 9, 13, 128, 128)])
+def test_halo_wgrad_experimental(B, H, W, C, K, monkeypatch):
+    from primia_b200._lib import ConvDesc, call, ptr, stream
+
+    monkeypatch.setenv("PRIMIA_HALO_WGRAD", "1")
+    g = torch.Generator().manual_seed(B + H + W + C + K)
+    d = ConvDesc(B, H, W, C, K, 3, 3, 1, 1, H, W)
+    x = bf(torch.randn(B, H, W, C, generator=g))
+    dy = bf(torch.randn(B, H, W, K, generator=g))
+    xr = x.float().permute(0, 3, 1, 2)
+    wr = torch.zeros(K, C, 3, 3, requires_grad=True)
+    F.conv2d(xr, wr, None, 1, 1).backward(dy.float().permute(0, 3, 1, 2))
+    xd, dyd = x.to(DEV), dy.to(DEV)
+    dw = torch.zeros(K, 3, 3, C, dtype=torch.float32, device=DEV)
+    call("pm_conv_wgrad_bf16", ctypes.byref(d), ptr(xd), ptr(dyd), ptr(dw), None, stream())
+    torch.cuda.synchronize()
+    assert rel(dw.permute(0, 3, 1, 2), wr.grad) < 1e-3, (B, H, W, C, K, rel(dw.permute(0, 3, 1, 2), wr.grad))
