@@ -25,6 +25,7 @@ def timeit(fn, n=10, inner=8):
     tot = 0.0
     for _ in range(n):
         flush.zero_()  # evict L2
+        torch.cuda._sleep(2_000_000)  # ~1 ms spin: the host queues all `inner` launches before the GPU reaches the bracket
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(inner):
@@ -52,6 +53,13 @@ for name, H, C, K in LAYERS:
         res[variant] = y.float().clone()
         t_d = timeit(lambda: call("pm_conv_dgrad_bf16", ctypes.byref(d), ptr(dy), ptr(wt), ptr(dx), 0, stream()))
         print(f"{name:24s} {variant:5s} fwd {t_f:7.1f} us {flops / t_f / 1e6:7.1f} TF/s | dgrad {t_d:7.1f} us {flops / t_d / 1e6:7.1f} TF/s")
+    # weight gradient: im2col-TMA kernel vs the opt-in halo-strip kernel (C, K multiples of 128 only)
+    dwb = torch.zeros(K, 3, 3, C, device=DEV, dtype=torch.float32)
+    for variant in ("tma", "halo"):
+        os.environ["PRIMIA_HALO_WGRAD"] = "1" if variant == "halo" else "0"
+        t_w = timeit(lambda: call("pm_conv_wgrad_bf16", ctypes.byref(d), ptr(x), ptr(dy), ptr(dwb), None, stream()))
+        print(f"{name:24s} {variant:5s} wgrad {t_w:7.1f} us {flops / t_w / 1e6:7.1f} TF/s")
+    os.environ["PRIMIA_HALO_WGRAD"] = "0"
     # per-CTA cycle counters of one profiled halo launch (fwd, then dgrad)
     import numpy as np
     os.environ["PRIMIA_NO_HALO"] = "0"
