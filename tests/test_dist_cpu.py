@@ -58,8 +58,8 @@ def test_reference_arm_prints_one_json_line_rank0_only():
                         "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0", "--ref-batch", "2"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 1
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]  # stdout carries the JSON line and nothing else (bench.claim_stdout)
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "federated_round_images_per_sec" and d["n_gpus"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
