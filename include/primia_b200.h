@@ -269,6 +269,11 @@ int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, 
 int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s);
 int pm_maxpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, uint8_t* idx, pm_stream_t s);
 int pm_maxpool3s2_bwd_bf16(const void* dy, const uint8_t* idx, int B, int H, int W, int C, void* dx, pm_stream_t s);
+/* AvgPool2d(3,2,1) (pooling="avg", models.py:386-387; zero padding counted, divisor 9): y [B,Ho,Wo,C]; backward dx [B,H,W,C] */
+int pm_avgpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, pm_stream_t s);
+int pm_avgpool3s2_bwd_f32(const float* dy, int B, int H, int W, int C, float* dx, pm_stream_t s);
+int pm_avgpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, pm_stream_t s);
+int pm_avgpool3s2_bwd_bf16(const void* dy, int B, int H, int W, int C, void* dx, pm_stream_t s);
 /* AvgPool2d(HW) -> [B,C] (models.py:400-404,477) and its backward (broadcast / HW) */
 int pm_gap_fwd_f32(const float* x, int B, int HW, int C, float* y, pm_stream_t s);
 int pm_gap_bwd_f32(const float* dy, int B, int HW, int C, float* dx, pm_stream_t s);

@@ -1188,6 +1188,83 @@ int bn_bwd_apply_t(const T* dy, const T* y_out, const T* x, const float* mean, c
                                                                 dgamma, dbeta);
   PM_LAUNCH_OK();
 }
+
+// ---- avg pool 3x3 s2 p1 (nn.AvgPool2d defaults: zero padding counted, divisor always 9 -- torchlib/models.py:386-387)
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int H, int W, int C, int Ho, int Wo, size_t total, T* __restrict__ y) {
+  constexpr int V = Vec<T>::N;
+  const int CV = C / V;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    size_t t = i / CV;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho);
+    const size_t b = t / Ho;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        float v[V];
+        Vec<T>::load(x + ((b * H + ih) * W + iw) * C + cv * V, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += v[k];   // window scanned row-major, as ATen's CPU kernel does
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = acc[k] / 9.f;
+    Vec<T>::store(y + i * V, acc);
+  }
+}
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int H, int W, int C, int Ho, int Wo, size_t total, T* __restrict__ dx) {
+  constexpr int V = Vec<T>::N;
+  const int CV = C / V;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    size_t t = i / CV;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const size_t b = t / H;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int oh = h / 2; oh <= (h + 1) / 2; ++oh) {
+      if (oh >= Ho) continue;
+      for (int ow = w / 2; ow <= (w + 1) / 2; ++ow) {
+        if (ow >= Wo) continue;
+        float g[V];
+        Vec<T>::load(dy + (((b * Ho + oh) * Wo + ow) * CV + cv) * V, g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += g[k] / 9.f;
+      }
+    }
+    Vec<T>::store(dx + i * V, acc);
+  }
+}
+
+template <typename T>
+int avgpool_fwd_t(const T* x, int B, int H, int W, int C, T* y, pm_stream_t s) {
+  PM_CHECK_ARG(x && y && B > 0 && C % Vec<T>::N == 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * Ho * Wo * (C / Vec<T>::N);
+  avgpool_fwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(x, H, W, C, Ho, Wo, total, y);
+  PM_LAUNCH_OK();
+}
+template <typename T>
+int avgpool_bwd_t(const T* dy, int B, int H, int W, int C, T* dx, pm_stream_t s) {
+  PM_CHECK_ARG(dy && dx && B > 0 && C % Vec<T>::N == 0);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * H * W * (C / Vec<T>::N);
+  avgpool_bwd_kernel<T><<<pm_grid(total, 256, 1, 16), 256, 0, S(s)>>>(dy, H, W, C, Ho, Wo, total, dx);
+  PM_LAUNCH_OK();
+}
 template <typename T>
 int maxpool_fwd_t(const T* x, int B, int H, int W, int C, T* y, uint8_t* idx, pm_stream_t s) {
   PM_CHECK_ARG(x && y && idx && B > 0);
@@ -1335,6 +1412,14 @@ int pm_maxpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, 
 }
 int pm_maxpool3s2_bwd_f32(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, pm_stream_t s) {
   return maxpool_bwd_t<float>(dy, idx, B, H, W, C, dx, s);
+}
+int pm_avgpool3s2_fwd_f32(const float* x, int B, int H, int W, int C, float* y, pm_stream_t s) { return avgpool_fwd_t<float>(x, B, H, W, C, y, s); }
+int pm_avgpool3s2_bwd_f32(const float* dy, int B, int H, int W, int C, float* dx, pm_stream_t s) { return avgpool_bwd_t<float>(dy, B, H, W, C, dx, s); }
+int pm_avgpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, pm_stream_t s) {
+  return avgpool_fwd_t<bf16>((const bf16*)x, B, H, W, C, (bf16*)y, s);
+}
+int pm_avgpool3s2_bwd_bf16(const void* dy, int B, int H, int W, int C, void* dx, pm_stream_t s) {
+  return avgpool_bwd_t<bf16>((const bf16*)dy, B, H, W, C, (bf16*)dx, s);
 }
 int pm_maxpool3s2_fwd_bf16(const void* x, int B, int H, int W, int C, void* y, uint8_t* idx, pm_stream_t s) {
   return maxpool_fwd_t<bf16>((const bf16*)x, B, H, W, C, (bf16*)y, idx, s);

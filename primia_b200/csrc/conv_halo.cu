@@ -70,8 +70,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bfull0 = sempty0 + 8 * SSTAGES, bempty0 = bfull0 + 8 * BSTAGES;
   const uint32_t tfull0 = bempty0 + 8 * BSTAGES, tempty0 = tfull0 + 16, bres = tempty0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SSTAGES + 2 * BSTAGES + 5);
-  float* cta_stats = reinterpret_cast<float*>(bars + 2 * SSTAGES + 2 * BSTAGES + 6);  // [2][N]
-  uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + 2 * g.N);              // [4 * NH warps][2048]
+  constexpr int NEW = 4 * NH;                                                          // epilogue warps
+  float* cta_stats = reinterpret_cast<float*>(bars + 2 * SSTAGES + 2 * BSTAGES + 6);  // [NEW warps][2][N]: one private slot per warp
+  uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + NEW * 2 * g.N);        // [NEW][2048]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   PROF_T(t_kernel);
@@ -101,7 +102,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (do_stats)
-    for (int i = tid; i < 2 * g.N; i += NTHR) cta_stats[i] = 0.f;
+    for (int i = tid; i < NEW * 2 * g.N; i += NTHR) cta_stats[i] = 0.f;
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -235,6 +236,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ epilogue (4 warps per 128-row accumulator)
     const int j = (warp - 4) >> 2, quad = warp & 3;
     uint8_t* epi_scr = epi_scr_all + (warp - 4) * 2048;
+    float* my_stats = cta_stats + (warp - 4) * 2 * g.N;
     float st[BN / 32][4];  // BatchNorm partial sums of this warp's rows, per 32-column chunk, kept across tiles
 #pragma unroll
     for (int cc = 0; cc < BN / 32; ++cc)
@@ -248,7 +250,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (do_stats && n0 != st_n0) {  // the column range changes between this CTA's tiles only if gridDim % ntn != 0
         if (st_n0 >= 0) {
 #pragma unroll
-          for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, cta_stats + st_n0 + cc * 32, cta_stats + g.N + st_n0 + cc * 32);
+          for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, my_stats + st_n0 + cc * 32, my_stats + g.N + st_n0 + cc * 32);
         }
         st_n0 = n0;
       }
@@ -282,7 +284,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (do_stats && st_n0 >= 0) {
 #pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, cta_stats + st_n0 + cc * 32, cta_stats + g.N + st_n0 + cc * 32);
+      for (int cc = 0; cc < BN / 32; ++cc) stats_flush32(st[cc], lane, my_stats + st_n0 + cc * 32, my_stats + g.N + st_n0 + cc * 32);
     }
     if (g.prof && tid == 128) {
       halo_prof[blockIdx.x * 8 + 4] = pw0;
@@ -299,8 +301,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (do_stats)
     for (int i = tid; i < 2 * g.N; i += NTHR) {
-      const float v = cta_stats[i];
-      if (v != 0.f) atomicAdd(stats + i, (double)v);
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < NEW; ++w) v += (double)cta_stats[w * 2 * g.N + i];  // fixed order
+      if (v != 0.0) atomicAdd(stats + i, v);
     }
   if (warp == 1) {
     tc_fence_after();
@@ -348,7 +352,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* 
   const int max_rows = (g.Wp - 1 + MT + 2 * g.Wp + 1) / g.Wp + 1;
   g.strip_bytes = (max_rows * g.Wp * 128 + 1023) / 1024 * 1024;
   g.b_bytes = RB ? 9 * (g.Cin / 64) * BN * 128 : BSTAGES * BN * 128;
-  const int smem = SSTAGES * g.strip_bytes + g.b_bytes + 256 + 2 * g.N * 4 + (MT / 32) * 2048 + 1024;
+  const int smem = SSTAGES * g.strip_bytes + g.b_bytes + 256 + (MT / 32) * 2 * g.N * 4 + (MT / 32) * 2048 + 1024;
   if (smem > 227 * 1024) return 1;
   auto kern = conv_halo_kernel<MT, BN, FLIP, RB>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;

@@ -91,8 +91,8 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 16, tfull0 = afull0 + 32, tempty0 = afull0 + 48, wfull0 = afull0 + 64,
                  wempty0 = afull0 + 80, pfull0 = afull0 + 96, pempty0 = afull0 + 112;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* cta_stats = reinterpret_cast<float*>(bars + 18);  // [2][64] (16-byte aligned: the scratch follows)
-  uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + 128);  // [8 warps][2048]
+  float* cta_stats = reinterpret_cast<float*>(bars + 18);  // [8 warps][2][64]: one private slot per epilogue warp (16-byte aligned)
+  uint8_t* epi_scr_all = reinterpret_cast<uint8_t*>(cta_stats + 8 * 128);  // [8 warps][2048]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -112,7 +112,7 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   }
   // the operand tiles start as zeros: chunk groups 21..23 (and wgrad's 4th block) are never written again
   for (int i = tid; i < 2 * A_BYTES / 16; i += NTHR) reinterpret_cast<uint4*>(a_buf)[i] = make_uint4(0, 0, 0, 0);
-  if (tid < 128) cta_stats[tid] = 0.f;
+  for (int i = tid; i < 8 * 128; i += NTHR) cta_stats[i] = 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
@@ -252,7 +252,7 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       }
-      if (stats) stats_flush32(st, lane, cta_stats + ch * 32, cta_stats + 64 + ch * 32);
+      if (stats) stats_flush32(st, lane, cta_stats + (warp - 12) * 128 + ch * 32, cta_stats + (warp - 12) * 128 + 64 + ch * 32);
     } else if (my_tiles > 0) {
       mbar_wait(tfull0, 0);
       tc_fence_after();
@@ -278,8 +278,10 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   }
   __syncthreads();
   if (!WGRAD && stats && tid < 128) {
-    const float t = cta_stats[tid];
-    if (t != 0.f) atomicAdd(stats + tid, (double)t);
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)cta_stats[w * 128 + tid];  // fixed order
+    if (t != 0.0) atomicAdd(stats + tid, t);
   }
   if (warp == 0) {
     tc_fence_after();
@@ -338,7 +340,7 @@ static SGeo geo(int B, int H, int W) {
   return g;
 }
 template <bool WGRAD>
-constexpr int smem_bytes() { return 2 * (WGRAD ? 4 : 3) * BLK + (WGRAD ? 2 * BLK : 3 * 8192) + 2 * PATCH_BYTES + 18 * 8 + 128 * 4 + 8 * 2048 + 1024; }
+constexpr int smem_bytes() { return 2 * (WGRAD ? 4 : 3) * BLK + (WGRAD ? 2 * BLK : 3 * 8192) + 2 * PATCH_BYTES + 18 * 8 + 8 * 128 * 4 + 8 * 2048 + 1024; }
 
 }  // namespace stem
 

@@ -129,7 +129,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tfull0 = full0 + 16 * STAGES, tempty0 = tfull0 + 16, bfull = tempty0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
   float* scratch_all = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // 4 x [32][33] transposition scratch
-  float* cta_stats = scratch_all + 4 * 32 * 33;                         // [2][N] per-CTA partial statistics
+  float* cta_stats = scratch_all + 4 * 32 * 33;                         // [4 warps][2][N]: one private slot per epilogue warp
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int OH = FLIP ? p.H : p.Ho, OW = FLIP ? p.W : p.Wo;
@@ -157,7 +157,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (do_stats)
-    for (int i = tid; i < 2 * N; i += NTHREADS) cta_stats[i] = 0.f;
+    for (int i = tid; i < 4 * 2 * N; i += NTHREADS) cta_stats[i] = 0.f;
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -245,8 +245,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             s1 += t;
             s2 = fmaf(t, t, s2);
           }
-          atomicAdd(&cta_stats[n0 + cc * 32 + lane], s1);
-          atomicAdd(&cta_stats[N + n0 + cc * 32 + lane], s2);
+          cta_stats[quad * 2 * N + n0 + cc * 32 + lane] += s1;   // this warp's slot: no atomics, fixed summation order
+          cta_stats[quad * 2 * N + N + n0 + cc * 32 + lane] += s2;
           __syncwarp();
         }
         if (row < M) {
@@ -281,8 +281,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   if (do_stats)
     for (int i = tid; i < 2 * N; i += NTHREADS) {
-      const float v = cta_stats[i];
-      if (v != 0.f) atomicAdd(stats + i, (double)v);
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) v += (double)cta_stats[w * 2 * N + i];
+      if (v != 0.0) atomicAdd(stats + i, v);
     }
   if (warp == 1) {
     tc_fence_after();
@@ -572,8 +574,8 @@ static bool set_smem(Kern k, int bytes) {
 
 constexpr int FSTAGES = 5;
 constexpr int RSTAGES = 6;  // resident-B variant: stages hold only the 16 KB activation tiles
-constexpr int smem_conv(int BN, int stages) { return stages * (TILE_BYTES + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4 + 2 * 512 * 4; }
-constexpr int smem_conv_rb(int stages) { return stages * TILE_BYTES + RB_MAX_BYTES + 1024 + 256 + 4 * 32 * 33 * 4 + 2 * 512 * 4; }
+constexpr int smem_conv(int BN, int stages) { return stages * (TILE_BYTES + BN * 128) + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * 2 * 512 * 4; }
+constexpr int smem_conv_rb(int stages) { return stages * TILE_BYTES + RB_MAX_BYTES + 1024 + 256 + 4 * 32 * 33 * 4 + 4 * 2 * 512 * 4; }
 constexpr int smem_wg(int BN, int stages) { return stages * (2 * TILE_BYTES + (BN / 64) * TILE_BYTES) + 1024 + 256; }
 
 static Geo geo(const pm_conv_t* p) { return Geo{p->B, p->H, p->W, p->C, p->K, p->R, p->S, p->stride, p->pad, p->Ho, p->Wo}; }

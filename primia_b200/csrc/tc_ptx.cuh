@@ -185,14 +185,18 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], bool v
   }
   __syncwarp();  // the scratch is reused by the next chunk
 }
-// adds the warp's partial sums of one 32-column chunk into s1[32] / s2[32] (shared memory) and clears them
+// adds the warp's partial sums of one 32-column chunk into s1[32] / s2[32] and clears them.  s1 / s2 point into THIS WARP's
+// private shared-memory slot (no atomics): every CTA-level sum is then formed in a fixed order, so the statistics -- and with
+// them the whole bf16 forward -- do not depend on warp scheduling (the cross-CTA step is a double-precision atomic per CTA and
+// channel: a 1e-16 relative order effect, far below fp32 resolution).
 __device__ __forceinline__ void stats_flush32(float (&st)[4], int lane, float* s1, float* s2) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) st[k] += __shfl_xor_sync(0xffffffffu, st[k], 16);
   if (lane < 16) {
-    atomicAdd(s1 + 2 * lane, st[0]); atomicAdd(s1 + 2 * lane + 1, st[1]);
-    atomicAdd(s2 + 2 * lane, st[2]); atomicAdd(s2 + 2 * lane + 1, st[3]);
+    s1[2 * lane] += st[0]; s1[2 * lane + 1] += st[1];
+    s2[2 * lane] += st[2]; s2[2 * lane + 1] += st[3];
   }
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < 4; ++k) st[k] = 0.f;
 }

@@ -49,6 +49,22 @@ class ShareRNG:
 DEFAULT_RNG = ShareRNG()  # one stream per process: every fresh sharing draws a new Philox offset
 
 
+def provider_of(crypto_provider, seed=None):
+    """``crypto_provider=`` of the PySyft verbs is a WORKER (inference.py:281-285); the object that generates primitives on
+    that worker's GPU is created once per worker and reused, so its Philox counter never restarts."""
+    if crypto_provider is None or isinstance(crypto_provider, TripleProvider):
+        return crypto_provider
+    prov = getattr(crypto_provider, "_triple_provider", None)
+    if prov is None:
+        if seed is None:
+            import secrets
+
+            seed = secrets.randbits(63)
+        prov = TripleProvider(crypto_provider, seed)
+        crypto_provider._triple_provider = prov
+    return prov
+
+
 class AdditiveSharingTensor:
     """2-party additive sharing over Z_2^64; ``child[j]`` is party j's share on party j's GPU."""
 
@@ -174,8 +190,7 @@ class FixedPrecisionTensor:
 
     def share(self, *parties, crypto_provider=None, rng=None, **_):
         """precision.py:910-957 -> native.share native.py:887-949"""
-        prov = crypto_provider if isinstance(crypto_provider, TripleProvider) or crypto_provider is None else TripleProvider(crypto_provider)
-        ast = AdditiveSharingTensor.share_secret(self.child, list(parties), prov, rng)
+        ast = AdditiveSharingTensor.share_secret(self.child, list(parties), provider_of(crypto_provider), rng)
         return FixedPrecisionTensor(ast, self.base, self.precision_fractional)
 
     def get(self):

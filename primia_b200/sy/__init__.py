@@ -63,9 +63,11 @@ class VirtualWorker(Party):
 
 
 class PointerTensor:
-    """syft/generic/pointers/pointer_tensor.py: a handle to a tensor living on ``location``'s GPU."""
+    """syft/generic/pointers/pointer_tensor.py: a handle to a tensor living on ``location``'s GPU.  The verbs the entry points
+    call on pointers (inference.py:298-311: shape / squeeze / unsqueeze / to / fix_precision / share / copy / get) run on the
+    owner's GPU and return pointers; ``get`` hands the object over."""
 
-    def __init__(self, location: VirtualWorker, tensor: torch.Tensor):
+    def __init__(self, location: VirtualWorker, tensor):
         self.location = location
         self._t = tensor
 
@@ -85,6 +87,23 @@ class PointerTensor:
     def __getitem__(self, idx):
         return PointerTensor(self.location, self._t[idx])
 
+    def squeeze(self, *a):
+        return PointerTensor(self.location, self._t.squeeze(*a))
+
+    def unsqueeze(self, dim):
+        return PointerTensor(self.location, self._t.unsqueeze(dim))
+
+    def to(self, *_a, **_k):
+        return self  # the data stays on its owner's GPU
+
+    def fix_precision(self, **kw):
+        return PointerTensor(self.location, _fix_precision(self._t, **kw))
+
+    fix_prec = fix_precision
+
+    def share(self, *workers, **kw):
+        return PointerTensor(self.location, self._t.share(*workers, **kw))
+
 
 def _tag(self, *tags):
     self._sy_tags = tuple(getattr(self, "_sy_tags", ())) + tags
@@ -99,10 +118,91 @@ def _send(self, worker):
 
 
 def _fix_precision(self, precision_fractional=3, dtype="long", base=10, **_):
+    """native.fix_prec native.py:835-864 -> FixedPrecisionTensor.fix_precision precision.py:117-132"""
     if dtype != "long":
         raise NotImplementedError("the ring is Z_2^64 (dtype='long'), as inference.py:280 uses")
     x = self if self.is_cuda else self.cuda()
-    return FixedPrecisionTensor.fix_precision(x.float().contiguous(), base, precision_fractional)
+    return FixedPrecisionTensor.fix_precision(x.detach().float().contiguous(), base, precision_fractional)
+
+
+def _share(self, *workers, crypto_provider=None, protocol="fss", requires_grad=False, **_):
+    """native.share native.py:887-949 on a raw tensor: only integer tensors can be additively shared (:931-932)"""
+    if self.is_floating_point():
+        raise TypeError("FloatTensor cannot be additively shared, Use fix_precision.")
+    if protocol != "fss":
+        raise NotImplementedError("protocol 'fss' (function secret sharing) is the built comparison protocol; 'snn' is not")
+    x = (self if self.is_cuda else self.cuda()).to(torch.int64).contiguous()
+    return AdditiveSharingTensor.share_secret(x, list(workers), ring.tensors.provider_of(crypto_provider))
+
+
+# ---- torch.nn.Module verbs (hook.py:613-807).  PySyft replaces every parameter AND buffer in place (tensor_iterator :626-632
+# iterates ``parameters`` and ``buffers``); torch 2 Parameters cannot hold our share objects, so the converted tensors live in
+# ``module._sy_shared`` (state_dict key -> FixedPrecisionTensor) beside the untouched fp32 Parameters.
+def _named_tensors(module):
+    for k, v in module.named_parameters():
+        yield k, v
+    for k, v in module.named_buffers():
+        yield k, v
+
+
+def _module_fix_precision(self, **kw):
+    """module_fix_precision_ hook.py:738-765"""
+    self._sy_shared = {k: _fix_precision(v.data, **kw) for k, v in _named_tensors(self)
+                       if v.is_floating_point()}  # num_batches_tracked (int64 counter) is never read by the eval forward
+    self._sy_state = "fixed"
+    return self
+
+
+def _module_share(self, *workers, **kw):
+    """module_share_ hook.py:767-782: every parameter and buffer .share()d in place"""
+    if getattr(self, "_sy_state", None) != "fixed":
+        raise RuntimeError("call model.fix_precision(...) before model.share(...) (FloatTensor cannot be additively shared)")
+    self._sy_shared = {k: v.share(*workers, **kw) for k, v in self._sy_shared.items()}
+    self._sy_state = "shared"
+    return self
+
+
+def _module_float_precision(self):
+    """module_float_precision_ hook.py:784-796 (after .get())"""
+    for k, v in _named_tensors(self):
+        if k in getattr(self, "_sy_shared", {}):
+            v.data.copy_(self._sy_shared[k].float_precision().reshape(v.shape))
+    self._sy_shared, self._sy_state = None, None
+    return self
+
+
+def _module_send(self, *dest, **_):
+    """module_send_ hook.py:650-664: parameters and buffers move to the worker's GPU; the module remembers its location"""
+    (worker,) = dest
+    if any(True for _ in self.parameters()) or any(True for _ in self.buffers()):
+        self.to(worker.device)
+    self.location = worker
+    worker.object_store.register(self)
+    return self
+
+
+def _module_get(self):
+    """module_get_ hook.py:693-706: for shared modules reconstruct every tensor, otherwise just drop the location"""
+    if getattr(self, "_sy_state", None) == "shared":
+        self._sy_shared = {k: v.get() for k, v in self._sy_shared.items()}
+        self._sy_state = "fixed"
+    self.location = None
+    return self
+
+
+def _module_copy(self):
+    """module_copy hook.py:798-807"""
+    import copy
+
+    # engines / encrypted evaluators are caches bound to device buffers: the copy starts without them
+    held = {k: self.__dict__.pop(k) for k in ("_engines", "_encrypted") if k in self.__dict__}
+    try:
+        new = copy.deepcopy(self)
+    finally:
+        self.__dict__.update(held)
+    if "_engines" in held:
+        new._engines, new._encrypted = {}, None
+    return new
 
 
 class TorchHook:
@@ -115,6 +215,16 @@ class TorchHook:
         T.send = _send
         T.fix_precision = _fix_precision
         T.fix_prec = _fix_precision
+        T.share = _share
+        M = torch_module.nn.Module
+        M.fix_precision = M.fix_prec = _module_fix_precision
+        M.share = _module_share
+        M.float_precision = M.float_prec = _module_float_precision
+        M.send = _module_send
+        M.get = _module_get
+        M.copy = _module_copy
+        if not hasattr(M, "location"):
+            M.location = None
         hook = self
         local_worker = VirtualWorker(self, id="me", device="cuda:0" if torch.cuda.is_available() else "cpu")
         self.local_worker = local_worker
@@ -183,11 +293,25 @@ class FederatedDataLoader:
             yield PointerTensor(ds.location, data[idx]), PointerTensor(ds.location, targets[idx])
 
 
+class RemoteTensorDataset:
+    """torchlib/dataloader.py RemoteTensorDataset (inference.py:229): items are pointers to single images on the data owner"""
+
+    def __init__(self, tensor: PointerTensor):
+        self.tensor = tensor
+
+    def __len__(self):
+        return len(self.tensor)
+
+    def __getitem__(self, i):
+        return self.tensor[i].copy()
+
+
 class serde:  # inference.py:37-39 touches sy.serde.compression.* : accepted and ignored (no bytes are serialised here)
     class compression:
         NO_COMPRESSION = 40
         default_compress_scheme = 40
 
 
-def make_crypto_provider(worker: VirtualWorker, seed=0x5EED) -> TripleProvider:
-    return TripleProvider(worker, seed)
+def make_crypto_provider(worker: VirtualWorker, seed=None) -> TripleProvider:
+    """the TripleProvider that generates Beaver triples / FSS keys on ``worker``'s GPU (one per worker, created on first use)"""
+    return ring.tensors.provider_of(worker, seed)

@@ -111,15 +111,32 @@ def _telescoping_shares(q: torch.Tensor, n: int, seed: int, counter: int):
     return shares
 
 
+def _mask_stream(worker: HospitalWorker, n: int, seed: Optional[int]):
+    """(seed, first counter) of the Philox stream this hospital masks its state with in ONE aggregation.  The seed is a
+    per-hospital secret drawn from the OS (never derivable by a peer) and the counter only moves forward, so no pad is ever
+    reused across rounds -- a reused pad would hand the receiving hospital the difference of two rounds' weights, a public
+    one the weights themselves.  ``seed`` (tests only) pins the stream."""
+    if seed is not None:
+        return seed, 1
+    if getattr(worker, "_mask_seed", None) is None:
+        import secrets
+
+        worker._mask_seed, worker._mask_counter = secrets.randbits(63), 1
+    c = worker._mask_counter
+    worker._mask_counter += max(n - 1, 1)
+    return worker._mask_seed, c
+
+
 def secure_aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float]] = None, group=None,
-                       precision_fractional: int = 16, base: int = 10, seed: int = 0x5A6E):
+                       precision_fractional: int = 16, base: int = 10, seed: Optional[int] = None):
     """The reference's DEFAULT aggregation (``secure=True``, utils.py:1045-1060,1078-1090) on GPUs:
 
         (param * w_i).fix_prec(pf).share(*workers).get()  ->  share-wise sum over hospitals  ->  .get()  ->  .float_prec()  [-> / n]
 
     Every hospital fixed-point-encodes its flat state (pm_encode_f32_i64), splits it into one additive share per hospital
     (Philox), share j travels to hospital j (all-to-all over NVLink when one hospital runs per rank), hospital j adds the
-    shares it received -- no party ever sees another hospital's plaintext weights -- and the per-hospital sums are
+    shares it received -- a hospital only ever sees uniformly random shares of another hospital's weights, masked with pads
+    from that hospital's own secret Philox stream (``_mask_stream``) -- and the per-hospital sums are
     reconstructed with an int64 SUM all-reduce (two's-complement wraparound == arithmetic mod 2^64) and decoded.
     Result (identical on every hospital) == decode(sum_i encode(theta_i * w_i)) [/ n], the reference's arithmetic."""
     import torch.distributed as dist
@@ -140,7 +157,7 @@ def secure_aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str
             encoded.append(ops.encode(x, base, precision_fractional))
     if distributed:
         q = encoded[0]
-        shares = _telescoping_shares(q, n, seed + rank, 1)
+        shares = _telescoping_shares(q, n, *_mask_stream(workers[0], n, None if seed is None else seed + rank))
         send = torch.stack(shares)                      # [n, len]: row j goes to hospital j
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=group)
@@ -153,7 +170,7 @@ def secure_aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str
         dev = workers[0].engine.device
         held = [None] * n                                # held[j]: what hospital j accumulates
         for i, q in enumerate(encoded):
-            for j, sh in enumerate(_telescoping_shares(q, n, seed + i, 1)):
+            for j, sh in enumerate(_telescoping_shares(q, n, *_mask_stream(workers[i], n, None if seed is None else seed + i))):
                 sh = sh.to(workers[j].engine.device)
                 held[j] = sh if held[j] is None else ops.axpby(1, held[j], 1, sh)
         total = held[0].to(dev)
@@ -206,15 +223,35 @@ def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float
 
 
 def federated_round(workers: List[HospitalWorker], sync_every_n_batch: int = 1, weights=None, keep_optim_dict=False,
-                    group=None, secure: bool = False, precision_fractional: int = 16):
-    """secure_aggregation_epoch (utils.py:1108-1233) with unencrypted aggregation.  Hospitals of this process are
-    visited in order (utils.py:1160); with one hospital per rank they run concurrently on their own GPUs."""
+                    group=None, secure: bool = False, precision_fractional: int = 16, opt_lr: Optional[float] = None):
+    """secure_aggregation_epoch (utils.py:1108-1233).  Hospitals of this process are visited in order (utils.py:1160); with
+    one hospital per rank they run concurrently on their own GPUs.
+
+    Reference semantics kept: (1) optimizers are re-created at the start of the epoch and after every mid-epoch aggregation
+    unless ``keep_optim_dict`` -- WITH ``lr = args.lr`` (utils.py:1131-1145,1209-1218; pass it as ``opt_lr``), which discards
+    whatever the epoch's learning-rate schedule had set; (2) a hospital that has run out of batches is skipped
+    (:1166-1167), still contributes its (stale) model to every later aggregation, but receives the new model only at the end
+    of the epoch (send_new_models is restricted to ``num_batches[w] > batch_idx``, :1187-1194); (3) the returned loss is the
+    mean over every local step of every hospital.  With one hospital per rank the number of rounds is the maximum over ranks
+    and exhausted ranks keep taking part in the collectives."""
+    import torch.distributed as dist
+
+    def reset(w):
+        w.engine.reset_optimizer()
+        if opt_lr is not None:
+            w.engine.lr = opt_lr
+
     if not keep_optim_dict:
         for w in workers:
-            w.engine.reset_optimizer()
+            reset(w)
     losses = []
     nb = {w.id: len(w.batches) for w in workers}
     max_b = max(nb.values())
+    dev = workers[0].engine.device
+    if group is not None:
+        t = torch.tensor([max_b], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        max_b = int(t.item())
     for batch_idx in range(max_b):
         for w in workers:
             if batch_idx >= nb[w.id]:
@@ -222,11 +259,19 @@ def federated_round(workers: List[HospitalWorker], sync_every_n_batch: int = 1, 
             d, t = w.batches[batch_idx]
             losses.append(w.local_step(d, t).clone())  # engine.loss is a reused device buffer
         if batch_idx > 0 and batch_idx % sync_every_n_batch == 0:
+            done = [w for w in workers if nb[w.id] <= batch_idx]
+            stale = {w.id: w.engine.flat.clone() for w in done}
             aggregation(workers, weights, group, secure, precision_fractional)
+            for w in done:  # not in send_new_models' recipient list: keeps the model it finished with
+                w.engine.flat.copy_(stale[w.id])
             if not keep_optim_dict:
                 for w in workers:
-                    w.engine.reset_optimizer()
+                    reset(w)
     aggregation(workers, weights, group, secure, precision_fractional)
-    if not losses:
-        return torch.zeros(())
-    return torch.stack([l.reshape(()).to(losses[0].device) for l in losses]).mean()
+    tot = torch.zeros(2, dtype=torch.float64, device=dev)
+    if losses:
+        tot[0] = torch.stack([l.reshape(()).to(dev).double() for l in losses]).sum()
+        tot[1] = len(losses)
+    if group is not None:
+        dist.all_reduce(tot, group=group)
+    return (tot[0] / tot[1].clamp_min(1)).float()

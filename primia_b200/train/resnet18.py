@@ -47,12 +47,13 @@ class ResNet18Engine:
     BN_MOMENTUM = 0.1
 
     def __init__(self, batch, num_classes=3, in_channels=3, input_size=224, pooling="max", device="cuda:0", mode="f32",
-                 optimizer="Adam", lr=1e-4, betas=(0.5, 0.99), weight_decay=5e-4, eps=1e-8, class_weights=None):
-        if pooling != "max":
-            raise NotImplementedError("pooling='max' (MaxPool2d(3,2,1), models.py:384-385) is the built path")
+                 optimizer="Adam", lr=1e-4, betas=(0.5, 0.99), weight_decay=5e-4, eps=1e-8, class_weights=None, adptpool=False):
+        if pooling not in ("max", "avg"):
+            raise NotImplementedError("pooling type unknown: {:s}".format(str(pooling)))  # models.py:388-389
         if mode not in ("f32", "bf16"):
             raise ValueError(mode)
         self.B, self.ncls, self.cin, self.size = batch, num_classes, in_channels, input_size
+        self.pooling, self.adptpool = pooling, adptpool
         self.device = torch.device(device)
         self.mode = mode
         self.adt = torch.float32 if mode == "f32" else torch.bfloat16
@@ -67,7 +68,7 @@ class ResNet18Engine:
         self.overlap_wgrad = mode == "bf16"
         # bf16 throughput mode: the stem's BN + ReLU + max-pool run as one pass (the 112x112 activation is never written) and
         # BN backward recomputes the ReLU decision from x instead of reading the stored activation where no residual is added
-        self.fuse_stem_pool = mode == "bf16"
+        self.fuse_stem_pool = mode == "bf16" and pooling == "max"
         self.bn_xmask = mode == "bf16"
         # bf16 stem as a direct implicit GEMM over the fp32 NCHW input (conv_stem.cu): no im2col matrix.  The im2col + dense
         # GEMM route stays for other channel counts and as the cross-check (PRIMIA_NO_DIRECT_STEM=1).
@@ -112,8 +113,9 @@ class ResNet18Engine:
                 inpl, H = planes, ca.Ho
         self.convs, self.bns, self.blocks = convs, bns, blocks
         self.final_hw = H
-        if H * 32 != S and int(S / 32) != H:
-            pass
+        if not self.adptpool and int(S / 32) != H:
+            # AvgPool2d(int(input_size / 32)) (models.py:400-404) would leave more than one pixel: the reference's fc then fails
+            raise ValueError(f"input_size {S}: final feature map {H}x{H} != AvgPool2d({int(S / 32)}); use adptpool=True")
         self.feat_dim = 512
         # parameter order == model.parameters() order of the reference module
         order = [("conv1.weight", c1.wshape), ("bn1.weight", (64,)), ("bn1.bias", (64,))]
@@ -265,12 +267,13 @@ class ResNet18Engine:
                 ordered[bn + ".num_batches_tracked"] = torch.tensor(self.step_count, dtype=torch.int64)
         return ordered
 
-    def grad_dict(self):
-        """gradients in the reference layout (KCRS) -- used by the parity tests"""
+    def flat_to_torch_layout(self, flat):
+        """a parameter-shaped flat buffer (gradients, Adam moments) as {name: tensor} in the reference layout (KCRS)"""
         out = OrderedDict()
         with torch.cuda.device(self.device):
             for name, _ in self.param_order:
-                t = self.g[name]
+                o, n, shape = self.offsets[name]
+                t = flat[o:o + n].view(shape)
                 if t.dim() == 4:
                     K, R, S_, C = t.shape
                     dst = torch.empty((K, C, R, S_), dtype=torch.float32, device=self.device)
@@ -279,6 +282,23 @@ class ResNet18Engine:
                 else:
                     out[name] = t.clone()
         return out
+
+    def torch_layout_to_flat(self, tensors, flat):
+        """inverse of ``flat_to_torch_layout``: {name: tensor in the reference layout} -> the flat buffer (in place)"""
+        with torch.cuda.device(self.device):
+            for name, _ in self.param_order:
+                o, n, shape = self.offsets[name]
+                src = tensors[name].detach().to(self.device, torch.float32).contiguous()
+                dst = flat[o:o + n].view(shape)
+                if src.dim() == 4:
+                    K, C, R, S_ = src.shape
+                    call("pm_kcrs_to_krsc_f32", ptr(src), K, C, R, S_, ptr(dst), stream())
+                else:
+                    dst.copy_(src.view(shape))
+
+    def grad_dict(self):
+        """gradients in the reference layout (KCRS) -- used by the parity tests"""
+        return self.flat_to_torch_layout(self.grads)
 
     # ------------------------------------------------------------------ kernels
     def _prof_begin(self, tag="conv"):
@@ -435,8 +455,11 @@ class ResNet18Engine:
                      ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.running_mean"]), ptr(self.p["bn1.running_var"]), stream())
             else:
                 self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
-                call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
-                     ptr(self.pool_idx), stream())
+                if self.pooling == "avg":
+                    call("pm_avgpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]), stream())
+                else:
+                    call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
+                         ptr(self.pool_idx), stream())
             xin = self.act["p1"]
             for pre, ca, cb, ds in self.blocks:
                 ia, ib = bn_ids[pre + ".bn1"], bn_ids[pre + ".bn2"]
@@ -515,6 +538,10 @@ class ResNet18Engine:
                      ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
                      ptr(self._stat_slot(len(self.bns) + bn_ids["bn1"])), ptr(dc1), ptr(self.g["bn1.weight"]),
                      ptr(self.g["bn1.bias"]), stream())
+            elif self.pooling == "avg":
+                d_a1 = self._gbuf(("da1",), self.act["a1"])
+                call("pm_avgpool3s2_bwd" + self.sfx, ptr(d_out), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
+                self._bn_bwd("bn1", bn_ids["bn1"], d_a1, self.act["a1"], self.act["conv1"], dc1, c1.P)
             elif self.fuse_bn_bwd:
                 # max-pool backward is gathered inside the stem's BN backward (no full-resolution gradient round trip)
                 call("pm_bn_bwd_fused_pool" + self.sfx, ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["a1"]),
@@ -580,13 +607,21 @@ class ResNet18Engine:
         """utils.py:1168-1174: zero_grad; pred = model(data); loss; backward; step.
         Replays the captured CUDA graph when one exists for this (optimizer step index, target kind)."""
         gr = self._graph
-        if gr is not None and gr["step"] == self.step_count + 1 and gr["tdtype"] == target.dtype:
+        if (gr is not None and gr["step"] == self.step_count + 1 and gr["tdtype"] == target.dtype
+                and gr["hyper"] == self._hyper_key()):
             gr["x"].copy_(x_nchw, non_blocking=True)
             gr["y"].copy_(target, non_blocking=True)
             gr["graph"].replay()
             self.step_count += 1
             return self.loss
         return self._train_step_eager(x_nchw, target)
+
+    def _hyper_key(self):
+        """everything a captured step bakes into kernel arguments besides the Adam step index: a replay is legal only while
+        none of it changed (train.py:433-440 adjusts lr per epoch; class weights / eval mode switch kernels)"""
+        cw = None if self.class_weights is None else self.class_weights.data_ptr()
+        return (self.opt_name, float(self.lr), tuple(float(b) for b in self.betas), float(self.wd), float(self.opt_eps), cw,
+                bool(self.training))
 
     def capture_graph(self, x_nchw, target):
         """Capture one local step (all ~190 kernel launches) in a CUDA graph.  Adam's bias correction bakes the step
@@ -610,7 +645,8 @@ class ResNet18Engine:
                 self._train_step_eager(gx, gy)
             launches = _lib.launch_counter - n0 + 1  # + stats.zero_()
             self.step_count = snap[3]
-            self._graph = {"graph": graph, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype, "launches": launches}
+            self._graph = {"graph": graph, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype, "launches": launches,
+                           "hyper": self._hyper_key()}
         return launches
 
     def profile_conv_time(self, x_nchw, target, steps=2):

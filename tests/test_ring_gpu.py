@@ -162,6 +162,20 @@ def test_conv2d_full_size_layer1(ring):
     _shared_conv_case(ring, g, 1, 64, 56, 64, 3, 1, 1, 10, 16)
 
 
+FULL_SIZE_SHAPES = [  # BASELINE config C4: every distinct conv geometry of ResNet-18 on ONE 224x224 image, at full size
+    (3, 224, 64, 7, 2, 3), (64, 56, 64, 3, 1, 1), (64, 56, 128, 3, 2, 1), (64, 56, 128, 1, 2, 0), (128, 28, 128, 3, 1, 1),
+    (128, 28, 256, 3, 2, 1), (128, 28, 256, 1, 2, 0), (256, 14, 256, 3, 1, 1), (256, 14, 512, 3, 2, 1), (256, 14, 512, 1, 2, 0),
+    (512, 7, 512, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("shape", FULL_SIZE_SHAPES, ids=lambda s: "C%d_H%d_K%d_k%d_s%d" % s[:5])
+def test_conv2d_on_shares_full_size_geometries_pf16(ring, shape):
+    """the Beaver conv at the sizes encrypted inference of a 224x224 image runs (M up to 12544, K up to 4608), pf = 16"""
+    g = torch.Generator().manual_seed(1000 + shape[0] + shape[1])
+    _shared_conv_case(ring, g, 1, *shape, 10, 16)
+
+
 def test_provider_generated_triples_reconstruct_true_product(ring):
     """full-size property: with provider-made triples, reconstruct(z0+z1) == im2col(x) @ w^T mod 2^64."""
     g = torch.Generator().manual_seed(9)

@@ -2,9 +2,12 @@
 """train.py -- entry point with the reference's CLI (train.py:555-631): ``python train.py --config <ini> --train_federated``.
 
 Flow mirrors train.py:54-552 + torchlib/utils.py:516-856 (setup_pysyft), :936 (train_federated), :1108
-(secure_aggregation_epoch), :1354 (test), :1470 (save_model), with every hospital (VirtualWorker) pinned to one GPU and
-all arithmetic in the primia_b200 C ABI.  Data are synthetic 224x224x3 tensors (``--data_dir`` is accepted for CLI
-compatibility; image I/O / albumentations are out of scope).
+(secure_aggregation_epoch), :1470 (save_model): roster from ``configs/websetting/config.csv`` (the reference's file works as
+is), one ``sy.VirtualWorker`` per hospital pinned to one GPU, ``model.copy().send(worker)`` per hospital, per-worker
+optimizers, log-linear learning-rate schedule, FedAvg (plain or secure) every ``sync_every_n_batch`` batches, checkpoints in
+the reference's format (``--resume_checkpoint`` continues from one).  All arithmetic is the primia_b200 C ABI.  Data are
+synthetic 224x224x3 tensors (``--data_dir`` is accepted for CLI compatibility; image I/O / albumentations are out of scope,
+SURVEY.md section 2 #4).
 Multi-GPU: launch with ``python -m torch.distributed.run --nproc-per-node N train.py ...``: rank i hosts hospital i and
 FedAvg is an NCCL all-reduce; in a single process the hospitals time-share the visible GPU(s) round-robin.
 """
@@ -12,66 +15,45 @@ from __future__ import annotations
 
 import argparse
 import configparser
-import csv
+import math
 import os
 import sys
 import time
+import zlib
 
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-
-class Arguments:
-    """subset of torchlib/utils.py:92-302 that the federated path reads (ini -> attributes)"""
-
-    def __init__(self, cmd_args, config):
-        c, f = config["config"], config["federated"] if "federated" in config else {}
-        self.batch_size = c.getint("batch_size", 64)
-        self.train_resolution = c.getint("train_resolution", 224)
-        self.test_batch_size = c.getint("test_batch_size", 64)
-        self.test_interval = c.getint("test_interval", 1)
-        self.epochs = c.getint("epochs", 1)
-        self.lr = c.getfloat("lr", 1e-4)
-        self.end_lr = c.getfloat("end_lr", self.lr)
-        self.beta1, self.beta2 = c.getfloat("beta1", 0.5), c.getfloat("beta2", 0.99)
-        self.weight_decay = c.getfloat("weight_decay", 5e-4)
-        self.seed = c.getint("seed", 42)
-        self.optimizer = c.get("optimizer", "Adam")
-        self.model = c.get("model", "resnet-18")
-        self.pooling_type = c.get("pooling_type", "max")
-        self.sync_every_n_batch = int(f.get("sync_every_n_batch", 1))
-        self.keep_optim_dict = str(f.get("keep_optim_dict", "no")).lower() in ("yes", "true", "1")
-        self.weighted_averaging = str(f.get("weighted_averaging", "no")).lower() in ("yes", "true", "1")
-        self.precision_fractional = int(f.get("precision_fractional", 16))
-        self.unencrypted_aggregation = cmd_args.unencrypted_aggregation or str(f.get("unencrypted_aggregation", "yes")).lower() in ("yes", "true", "1")
-        self.train_federated = cmd_args.train_federated
-        self.mode = cmd_args.mode
-        self.batches_per_worker = cmd_args.batches_per_worker
-        self.num_classes = 3
-        self.in_channels = 3
+from torchlib.run_websocket_server import read_websocket_config  # noqa: E402
+from torchlib.utils import (Arguments, LearningRateScheduler, MixUp, load_checkpoint, load_optimizer_state_dict,  # noqa: E402
+                            save_model)
 
 
-def read_websocket_config(path):
-    """torchlib/run_websocket_server.py:6-8: worker roster = rows of the CSV"""
-    with open(path) as fh:
-        return [row["id"] for row in csv.DictReader(fh)]
+def stable_seed(base: int, name: str) -> int:
+    """per-hospital data seed: reproducible across processes (python's hash() is salted per interpreter)"""
+    return base + zlib.crc32(name.encode()) % 1000
 
 
-def lr_at(args, epoch):
-    """log-linear schedule lr -> end_lr over the epochs (torchlib/utils.py:37-89, no restarts)"""
-    if args.epochs <= 1:
-        return args.lr
-    import math
+def global_batch_counts(local_counts: dict, group):
+    """{hospital: number of batches} over ALL ranks (utils.py:953-957 needs the global denominator for weighted averaging)"""
+    if group is None:
+        return dict(local_counts)
+    import torch.distributed as dist
 
-    t = (epoch - 1) / (args.epochs - 1)
-    return math.exp(math.log(args.lr) + t * (math.log(args.end_lr) - math.log(args.lr)))
+    gathered = [None] * dist.get_world_size(group)
+    dist.all_gather_object(gathered, local_counts, group=group)
+    out = {}
+    for d in gathered:
+        out.update(d)
+    return out
 
 
 def main(argv=None):
     import primia_b200.sy as sy
-    from primia_b200.train import HospitalWorker, ResNet18Engine, aggregation, federated_round
+    from primia_b200.models import resnet18
+    from primia_b200.train import HospitalWorker, federated_round
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default=os.path.join(ROOT, "configs/torch/pneumonia-resnet-synthetic.ini"))
@@ -79,19 +61,26 @@ def main(argv=None):
     ap.add_argument("--unencrypted_aggregation", action="store_true")
     ap.add_argument("--data_dir", default=None, help="accepted for CLI compatibility; synthetic tensors are used")
     ap.add_argument("--websockets_config", default=os.path.join(ROOT, "configs/websetting/config.csv"))
+    ap.add_argument("--websockets", action="store_true", help="network workers are out of scope: refused")
     ap.add_argument("--cuda", action="store_true", help="accepted; the GPU is the only device")
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--resume_checkpoint", default=None, help="continue from a checkpoint in the reference's format")
+    ap.add_argument("--training_name", default=None)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "f32", "f32x3"])
     ap.add_argument("--batches_per_worker", type=int, default=4)
     ap.add_argument("--save_dir", default="model_weights")
     cmd = ap.parse_args(argv)
     config = configparser.ConfigParser()
     assert os.path.isfile(cmd.config), "config file not found"
     config.read(cmd.config)
-    args = Arguments(cmd, config)
+    args = Arguments(cmd, config, mode="train")
+    if cmd.websockets:
+        raise SystemExit("websocket / PyGrid workers are out of scope (SURVEY.md section 2): use VirtualWorkers")
     if not args.train_federated:
         raise SystemExit("only the federated path (--train_federated) is built: it is the hot path (BASELINE.json north_star)")
     if args.model != "resnet-18":
         raise NotImplementedError("model unknown / out of scope: " + args.model)
+    if cmd.unencrypted_aggregation is False and config.has_option("federated", "unencrypted_aggregation"):
+        args.unencrypted_aggregation = config.getboolean("federated", "unencrypted_aggregation")
 
     import torch.distributed as dist
 
@@ -101,67 +90,122 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
         group = dist.group.WORLD
+    if args.deterministic:
+        torch.manual_seed(args.seed)
     hook = sy.TorchHook(torch)
-    names = read_websocket_config(cmd.websockets_config)
-    if world > 1:
-        names = [names[rank % len(names)] + (str(rank) if rank >= len(names) else "")]
-    workers = {n: sy.VirtualWorker(hook, id=n, device=f"cuda:{torch.cuda.current_device()}" if world > 1 else None) for n in names}
-    crypto_provider = sy.VirtualWorker(hook, id="crypto_provider")  # noqa: F841 (utils.py:603)
+    # ---- setup_pysyft (utils.py:516-603): roster, crypto provider, VirtualWorkers
+    worker_dict = read_websocket_config(cmd.websockets_config)
+    worker_names = [d["id"] for _, d in worker_dict.items()]
+    crypto_in_config = "crypto_provider" in worker_names
+    assert args.unencrypted_aggregation or crypto_in_config, "No crypto provider in configuration"
+    if crypto_in_config:
+        worker_names.remove("crypto_provider")
+    if world > 1:  # one hospital per rank; extra ranks get numbered names
+        worker_names = [worker_names[rank % len(worker_names)] + (str(rank) if rank >= len(worker_names) else "")]
+    dev_of = (lambda i: f"cuda:{torch.cuda.current_device()}") if world > 1 else (lambda i: None)
+    workers = {n: sy.VirtualWorker(hook, id=n, verbose=False, device=dev_of(i)) for i, n in enumerate(worker_names)}
+    for w in workers.values():
+        w.object_store.clear_objects()
+    crypto_provider = None
+    if not args.unencrypted_aggregation:
+        crypto_provider = sy.VirtualWorker(hook, id="crypto_provider", verbose=False)  # noqa: F841 (utils.py:598-601)
 
-    # synthetic per-hospital data, tagged and "sent" to the owner like utils.py:643-742
+    # ---- synthetic per-hospital data, tagged and sent to the owner like utils.py:643-742
     B, S = args.batch_size, args.train_resolution
-    loaders = {}
+    num_classes = 3
+    one_hot = args.mixup or args.weight_classes          # utils.py:671 / train.py:336: soft targets -> Cross_entropy_one_hot
     for n, w in workers.items():
-        g = torch.Generator().manual_seed(args.seed + hash(n) % 1000)
-        n_img = B * args.batches_per_worker
+        g = torch.Generator().manual_seed(stable_seed(args.seed, n))
+        n_img = B * cmd.batches_per_worker
         data = torch.randn(n_img, 3, S, S, generator=g).tag("#traindata")
-        target = torch.randint(0, 3, (n_img,), generator=g).tag("#traintargets")
+        target = torch.randint(0, num_classes, (n_img,), generator=g)
+        if one_hot:
+            target = torch.nn.functional.one_hot(target, num_classes).float()
+        target = target.tag("#traintargets")
         w.load_data([data.send(w).get(), target.send(w).get()])
     grid = sy.PrivateGridNetwork(*workers.values())
     data_ptrs, target_ptrs = grid.search("#traindata"), grid.search("#traintargets")
-    for n, w in workers.items():
+    loaders = {}
+    for n in workers:
         ds = sy.BaseDataset(data_ptrs[n][0], target_ptrs[n][0])
         loaders[n] = sy.FederatedDataLoader(sy.FederatedDataset([ds]), batch_size=B, shuffle=True, seed=args.seed)
 
-    # one model + optimizer per hospital (train.py:271-303), all starting from the same local_model
+    # ---- one model + optimizer per hospital (train.py:262-303), all starting from the same local_model
+    model = resnet18(pretrained=False, num_classes=num_classes, in_channels=3, adptpool=False, input_size=S,
+                     pooling=args.pooling_type)
+    model = {w: model.copy().send(workers[w]) for w in worker_names} | {"local_model": model}
+    opt_kw = dict(optimizer=args.optimizer, lr=args.lr, weight_decay=args.weight_decay)
+    if args.optimizer == "Adam":
+        opt_kw["betas"] = (args.beta1, args.beta2)
+    class_weights = None
+    if args.weight_classes:  # calc_class_weights (utils.py:470-513): inverse class frequency over all hospitals' targets
+        counts = sum(t.get().sum(0) for ts in target_ptrs.values() for t in ts)
+        if group is not None:
+            dist.all_reduce(counts, group=group)
+        class_weights = (1.0 / counts.clamp_min(1)).float()
+        class_weights = class_weights / class_weights.sum()
     hospitals = []
-    for n, w in workers.items():
-        eng = ResNet18Engine(B, args.num_classes, args.in_channels, S, args.pooling_type, str(w.device), args.mode,
-                             optimizer=args.optimizer, lr=args.lr, betas=(args.beta1, args.beta2), weight_decay=args.weight_decay)
-        eng.init_random(seed=args.seed)
+    for n in worker_names:
+        eng = model[n].engine_for(B if not (args.mixup and args.mixup_prob == 1.0) else B // 2, workers[n].device, cmd.mode,
+                                  class_weights=class_weights, **opt_kw)
         hospitals.append(HospitalWorker(n, eng))
+    optimizer = {h.id: h.engine for h in hospitals}  # the engine owns the optimizer state (Adam moments, step count)
 
-    total_batches = sum(len(l) for l in loaders.values())
-    weights = {n: len(l) / total_batches for n, l in loaders.items()} if args.weighted_averaging else None
-    for epoch in range(1, args.epochs + 1):
-        lr = lr_at(args, epoch)
+    start_at_epoch = 1
+    if cmd.resume_checkpoint:  # train.py:344-389
+        print("Resume training from a given checkpoint.")
+        state = load_checkpoint(cmd.resume_checkpoint)
+        start_at_epoch = state["epoch"]
+        ck_args = state["args"]
+        opt_sd = state["optim_state_dict"]
+        if getattr(ck_args, "train_federated", False):
+            for w in worker_names:
+                if w not in opt_sd:
+                    raise SystemExit("The worker names of the checkpoint and the current configuration cannot be matched.")
+                load_optimizer_state_dict(optimizer[w], opt_sd[w])
+        else:
+            assert len(opt_sd) == 2 and "param_groups" in opt_sd and "state" in opt_sd  # non-federated checkpoint
+            for w in worker_names:
+                load_optimizer_state_dict(optimizer[w], opt_sd)
+        for key in model:
+            model[key].load_state_dict(state["model_state_dict"])
         for h in hospitals:
-            h.engine.lr = lr  # scheduler.adjust_learning_rate per worker, train.py:433-440
-            h.batches = [(d.get(), t.get()) for d, t in loaders[h.id]]
+            h.engine.load_state_dict(state["model_state_dict"])
+
+    scheduler = LearningRateScheduler(args.epochs, math.log10(args.lr), math.log10(args.end_lr), restarts=args.restarts)
+    mixup = MixUp(λ=args.mixup_lambda, p=args.mixup_prob) if args.mixup else None
+    counts = global_batch_counts({n: len(l) for n, l in loaders.items()}, group)
+    total_batches = sum(counts.values())
+    weights = {n: c / total_batches for n, c in counts.items()} if args.weighted_averaging else None  # utils.py:953-957
+    last_path = None
+    for epoch in range(start_at_epoch, args.epochs + 1):
+        for h in hospitals:
+            new_lr = scheduler.adjust_learning_rate(h.engine, epoch - 1)  # train.py:433-440
+            h.batches = []
+            for d, t in loaders[h.id]:
+                d, t = d.get(), t.get()
+                if mixup is not None:
+                    d, t = mixup((d, t))
+                if d.shape[0] == h.engine.B:  # the engine's buffers are sized for full batches; a ragged tail is dropped
+                    h.batches.append((d.contiguous(), t.contiguous()))
         t0 = time.time()
         loss = federated_round(hospitals, args.sync_every_n_batch, weights, args.keep_optim_dict, group,
-                               secure=not args.unencrypted_aggregation, precision_fractional=args.precision_fractional)
+                               secure=not args.unencrypted_aggregation, precision_fractional=int(args.precision_fractional),
+                               opt_lr=None if args.keep_optim_dict else args.lr)
         torch.cuda.synchronize()
         dt = time.time() - t0
-        n_img = sum(len(h.batches) for h in hospitals) * B * world
+        n_img = sum(len(h.batches) * h.engine.B for h in hospitals) * world
         if rank == 0:
-            print("Train Epoch: {} \tLoss: {:.6f}\t({:.0f} images/s)".format(epoch, loss.item(), n_img / dt))
-    if rank == 0:
-        save_model(hospitals[0].engine, args, cmd.save_dir, args.epochs)
+            print("Train Epoch: {} \tLoss: {:.6f}\tlr {:.2e}\t({:.0f} images/s)".format(epoch, loss.item(), new_lr, n_img / dt))
+        model["local_model"].load_state_dict(hospitals[0].engine.state_dict())  # every hospital holds the aggregate
+        if rank == 0 and (epoch % args.test_interval == 0 or epoch == args.epochs):
+            last_path = os.path.join(cmd.save_dir, f"federated_resnet18_epoch_{epoch:03d}.pt")
+            save_model(model, optimizer, last_path, args, epoch, torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]]))
+            print("saved", last_path)
     if world > 1:
         dist.destroy_process_group()
+    main.last_checkpoint = last_path
     return hospitals
-
-
-def save_model(engine, args, save_dir, epoch):
-    """torchlib/utils.py:1470-1493 checkpoint contract (consumed by inference.py:82-93,277)"""
-    os.makedirs(save_dir, exist_ok=True)
-    path = os.path.join(save_dir, f"federated_resnet18_epoch_{epoch:03d}.pt")
-    sd = {k: v.cpu() for k, v in engine.state_dict().items()}
-    torch.save({"epoch": epoch, "model_state_dict": sd, "optim_state_dict": {}, "args": vars(args),
-                "val_mean_std": torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]])}, path)
-    print("saved", path)
-    return path
 
 
 if __name__ == "__main__":
