@@ -69,6 +69,10 @@ def test_graph_replay_equals_eager_step(B, size):
     for i, (x, y) in enumerate(batches):
         for eng in (eager, graph):
             eng.reset_optimizer()  # the reference re-creates the optimizer after every aggregation (utils.py:1209-1218)
+        # every step is compared from IDENTICAL weights: the 1e-7 split-K atomics noise of the previous step's gradients would
+        # otherwise flip a few bf16 weight roundings and show up as ~1e-5 in the next loss (measured), which is not a property
+        # of graph replay
+        graph.flat.copy_(eager.flat)
         le = eager._train_step_eager(x.to(DEV), y.to(DEV)).item()
         lg = graph.train_step(x.to(DEV), y.to(DEV)).item()   # replay: step index and target dtype match the capture
         torch.cuda.synchronize()
@@ -116,6 +120,7 @@ def test_local_step_host_equals_local_step():
     for i, (x, y) in enumerate(batches):
         for w in (dev_w, host_w):
             w.engine.reset_optimizer()
+        host_w.engine.flat.copy_(dev_w.engine.flat)   # compare each step from identical weights (see above)
         ld = dev_w.local_step(x.to(DEV), y.to(DEV)).item()
         lh = host_w.local_step_host(*pinned[i])
         if i + 1 < len(batches):
