@@ -177,85 +177,135 @@ def cpu_baseline_sample(seconds_cap=25.0):
             "sample": f"{n} local steps of {Bs} images (fwd+bwd+Adam) with the torch-CPU fp32 oracle, {torch.get_num_threads()} threads"}
 
 
-def encrypted_cpu_sample(size=32, pf=16):
-    """CPU arm of path E on a bounded sample: the oracle restatement of inference.py:279-321 (torch-CPU int64 + hashlib
-    SHA-512, single thread like the reference's B=1 path) on one ``size`` x ``size`` image."""
+def encrypted_cpu_sample(size=224, pf=16):
+    """CPU arm of path E: the oracle restatement of inference.py:279-321 on ONE full-size image -- torch-CPU int64 Beaver convs,
+    the 80-step Newton BatchNorms, and the FSS comparisons through the oracle's C twin (SHA-512, OpenMP over the host cores;
+    the reference's own path is single-threaded at B = 1: spdz.py:95-107 leaves one non-empty slice).  Primitive generation
+    (offline) is timed separately from the online protocol."""
     import torch
 
+    from oracle import fss_oracle_c
     from oracle import ring_oracle as R
     from oracle import train_oracle as O
 
-    torch.manual_seed(42)
-    model = O.ResNet18(input_size=size).eval()
-    tape = R.GeneratingTape(1, 21 * 10 ** pf)
-    sh = lambda q: [(s0 := tape._r(q.shape)), q - s0]
-    P = {k: sh(R.encode(v.float().contiguous(), 10, pf)) for k, v in model.state_dict().items() if not k.endswith("num_batches_tracked")}
-    x = sh(R.encode(torch.randn(1, 3, size, size) * 0.1, 10, pf))
-    t0 = time.perf_counter()
-    R.resnet18_forward_shared(P, x, tape, 10, pf, size)
-    total = time.perf_counter() - t0
+    R.FSS = fss_oracle_c
+    try:
+        torch.manual_seed(42)
+        model = O.ResNet18(input_size=size).eval()
+        tape = R.GeneratingTape(1, 21 * 10 ** pf)
+        sh = lambda q: [(s0 := tape._r(q.shape)), q - s0]
+        P = {k: sh(R.encode(v.float().contiguous(), 10, pf)) for k, v in model.state_dict().items() if not k.endswith("num_batches_tracked")}
+        x = sh(R.encode(torch.randn(1, 3, size, size) * 0.1, 10, pf))
+        t0 = time.perf_counter()
+        R.resnet18_forward_shared(P, x, tape, 10, pf, size)
+        total = time.perf_counter() - t0
+    finally:
+        R.FSS = None
     return {"online_ms": (total - tape.gen_seconds) * 1e3, "offline_ms": tape.gen_seconds * 1e3, "comparisons": tape.n_fss,
             "beaver_products": tape.n_triples}
 
 
-def encrypted_inference_block(steps=3, cpu=True):
+CMP_PER_IMAGE = 64 * 56 * 56 * 8 + 64 * 56 * 56 + 4 * 64 * 56 * 56 + 4 * 128 * 28 * 28 + 4 * 256 * 14 * 14 + 4 * 512 * 7 * 7   # 3 311 616
+INT64_MAC_PER_IMAGE = 1.81356288e9      # forward MACs of the 20 convs + fc (SURVEY.md section 8d)
+FSS_INSTR_PER_HASH = 3728               # SASS instructions pm_fss_dif_eval executes per SHA-512 (profiles/README.md)
+ALU_WARP_INSTR_PER_CLK_SM = 1.94        # measured issue rate of the integer ALU pipe (scripts/ubench/int_pipes.cu)
+
+
+def fss_roofline(dev, sm_mhz=1965.0):
+    """the dominant kernel of path E timed alone: pm_fss_dif_eval on the largest layer's instance count (64 x 112 x 112)"""
+    import torch
+
+    from primia_b200 import ring
+
+    n = 64 * 112 * 112
+    keys = ring.fss.build_fss_keys(n, dev, 1, 1)
+    x = ring.ops.random_i64((n,), 2, 2, dev)
+    win = keys[0].window(n)
+    with torch.cuda.device(dev):
+        for _ in range(2):
+            ring.fss.dif_eval(0, x, win)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 5
+        for _ in range(reps):
+            ring.fss.dif_eval(0, x, win)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    achieved = 32 * n / ms / 1e6                                                       # G SHA-512 / s
+    peak = ALU_WARP_INSTR_PER_CLK_SM * 32 * 148 * sm_mhz * 1e6 / FSS_INSTR_PER_HASH / 1e9
+    key_bytes = sum(t.numel() * t.element_size() for t in keys[0].tensors()) + 16 * n
+    return {"bound": "int-alu", "kernel": "fss::fss_dif_eval_kernel (DIF.eval: 32 SHA-512 compressions per comparison; thread = instance)",
+            "achieved": achieved, "peak": peak, "unit": "G SHA-512/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic": f"32 hashes x {n} comparisons per launch = {32 * n / 1e6:.1f} M hashes, {FSS_INSTR_PER_HASH} integer instructions each",
+            "launch_ms": ms, "hbm_GBps": key_bytes / ms / 1e6,
+            "peak_source": "integer-ALU issue bound: 1.94 warp-instr/clk/SM measured by scripts/ubench/int_pipes.cu x 32 lanes x 148 SMs "
+                           f"x {sm_mhz:.0f} MHz / {FSS_INSTR_PER_HASH} instr per hash (IADD3 partly dual-issues on the FMA pipe, so slightly "
+                           "above 1.0 is possible); neither the HBM nor the tensor roofline applies: keys are 1.2 KB per comparison read once"}
+
+
+def encrypted_inference_block(steps=3, devs=None, label=None):
     """Path E beside the headline: the reference's encrypted inference of ONE image (inference.py:292-317) end to end on
     shares -- 20 convs + fc (Beaver matmuls on the int8 tensor cores), 20 BatchNorms (80-step Newton inverse sqrt), 17 ReLUs
-    and the 3x3 max-pool (FSS comparisons: 32 SHA-512 per element per party), avg-pool -- with the two share holders and the
-    crypto provider time-sharing this GPU.  Offline (triples + FSS keys) and online phases are timed separately."""
+    and the 3x3 max-pool (FSS comparisons: 32 SHA-512 per element per party), avg-pool.  ``devs`` = (model_owner, data_owner,
+    crypto_provider) devices: all on one GPU, or the SURVEY.md section 8e placement on three GPUs (openings = peer reads over
+    NVLink, one multi-device CUDA graph).  Offline (triples + FSS keys) and online phases are timed separately."""
     import torch
     import torchvision
 
     from primia_b200 import _lib, ring
-    from primia_b200.ring.resnet import EncryptedInferenceGraph, EncryptedLinearGraph, SharedLinearLayers
+    from primia_b200.ring.resnet import EncryptedInferenceGraph
+
+    cur = "cuda:%d" % torch.cuda.current_device()
+    devs = devs or [cur, cur, cur]
+    dev = devs[0]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    sync = lambda: [torch.cuda.synchronize(d) for d in set(devs)]
+    parties = [ring.Party("model_owner", devs[0]), ring.Party("data_owner", devs[1])]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", devs[2]), seed=42)
+    torch.manual_seed(42)
+    sd = torchvision.models.resnet18(num_classes=3).state_dict()   # key-compatible with torchlib/models.py resnet18
+    net = ring.EncryptedResNet18.from_state_dict(sd, parties, prov, 10, 16, input_size=224)
+    himg = (torch.randn(1, 3, 224, 224) * 0.1).pin_memory()
+    eg = EncryptedInferenceGraph(net, himg)                         # warm-up, primitive schedule, capture of the online phase
+    off, on = [], []
+    hout = torch.zeros(1, 3).pin_memory()
+    with torch.cuda.device(dev):
+        for it in range(steps + 2):
+            sync()
+            e = [ev() for _ in range(3)]
+            e[0].record()
+            eg.offline()                                            # fresh triples + FSS keys into the static buffers
+            for d in set(devs) - {dev}:
+                torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
+            e[1].record()
+            out, _pred = eg.online(himg.to(dev, non_blocking=True)) # H2D image, encode+share, graph replay (forward, reconstruct, decode)
+            hout.copy_(out)                                         # D2H logits
+            e[2].record()
+            sync()
+            if it >= 2:                                             # two warm-up images (allocator growth)
+                off.append(e[0].elapsed_time(e[1]))
+                on.append(e[1].elapsed_time(e[2]))
+    gb = prov.generated_bytes / (steps + 4) / 1e9
+    launches = eg.kernels_in_graph
+    del eg, net, parties, prov
+    torch.cuda.empty_cache()
+    on_ms, off_ms = sum(on) / len(on), sum(off) / len(off)
+    n_gpus = len(set(devs))
+    return {"placement": label or f"{n_gpus} GPU", "devices": devs, "online_ms": on_ms, "offline_ms": off_ms, "gpu_launches": launches,
+            "primitives_GB_per_image": gb}
+
+
+def linear_layers_block(steps=3):
+    """the 21 linear layers alone (the Beaver matmuls named in north_star) on synthetic activation shares, as one CUDA graph"""
+    import torch
+
+    from primia_b200 import ring
+    from primia_b200.ring.resnet import EncryptedLinearGraph, SharedLinearLayers
 
     dev = "cuda:%d" % torch.cuda.current_device()
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def full_forward(size, reps):
-        parties = [ring.Party("model_owner", dev), ring.Party("data_owner", dev)]
-        prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", dev), seed=42)
-        torch.manual_seed(42)
-        sd = torchvision.models.resnet18(num_classes=3).state_dict()   # key-compatible with torchlib/models.py resnet18
-        net = ring.EncryptedResNet18.from_state_dict(sd, parties, prov, 10, 16, input_size=size)
-        himg = (torch.randn(1, 3, size, size) * 0.1).pin_memory()
-        eg = EncryptedInferenceGraph(net, himg)                         # warm-up, primitive schedule, capture of the online phase
-        off, on, launches = [], [], 0
-        hout = torch.zeros(1, 3).pin_memory()
-        for it in range(reps + 2):
-            torch.cuda.synchronize()
-            e = [ev() for _ in range(3)]
-            e[0].record()
-            eg.offline()                                                # fresh triples + FSS keys into the static buffers
-            e[1].record()
-            l0 = _lib.launch_counter
-            out, _pred = eg.online(himg.to(dev, non_blocking=True))     # H2D image, encode+share, graph replay (forward, reconstruct, decode)
-            hout.copy_(out)                                             # D2H logits
-            e[2].record()
-            torch.cuda.synchronize()
-            if it >= 2:                                                 # two warm-up images (allocator growth)
-                off.append(e[0].elapsed_time(e[1]))
-                on.append(e[1].elapsed_time(e[2]))
-        launches = eg.kernels_in_graph
-        gb = prov.generated_bytes / (reps + 4) / 1e9
-        del eg, net, parties, prov
-        torch.cuda.empty_cache()
-        return sum(on) / len(on), sum(off) / len(off), launches, gb
-
-    on_ms, off_ms, launches, gb = full_forward(224, steps)
-    out = {"metric": "encrypted_inference_ms_per_image", "value": on_ms, "unit": "ms/image", "higher_is_better": False,
-           "dtype": "int64", "online_ms": on_ms, "offline_ms": off_ms, "gpu_launches": launches,
-           "primitives_GB_per_image": gb,
-           "e2e": {"value": on_ms, "unit": "ms/image", "h2d_bytes_per_step": 3 * 224 * 224 * 4, "d2h_bytes_per_step": 12,
-                   "note": "host image -> H2D -> encode+share -> forward on shares -> reconstruct -> decode -> D2H logits"},
-           "config": {"workload": "C4: SPDZ 2-party + crypto provider ResNet-18, base 10 pf 16 int64 ring, one 224x224x3 image, "
-                                  "protocol fss, parties time-sharing one GPU, online phase = one CUDA-graph replay"}}
-    # FSS evaluation is the dominant kernel: integer-ALU bound (no memory or tensor roofline applies)
-    cmp_per_image = 64 * 56 * 56 * 8 + 64 * 56 * 56 + 4 * 64 * 56 * 56 + 4 * 128 * 28 * 28 + 4 * 256 * 14 * 14 + 4 * 512 * 7 * 7
-    out["fss"] = {"comparisons_per_image": cmp_per_image, "sha512_per_image_online": cmp_per_image * 64,
-                  "note": "pm_fss_dif_eval: 32 SHA-512 compressions per comparison per party; measured 5.08 G hash/s = ~96% of the "
-                          "integer ALU-pipe issue rate for this instruction mix (profiles/README.md)"}
-    # the linear layers alone (the Beaver matmuls named in north_star), online phase replayed as one CUDA graph
     parties = [ring.Party("model_owner", dev), ring.Party("data_owner", dev)]
     prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", dev), seed=42)
     lin = SharedLinearLayers(parties, prov, 10, 16)
@@ -276,19 +326,63 @@ def encrypted_inference_block(steps=3, cpu=True):
             offl.append(e[0].elapsed_time(e[1]))
             onl.append(e[2].elapsed_time(e[3]))
     lon = sum(onl) / len(onl)
-    out["linear_layers"] = {"online_ms": lon, "offline_triple_gen_ms": sum(offl) / len(offl),
-                            "int64_gmac_per_s_per_party": 2 * 1.81356288e9 / (lon * 1e-3) / 1e9,
-                            "scope": "20 convs + fc Beaver protocol only (mask, open, combine on the int8 tensor cores, truncate), CUDA graph",
-                            "triple_bytes_per_party": 226733592}
+    tri_bytes = 226733592
+    pk = peaks()
+    # per party and image: 2 GEMMs (delta@(b+eps) and a@eps fused as [delta|a]@[b+eps;eps]) = 2 x 1.81 G int64-MAC = 72 x that in
+    # int8 MACs (36 limb pairs); bytes: triples read + delta/eps written, exchanged and read back ~ 3 x 227 MB per party
+    int8_tops = 2 * 2 * INT64_MAC_PER_IMAGE * 36 * 2 / (lon * 1e-3) / 1e12
+    hbm = 2 * 3 * tri_bytes / (lon * 1e-3) / 1e9
+    return {"online_ms": lon, "offline_triple_gen_ms": sum(offl) / len(offl),
+            "int64_gmac_per_s_per_party": 2 * INT64_MAC_PER_IMAGE / (lon * 1e-3) / 1e9,
+            "scope": "20 convs + fc Beaver protocol only (mask, open, combine on the int8 tensor cores, truncate), CUDA graph",
+            "triple_bytes_per_party": tri_bytes,
+            "roofline": {"bound": "hbm", "kernel": "ring_i8::ring_gemm_i8_kernel + mask / planarize / open / truncate kernels (~330 launches)",
+                         "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm / pk["hbm_gbs"], "traffic": None,
+                         "algorithmic": "per party: 226.7 MB of triples read + 206.9 MB of masked operands written and opened + outputs ~ 3 x "
+                                        "226.7 MB; both parties on this GPU",
+                         "int8_tensor": {"achieved_TOPs": int8_tops, "peak_TOPs": 2 * pk["bf16_tflops"],
+                                         "frac": int8_tops / (2 * pk["bf16_tflops"]),
+                                         "note": "36 u8 x u8 limb-pair products per int64 MAC, 2 ops per MAC; int8 dense peak taken as 2 x the "
+                                                 "measured bf16 peak"}}}
+
+
+def encrypted_inference_report(steps=3, cpu=True, enc_gpus=None):
+    """the ``encrypted_inference`` object of the bench line: placements, rooflines, CPU baseline at the same 224 x 224 size"""
+    import torch
+
+    cur = torch.cuda.current_device()
+    placements = [encrypted_inference_block(steps, None, "1 GPU: both parties and the crypto provider time-share it")]
+    want3 = (enc_gpus or 0) >= 3 or (enc_gpus is None and torch.cuda.device_count() >= 3)
+    if want3 and torch.cuda.device_count() >= 3:
+        trio = [f"cuda:{(cur + i) % torch.cuda.device_count()}" for i in range(3)]
+        try:
+            placements.append(encrypted_inference_block(steps, trio, "3 GPUs: model_owner / data_owner / crypto_provider, openings over "
+                                                                     "NVLink peer reads, one multi-device CUDA graph"))
+        except Exception as exc:
+            placements.append({"placement": "3 GPUs", "error": repr(exc)})
+    best = min((p for p in placements if "online_ms" in p), key=lambda p: p["online_ms"])
+    one = placements[0]
+    out = {"metric": "encrypted_inference_ms_per_image", "value": best["online_ms"], "unit": "ms/image", "higher_is_better": False,
+           "dtype": "int64", "online_ms": best["online_ms"], "offline_ms": best["offline_ms"], "gpu_launches": best["gpu_launches"],
+           "n_gpus": len(set(best["devices"])), "placements": placements,
+           "primitives_GB_per_image": one["primitives_GB_per_image"],
+           "e2e": {"value": best["online_ms"], "unit": "ms/image", "h2d_bytes_per_step": 3 * 224 * 224 * 4, "d2h_bytes_per_step": 12,
+                   "note": "host image -> H2D -> encode+share -> forward on shares -> reconstruct -> decode -> D2H logits"},
+           "config": {"workload": "C4: SPDZ 2-party + crypto provider ResNet-18, base 10 pf 16 int64 ring, one 224x224x3 image, "
+                                  "protocol fss, online phase = one CUDA-graph replay; value = the best placement measured"}}
+    out["roofline"] = fss_roofline(f"cuda:{cur}")
+    out["fss"] = {"comparisons_per_image": CMP_PER_IMAGE, "sha512_per_image_online": CMP_PER_IMAGE * 64,
+                  "eval_ms_per_image_at_roofline_rate": CMP_PER_IMAGE * 64 / (out["roofline"]["achieved"] * 1e6),
+                  "note": "both parties evaluate every comparison: 2 x 32 hashes; on one GPU the two parties' evaluations share the ALU pipe, "
+                          "on separate GPUs they run concurrently"}
+    out["linear_layers"] = linear_layers_block(steps)
     if cpu:
-        g_on, g_off, _l, _g = full_forward(32, 2)
-        c = encrypted_cpu_sample(32, 16)
-        out["cpu_baseline"] = {"kind": "port", "cores": 1, "unit": "ms/image",
-                               "sample": "the same encrypted forward on ONE 32x32 image (67 584 comparisons instead of 3.3 M): oracle "
-                                         "restatement, torch-CPU int64 + hashlib SHA-512, single thread as the reference's B=1 path "
-                                         "(spdz.py:95-107 leaves one non-empty slice)",
-                               "value": c["online_ms"], "offline_ms": c["offline_ms"],
-                               "gpu_same_sample": {"online_ms": g_on, "offline_ms": g_off}}
+        c = encrypted_cpu_sample(224, 16)
+        out["cpu_baseline"] = {"kind": "port", "cores": host_cores(), "unit": "ms/image", "value": c["online_ms"],
+                               "offline_ms": c["offline_ms"],
+                               "sample": "the SAME workload: one 224x224 image, pf 16, 3 311 616 comparisons -- oracle restatement, torch-CPU "
+                                         "int64 matmuls + C/OpenMP SHA-512 on all host cores (the reference's own B=1 path is single-"
+                                         "threaded and pays PySyft message overhead on top: this is a lower bound on its time)"}
     return out
 
 
@@ -407,9 +501,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
             try:
-                line["encrypted_inference"] = encrypted_inference_block()
+                line["encrypted_inference"] = encrypted_inference_report(cpu=True, enc_gpus=args.enc_gpus)
             except Exception as exc:  # the headline must still print
-                line["encrypted_inference"] = {"error": repr(exc)}
+                import traceback
+
+                line["encrypted_inference"] = {"error": repr(exc), "trace": traceback.format_exc()[-1500:]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -448,10 +544,25 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=64, help="images per hospital per step for the bounded CPU reference sample")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--enc-gpus", type=int, default=None, help="path E placement: 1, or 3 = parties on two GPUs + provider on a third "
+                                                                "(default: 3 when three GPUs are visible)")
+    ap.add_argument("--path", default="T", choices=["T", "E"], help="E: print the encrypted-inference line alone")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.path == "E":
+        import torch
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if int(os.environ.get("RANK", "0")) == 0:
+            sampler = ClockSampler(torch.cuda.current_device())
+            sampler.start()
+            line = encrypted_inference_report(steps=max(args.steps, 3) if args.steps < 10 else 5, cpu=not args.no_cpu, enc_gpus=args.enc_gpus)
+            line["clocks"] = sampler.stop()
+            line.update({"steps": args.steps, "warmup": 2, "data": "synthetic", "vs_baseline": None, "scaling": "replicas only"})
+            emit(line)
+        return
     run_ours(args)
 
 

@@ -108,6 +108,22 @@ typedef struct {
 } pm_newton_job_t;
 int pm_bn_newton_fused_i64(const pm_newton_job_t* jobs, int n_jobs, int iters, int64_t divisor, int64_t newton_c,
                            pm_stream_t s);
+/* The same Newton iteration when the two share holders sit on DIFFERENT GPUs: each party calls this
+ * once, on its own device and stream, with ITS shares only; the 3*(iters-1) openings per channel travel over NVLink through
+ * mailboxes: `inbox` is this party's (local) mailbox, `peer_inbox` the other party's mailbox as a peer-mapped pointer, both
+ * pm_bn_newton_p2p_mailbox_bytes(n_jobs, iters, max_channels) bytes, zero-initialised once; `epoch` (device uint64, zero-
+ * initialised once, one per party) is bumped by every call so messages of successive images are told apart (CUDA-graph
+ * replays included); `err` (device int) is set to 1 if the peer's messages never arrive (the peer kernel was not launched).
+ * The two calls must not be stream-ordered after one another: the kernels exchange data while both are running.
+ * Per job: v,x [C]; a,b,c [3*(iters-1)][C]; k [iters] -- this party's shares. */
+typedef struct {
+  const int64_t *v, *a, *b, *c, *k;
+  int64_t* x;
+  int C;
+} pm_newton_p2p_job_t;
+size_t pm_bn_newton_p2p_mailbox_bytes(int n_jobs, int iters, int max_channels);
+int pm_bn_newton_p2p_i64(int party, const pm_newton_p2p_job_t* jobs, int n_jobs, int iters, int64_t divisor, int64_t newton_c,
+                         void* inbox, void* peer_inbox, uint64_t* epoch, int max_channels, int* err, pm_stream_t s);
 /* avg pool k x k, stride k on one share: sum / (k*k) with trunc  functional.py:460-525 + additive_shared.py:720-729 */
 int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t* out, pm_stream_t s);
 /* batch_norm layout shuffles functional.py:52-55,70-73: NCHW [B,C,H,W] <-> [P=B*H*W, C] */

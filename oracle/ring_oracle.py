@@ -23,6 +23,10 @@ from __future__ import annotations
 import torch
 
 I64 = torch.int64
+# which restatement of the FSS comparison the shared-tensor functions below evaluate with: the numpy + hashlib one
+# (oracle/fss_oracle.py, default) or its C twin (oracle/fss_oracle_c.py: same results, pinned to the same fixtures, ~100x
+# faster -- full-size 224 x 224 runs set ``ring_oracle.FSS = fss_oracle_c``)
+FSS = None
 
 
 # --------------------------------------------------------------------------- E2 / E14
@@ -253,7 +257,10 @@ def linear_shared(x_sh, w_sh, b_sh, triple_sh, base, pf):
 def fss_le_shared(x1_sh, x2_sh, fss_key, alpha_sh):
     """fss.le(x1, x2) -- syft/frameworks/torch/mpc/fss.py:97-185,279-283: shares of [x1 <= x2] (0/1, unscaled).
     fss_key / alpha_sh: explicit DIF key material for x.numel() instances (oracle/fss_oracle.py layout)."""
-    from . import fss_oracle as F
+    if FSS is None:
+        from . import fss_oracle as F
+    else:
+        F = FSS
 
     shape = x1_sh[0].shape
     out = F.fss_le([t.reshape(-1).numpy() for t in x1_sh], [t.reshape(-1).numpy() for t in x2_sh], fss_key, alpha_sh)
@@ -467,7 +474,10 @@ class GeneratingTape(Tape):
     def fss_keys(self, n):
         import numpy as np
 
-        from . import fss_oracle as F
+        if FSS is None:
+            from . import fss_oracle as F
+        else:
+            F = FSS
 
         import time
 

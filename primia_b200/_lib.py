@@ -39,6 +39,12 @@ class NewtonJob(ctypes.Structure):
         ("C", ctypes.c_int)]
 
 
+class NewtonP2PJob(ctypes.Structure):
+    """pm_newton_p2p_job_t"""
+
+    _fields_ = [(n, ctypes.c_void_p) for n in ("v", "a", "b", "c", "k", "x")] + [("C", ctypes.c_int)]
+
+
 _SCALARS = {
     "int": ctypes.c_int,
     "size_t": ctypes.c_size_t,
@@ -119,7 +125,7 @@ def stream():
 # kernels launched per entry point when it is not exactly one (used for the gpu_launches claim in bench.py)
 KERNELS_PER_CALL = {
     "pm_conv_wgrad_f32": 2, "pm_linear_ce_f32": 2, "pm_stem_pool_bn_bwd_bf16": 2,
-    "pm_spdz_combine_matmul_i64": 1,
+    "pm_spdz_combine_matmul_i64": 1, "pm_bn_newton_p2p_i64": 2,
 }
 launch_counter = 0
 

@@ -454,6 +454,70 @@ bn_newton_fused_kernel(const __grid_constant__ NewtonJobs jobs, int iters, int64
   J.x1[ch] = (int64_t)X1;
 }
 
+
+// The same iteration when the two share holders live on DIFFERENT GPUs: each party runs this kernel on its own device and
+// the openings travel over NVLink peer-to-peer.  Per Beaver product a thread (= channel) writes its masked operands
+// (delta_j, eps_j) into the PEER's mailbox (remote stores through the peer-mapped pointer), publishes them with a
+// release-store of the launch's epoch number into the mailbox flag, and polls its OWN mailbox (local memory) for the
+// peer's message of the same round.  Mailbox slot = (job, round, channel): written once per launch, so there is no reuse
+// hazard inside a launch; across launches the flag value (epoch, bumped by the host-ordered bump kernel before every
+// launch on both devices) tells a fresh message from last image's.  The two kernels must be able to run concurrently
+// (they sit on different GPUs and neither launch is stream-ordered after the other).  `err` is set when a message does
+// not arrive within ~2^24 polls, i.e. seconds (peer kernel never launched): the thread then gives up instead of hanging the GPU.
+struct NewtonMsg { u64 d, e, flag, pad; };
+struct NewtonP2PJobs { pm_newton_p2p_job_t job[PM_NEWTON_MAX_JOBS]; };
+
+__global__ void newton_epoch_bump_kernel(unsigned long long* epoch) { *epoch += 1ull; }
+
+__global__ void __launch_bounds__(64)
+bn_newton_p2p_kernel(const __grid_constant__ NewtonP2PJobs jobs, int party, int iters, int64_t div, int64_t Cc,
+                     NewtonMsg* inbox, NewtonMsg* peer_inbox, const unsigned long long* __restrict__ epoch_p,
+                     int slot_stride /* channels per (job, round) */, int* __restrict__ err) {
+  const pm_newton_p2p_job_t& J = jobs.job[blockIdx.y];
+  const int C = J.C;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const u64 epoch = *epoch_p;
+  const u64 *ta = (const u64*)J.a, *tb = (const u64*)J.b, *tc = (const u64*)J.c, *kk = (const u64*)J.k;
+  const double inv_div = 1.0 / (double)div, inv_c = 1.0 / (double)Cc;
+  const int rounds = 3 * (iters - 1);
+  const size_t slot0 = (size_t)blockIdx.y * rounds * slot_stride + ch;
+  const u64 V = (u64)J.v[ch];
+  u64 X = (u64)trunc_div_inv((int64_t)(0 - (V - kk[0])), Cc, inv_c);
+  bool dead = false;
+  auto beaver = [&](u64 p, u64 q, int round) -> u64 {
+    const size_t o = (size_t)round * C + ch;
+    const u64 a = ta[o], b = tb[o], c = tc[o];
+    const u64 dj = p - a, ej = q - b;                                    // spdz_mask
+    NewtonMsg* out = peer_inbox + slot0 + (size_t)round * slot_stride;
+    out->d = dj; out->e = ej;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&out->flag), "l"(epoch) : "memory");
+    const NewtonMsg* in = inbox + slot0 + (size_t)round * slot_stride;
+    u64 f = 0;
+    if (!dead) {
+      unsigned long long spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&in->flag) : "memory");
+        if (++spins > (1ull << 24)) { dead = true; atomicExch(err, 1); break; }  // ~10 s
+      } while (f != epoch);
+    }
+    // the mailbox is written by the other GPU while this kernel runs: volatile loads, ordered after the acquire above
+    const u64 d = dj + *reinterpret_cast<const volatile u64*>(&in->d), e = ej + *reinterpret_cast<const volatile u64*>(&in->e);  // opening (spdz.py:162-163)
+    u64 z = d * b + a * e + c;                                           // spdz_compute
+    if (party == 0) z += d * e;
+    return (u64)trunc_div_inv((int64_t)z, div, inv_div);                 // truncate
+  };
+  for (int it = 1; it < iters; ++it) {
+    const u64 K = kk[it];
+    const u64 xx = beaver(X, X, 3 * (it - 1));
+    const u64 w = beaver(V, xx, 3 * (it - 1) + 1);
+    const u64 y = 0 - (w - K);
+    const u64 t = beaver(y, X, 3 * (it - 1) + 2);
+    X = (u64)trunc_div_inv((int64_t)t, Cc, inv_c);
+  }
+  J.x[ch] = (int64_t)X;
+}
+
 __global__ void avgpool_kernel(const int64_t* __restrict__ x, int H, int W, int k, int64_t* __restrict__ out,
                                size_t total) {
   const int Ho = H / k, Wo = W / k;
@@ -616,6 +680,30 @@ int pm_bn_newton_fused_i64(const pm_newton_job_t* jobs, int n_jobs, int iters, i
     if (j.C > maxC) maxC = j.C;
   }
   bn_newton_fused_kernel<<<dim3((maxC + 63) / 64, n_jobs), 64, 0, S(s)>>>(J, iters, divisor, newton_c);
+  PM_LAUNCH_OK();
+}
+
+size_t pm_bn_newton_p2p_mailbox_bytes(int n_jobs, int iters, int max_channels) {
+  return (size_t)n_jobs * 3 * (size_t)(iters > 1 ? iters - 1 : 0) * (size_t)max_channels * sizeof(NewtonMsg);
+}
+
+int pm_bn_newton_p2p_i64(int party, const pm_newton_p2p_job_t* jobs, int n_jobs, int iters, int64_t divisor, int64_t newton_c,
+                         void* inbox, void* peer_inbox, uint64_t* epoch, int max_channels, int* err, pm_stream_t s) {
+  PM_CHECK_ARG(jobs && n_jobs > 0 && n_jobs <= PM_NEWTON_MAX_JOBS && iters >= 1 && divisor > 0 && newton_c > 0);
+  PM_CHECK_ARG((party == 0 || party == 1) && inbox && peer_inbox && epoch && err && max_channels > 0);
+  NewtonP2PJobs J;
+  int maxC = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const pm_newton_p2p_job_t& j = jobs[i];
+    PM_CHECK_ARG(j.v && j.k && j.x && j.C > 0 && j.C <= max_channels);
+    PM_CHECK_ARG(iters == 1 || (j.a && j.b && j.c));
+    J.job[i] = j;
+    if (j.C > maxC) maxC = j.C;
+  }
+  newton_epoch_bump_kernel<<<1, 1, 0, S(s)>>>((unsigned long long*)epoch);
+  bn_newton_p2p_kernel<<<dim3((maxC + 63) / 64, n_jobs), 64, 0, S(s)>>>(J, party, iters, divisor, newton_c, (NewtonMsg*)inbox,
+                                                                        (NewtonMsg*)peer_inbox, (const unsigned long long*)epoch,
+                                                                        max_channels, err);
   PM_LAUNCH_OK();
 }
 

@@ -165,7 +165,7 @@ def build_fss_keys(n_instances: int, device, seed: int, counter: int):
 # ------------------------------------------------------------------------------------------ protocol
 def le(x1_shares, x2_shares, parties, provider=None):
     """fss.le -> fss_op(x1, x2, "comp") (fss.py:97-185,279-283): per-party int64 shares of [x1 <= x2]."""
-    from .spdz import EmptyCryptoPrimitiveStoreError, _ensure_peer
+    from .spdz import EmptyCryptoPrimitiveStoreError, _ensure_peer, release_after_peer_reads
 
     ref = x1_shares if x1_shares[0] is not None else x2_shares
     n = ref[0].numel()
@@ -185,6 +185,7 @@ def le(x1_shares, x2_shares, parties, provider=None):
             if not _ensure_peer(p.device, peer.device):
                 peer = peer.to(p.device)
         masked.append(open_mod32(r[j], peer))
+    release_after_peer_reads(parties)
     out = []
     for j, p in enumerate(parties):
         win = p.crypto_store.get_keys(op=OP, n_instances=n, remove=True)

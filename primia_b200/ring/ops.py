@@ -16,7 +16,7 @@ I64 = torch.int64
 __all__ = [
     "encode", "decode", "share_gen", "random_i64", "im2col", "mask", "mask_im2col", "mask_wt", "open_add",
     "combine_matmul", "combine_mul", "matmul", "trunc_div", "trunc_post_conv", "axpby", "avgpool",
-    "nchw_to_pc", "pc_to_nchw", "conv_out_size", "stack", "bn_newton_fused",
+    "nchw_to_pc", "pc_to_nchw", "conv_out_size", "stack", "bn_newton_fused", "bn_newton_p2p",
 ]
 
 
@@ -307,4 +307,77 @@ def bn_newton_fused(jobs, iters: int, divisor: int, newton_c: int):
         with torch.cuda.device(dev):
             call("pm_bn_newton_fused_i64", ctypes.cast(arr, ctypes.c_void_p), len(chunk), iters, int(divisor), int(newton_c),
                  stream())
+    return outs
+
+
+_P2P_MAILBOX = {}
+
+
+def _p2p_mailbox(dev0, dev1, n_jobs, iters, max_c):
+    """per GPU pair: (inbox on dev0, inbox on dev1, epoch0, epoch1, err0, err1), allocated and zeroed once"""
+    from .._lib import lib
+    from .spdz import _ensure_peer
+
+    key = (dev0, dev1, n_jobs, iters, max_c)
+    st = _P2P_MAILBOX.get(key)
+    if st is None:
+        if dev0 != dev1 and not (_ensure_peer(dev0, dev1) and _ensure_peer(dev1, dev0)):
+            raise PrimiaError(f"no peer access between {dev0} and {dev1}: the cross-GPU Newton kernel needs NVLink / PCIe P2P")
+        fn = lib().pm_bn_newton_p2p_mailbox_bytes
+        fn.restype = ctypes.c_size_t
+        nbytes = int(fn(n_jobs, iters, max_c))
+        st = tuple(torch.zeros(nbytes // 8, dtype=I64, device=d) for d in (dev0, dev1)) + tuple(
+            torch.zeros(1, dtype=I64, device=d) for d in (dev0, dev1)) + tuple(
+            torch.zeros(1, dtype=torch.int32, device=d) for d in (dev0, dev1))
+        for d in (dev0, dev1):
+            torch.cuda.synchronize(d)
+        _P2P_MAILBOX[key] = st
+    return st
+
+
+def bn_newton_p2p(jobs, iters: int, divisor: int, newton_c: int):
+    """precision.py:507-518 with the two share holders on DIFFERENT GPUs: one kernel per party, launched back to back on the two
+    devices' current streams, exchanging the masked operands of every Beaver product through peer-mapped mailboxes over NVLink
+    (pm_bn_newton_p2p_i64).  Same job layout as ``bn_newton_fused``; party j's tensors live on party j's GPU."""
+    from .._lib import NewtonP2PJob
+
+    assert len(jobs) <= 32
+    devs = [jobs[0][0][j].device for j in range(2)]
+    max_c = max(int(v[0].shape[0]) for v, _t, _k in jobs)
+    box0, box1, ep0, ep1, err0, err1 = _p2p_mailbox(devs[0], devs[1], len(jobs), iters, max_c)
+    outs = [[None, None] for _ in jobs]
+    keep = []
+    # the two kernels talk to each other while running: neither launch may be stream-ordered after the other.  On two GPUs
+    # the devices' current streams are independent; with both parties on ONE GPU (tests) party 1 gets a side stream that is
+    # forked BEFORE party 0's kernel is enqueued.
+    side = cur = None
+    if devs[0] == devs[1]:
+        with torch.cuda.device(devs[0]):
+            cur = torch.cuda.current_stream()
+            side = _P2P_MAILBOX.setdefault(("side", devs[0]), torch.cuda.Stream(devs[0]))
+            side.wait_stream(cur)
+    for j in range(2):
+        arr = (NewtonP2PJob * len(jobs))()
+        for i, (v, tri, k) in enumerate(jobs):
+            vj, kj = _chk(v[j]), _chk(k[j])
+            a, b, c = (_chk(t) for t in tri[j])
+            C = vj.shape[0]
+            assert tuple(a.shape) == (3 * (iters - 1), C) and vj.device == devs[j] and a.device == devs[j] and kj.device == devs[j]
+            x = torch.empty_like(vj)
+            for name, t in zip(("v", "a", "b", "c", "k", "x"), (vj, a, b, c, kj, x)):
+                setattr(arr[i], name, t.data_ptr())
+            arr[i].C = C
+            keep.append((vj, kj, a, b, c))
+            outs[i][j] = x
+        inbox, peer = (box0, box1) if j == 0 else (box1, box0)
+        with torch.cuda.device(devs[j]):
+            st = side if (j == 1 and side is not None) else torch.cuda.current_stream()
+            call("pm_bn_newton_p2p_i64", j, ctypes.cast(arr, ctypes.c_void_p), len(jobs), iters, int(divisor), int(newton_c),
+                 ptr(inbox), ctypes.c_void_p(peer.data_ptr()), ptr(ep0 if j == 0 else ep1), max_c, ptr(err0 if j == 0 else err1),
+                 ctypes.c_void_p(st.cuda_stream))
+    if side is not None:
+        cur.wait_stream(side)
+        for o in outs:
+            o[1].record_stream(cur)
+    bn_newton_p2p.last_err = (err0, err1)
     return outs

@@ -1,10 +1,12 @@
-"""Encrypted ResNet-18 forward on shares (inference.py:279-321): layer schedule and geometry.
+"""Encrypted ResNet-18 forward on shares (inference.py:279-321): layer schedule, geometry, offline / online split.
 
-Round-1 scope: every *linear* layer of the encrypted forward (20 convs + fc: rows E4-E10, E13-linear of SURVEY.md
-section 8a) runs the full Beaver protocol on GPU shares at the reference's geometry and triple shapes; BatchNorm on
-shares (E11) is implemented and parity-tested (``functional.batch_norm``) and can be switched on; the comparison-based
-ops (ReLU / max-pool via FSS, E12 -- SURVEY.md section 8f "next") are not built yet, so ``linear_layers_forward`` feeds
-each layer a share tensor of the right shape rather than chaining activations."""
+``EncryptedResNet18`` is the whole forward of the reference's encrypted inference -- 20 Beaver convolutions + fc (rows E4-E10 of
+SURVEY.md section 8a), 20 BatchNorms on shares with the 80-step Newton inverse square root (E11), 17 ReLUs and the 3x3 max-pool
+through function secret sharing (E12, E13), average pool, reconstruction and decoding (E14) -- share for share equal to the
+oracle (tests/test_fss_gpu.py, at 32x32 / pf 4 and at the reference's 224x224 / pf 16).  ``EncryptedInferenceGraph`` captures
+its online phase in a CUDA graph (single- or multi-GPU placement).  ``SharedLinearLayers`` / ``EncryptedLinearGraph`` run the
+21 linear layers alone on synthetic activation shares: the Beaver-matmul micro-benchmark bench.py reports beside the full
+forward."""
 from __future__ import annotations
 
 import torch
@@ -175,10 +177,11 @@ class EncryptedResNet18:
 
     def _newton_all(self):
         """inverse standard deviations of all 20 BatchNorm layers (functional.py:62-64 -> precision.py:507-518) in one launch,
-        consuming triples and constant sharings in forward order; only when both parties share a GPU."""
+        consuming triples and constant sharings in forward order (one kernel for co-resident parties, one kernel per party
+        exchanging openings over NVLink when they sit on two GPUs)."""
         from . import tensors as T
 
-        if not T.FUSE_NEWTON or self.parties[0].device != self.parties[1].device:
+        if not T.FUSE_NEWTON:
             return {}
         inv = T.reciprocal_newton_batched([self.P[n + ".running_var"] for n in self.BN_ORDER])
         return dict(zip(self.BN_ORDER, inv))
@@ -243,13 +246,24 @@ class EncryptedInferenceGraph:
     CUDA graph: ~1.4 k launches of mostly tiny kernels are launch-bound when issued eagerly from Python.  Every primitive the
     forward consumes (Beaver triples, FSS keys, sharings of the Newton constant) lives in static buffers; ``offline()`` has
     the crypto provider generate a fresh set and copies it over them, ``online(img)`` is one graph replay.  The crypto-store
-    bookkeeping (peek / pop, primitives.py:52-102) runs on the host at capture time."""
+    bookkeeping (peek / pop, primitives.py:52-102) runs on the host at capture time.
+
+    Placement: with the two share holders on different GPUs (model_owner cuda:0, data_owner cuda:1,
+    crypto provider cuda:2) the capture is ONE multi-device graph: the second party's stream is forked from the capture stream
+    with an event, every opening is a kernel on the consuming GPU that loads the peer's share through its peer-mapped pointer
+    behind a cross-stream event edge, and the stream joins again before the capture ends.  Each party's FSS evaluation -- the
+    dominant cost -- then runs on its own GPU concurrently with the other's."""
 
     def __init__(self, net: EncryptedResNet18, example: torch.Tensor):
-        from .spdz import PrimitiveStorage
+        import contextlib
 
         self.net = net
         dev = net.parties[0].device
+        others = []
+        for p in net.parties[1:]:
+            if p.device != dev and p.device not in others:
+                others.append(p.device)
+        self.devices = [dev] + others
         assert net.rng is not None, "build the model with from_state_dict (it owns the share RNG)"
         x = net.share_input(example)
         net.trace(x)                                   # warm-up + primitive schedule
@@ -257,14 +271,14 @@ class EncryptedInferenceGraph:
         net.preprocess(1)
         self.static_state = [p.crypto_store.export_state() for p in net.parties]
         self.static_tensors = self._unique(self.static_state)
-        torch.cuda.synchronize(dev)
+        self._sync()
         net.rng.mode, net.rng.static = "record", []
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             net.forward(x)                             # consumes the static primitives once; records the constant sharings
         torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
+        self._sync()
         for p, st in zip(net.parties, self.static_state):
             p.crypto_store.import_state(st)
         net.rng.mode, net.rng.cursor = "replay", 0
@@ -272,13 +286,37 @@ class EncryptedInferenceGraph:
 
         l0 = _lib.launch_counter
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out_shares = net.forward(x)
-            self.logits = self.out_shares.get().float_prec()
+        # other devices: their allocations during the capture go to private pools that live as long as the graph (the replay
+        # reuses the addresses), and their current stream becomes a capturable (non-default) stream forked from the capture
+        self._pools = {d: torch.cuda.MemPool() for d in others}
+        self._streams = {d: torch.cuda.Stream(d) for d in others}
+        with contextlib.ExitStack() as es:
+            for d in others:
+                es.enter_context(torch.cuda.use_mem_pool(self._pools[d], device=d))
+            with torch.cuda.device(dev), torch.cuda.graph(self.graph, capture_error_mode="relaxed" if others else "global"):
+                main = torch.cuda.current_stream(dev)
+                prev = {}
+                for d in others:
+                    prev[d] = torch.cuda.current_stream(d)
+                    self._streams[d].wait_stream(main)         # fork: the stream joins the capture
+                    with torch.cuda.device(d):
+                        torch.cuda.set_stream(self._streams[d])
+                try:
+                    self.out_shares = net.forward(x)
+                    self.logits = self.out_shares.get().float_prec()
+                finally:
+                    for d in others:
+                        main.wait_stream(self._streams[d])     # join
+                        with torch.cuda.device(d):
+                            torch.cuda.set_stream(prev[d])
         self.kernels_in_graph = _lib.launch_counter - l0
         net.rng.mode = "live"
         for p in net.parties:
             p.crypto_store.clear()
+
+    def _sync(self):
+        for d in self.devices:
+            torch.cuda.synchronize(d)
 
     @staticmethod
     def _unique(states):
@@ -303,6 +341,9 @@ class EncryptedInferenceGraph:
         assert len(fresh) == len(self.static_tensors)
         for dst, src in zip(self.static_tensors, fresh):
             dst.copy_(src, non_blocking=True)
+        dev = self.devices[0]
+        for d in self.devices[1:]:
+            torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
         for p in net.parties:
             p.crypto_store.clear()
         net.rng.mode = "live"
@@ -313,5 +354,9 @@ class EncryptedInferenceGraph:
         s = self.net.share_input(img)
         for dst, src in zip(self.x_static.child.child, s.child.child):
             dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        dev = self.devices[0]
+        for d in self.devices[1:]:                      # the replay (launched on dev) must see the other GPUs' pending copies
+            torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
+        with torch.cuda.device(dev):
+            self.graph.replay()
         return self.logits, self.logits.argmax(dim=1)

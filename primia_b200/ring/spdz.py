@@ -280,7 +280,28 @@ def open_shares(parties, shares):
             if not _ensure_peer(p.device, peer.device):
                 peer = peer.to(p.device)  # staged copy when no P2P mapping exists
         outs.append(ops.open_add(shares[j], peer))
+    release_after_peer_reads(parties)
     return outs
+
+
+def release_after_peer_reads(parties):
+    """After a symmetric exchange each GPU has just read the other's buffer through a peer pointer.  The caching allocator
+    only orders a block's reuse on the OWNER's stream, so the owner's stream is made to wait for the reader's kernel: without
+    this edge a later kernel of the owner could overwrite a freed share while the peer is still loading it."""
+    devs = []
+    for p in parties:
+        if p.device not in devs:
+            devs.append(p.device)
+    if len(devs) < 2:
+        return
+    evs = {}
+    for d in devs:
+        with torch.cuda.device(d):
+            evs[d] = torch.cuda.current_stream(d).record_event()
+    for d in devs:
+        for o in devs:
+            if o != d:
+                torch.cuda.current_stream(d).wait_event(evs[o])
 
 
 def spdz_mul(op: str, x_shares, y_shares, parties, provider: TripleProvider = None):

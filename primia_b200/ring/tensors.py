@@ -247,10 +247,11 @@ class FixedPrecisionTensor:
     def reciprocal(self, method="newton"):
         """precision.py:507-518 -- literally (80 iterations, C = 20).  When both share holders are resident on one GPU the
         whole iteration runs as ONE kernel (pm_bn_newton_fused_i64) with identical per-party arithmetic and the same
-        consumption of triples and constant sharings; otherwise the protocol is issued op by op."""
+        consumption of triples and constant sharings; when they sit on two GPUs it is one kernel per party exchanging the
+        openings over NVLink (pm_bn_newton_p2p_i64); PRIMIA_FUSE_NEWTON=0 issues the protocol op by op."""
         assert method == "newton"
         ast = self.child
-        if (FUSE_NEWTON and len(ast.child[0].shape) == 1 and ast.parties[0].device == ast.parties[1].device):
+        if FUSE_NEWTON and len(ast.child[0].shape) == 1:
             return self._reciprocal_fused(80, 20)
         x = None
         C = 20
@@ -280,11 +281,19 @@ def reciprocal_newton_batched(fpts, iters=80, C=20):
         dev = ast.parties[0].device
         q = torch.full((iters,), int((C + 1) * f.scale), dtype=torch.int64, device=dev)
         k = ast.rng.share(q)  # the constant is freshly shared at every iteration (additive_shared.py:473-487)
+        k = (k[0], k[1].to(ast.parties[1].device))
         packed = [[ops.stack([t[i] for t in tri[j]]) for i in range(3)] for j in range(2)]
         jobs.append((ast.child, packed, k))
     scales = {f.scale for f in fpts}
     assert len(scales) == 1
-    xs = ops.bn_newton_fused(jobs, iters, scales.pop(), C)
+    scale = scales.pop()
+    parties = fpts[0].child.parties
+    if parties[0].device != parties[1].device:
+        xs = []
+        for base in range(0, len(jobs), 32):
+            xs += ops.bn_newton_p2p(jobs[base:base + 32], iters, scale, C)
+    else:
+        xs = ops.bn_newton_fused(jobs, iters, scale, C)
     return [f._new(f.child._new(x)) for f, x in zip(fpts, xs)]
 
 

@@ -277,12 +277,9 @@ def test_relu_full_size_stem_activation_reconstructs(ring):
 
 
 # ------------------------------------------------------------------------------------------------ the whole forward
-def test_encrypted_resnet18_forward_bit_exact_vs_oracle(ring):
-    """inference.py:279-321 end to end on a 32x32 image: every share the GPU path produces (logits and intermediate taps)
-    equals the oracle's, given the same parameter/input shares and the randomness the crypto provider generated."""
+def _full_forward_case(ring, base, pf, size, check_plain):
     from oracle import train_oracle as O
 
-    base, pf, size = 10, 4, 32
     torch.manual_seed(42)
     model = O.ResNet18(input_size=size)
     with torch.no_grad():  # non-trivial BN statistics, as after training
@@ -307,6 +304,11 @@ def test_encrypted_resnet18_forward_bit_exact_vs_oracle(ring):
     net.taps = {}
     out = net(mk(x_cpu))
     torch.cuda.synchronize()
+    got_taps = {k: [t.cpu() for t in v] for k, v in net.taps.items()}
+    got = [t.cpu() for t in out.child.child]
+    logits = out.get().float_prec().cpu()
+    del net, out
+    torch.cuda.empty_cache()
 
     tape = R.Tape(prov.triples, rng.log, prov.fss)
     taps = {}
@@ -314,15 +316,38 @@ def test_encrypted_resnet18_forward_bit_exact_vs_oracle(ring):
     assert tape.exhausted()
     for name, sh in taps.items():
         for j in range(2):
-            assert torch.equal(net.taps[name][j].cpu(), sh[j]), f"share mismatch at {name}, party {j}"
+            assert torch.equal(got_taps[name][j], sh[j]), f"share mismatch at {name}, party {j}"
     for j in range(2):
-        assert torch.equal(out.child.child[j].cpu(), ref[j])
-    # and the decoded logits track the plaintext model (pf=4 fixed point; max-pool/ReLU swapped as inference.py:289)
-    logits = out.get().float_prec().cpu()
-    with torch.no_grad():
-        model.pool, model.relu = model.relu, model.pool
-        want = model(img)
-    assert (logits - want).abs().max() < 0.15, (logits, want)
+        assert torch.equal(got[j], ref[j])
+    if check_plain:
+        # and the decoded logits track the plaintext model (pf=4 fixed point; max-pool/ReLU swapped as inference.py:289)
+        with torch.no_grad():
+            model.pool, model.relu = model.relu, model.pool
+            want = model(img)
+        assert (logits - want).abs().max() < 0.15, (logits, want)
+    return len(prov.triples), sum(k[0]["leaf"].shape[1] for k in prov.fss)
+
+
+def test_encrypted_resnet18_forward_bit_exact_vs_oracle(ring):
+    """inference.py:279-321 end to end on a 32x32 image: every share the GPU path produces (logits and intermediate taps)
+    equals the oracle's, given the same parameter/input shares and the randomness the crypto provider generated."""
+    _full_forward_case(ring, 10, 4, 32, check_plain=True)
+
+
+def test_encrypted_resnet18_forward_224_pf16_bit_exact_vs_oracle(ring):
+    """BASELINE config C4 itself: ONE 224 x 224 image at the reference's precision_fractional = 16 -- 20 full-size Beaver convs
+    (M up to 12544, K up to 4608), 20 x 80 Newton iterations, 3 311 616 FSS comparisons (17 ReLUs + the 3x3 max-pool), every
+    intermediate tap and the logits share for share against ``oracle.resnet18_forward_shared`` replaying the 8.9 GB of
+    primitives the GPU crypto provider generated.  The oracle evaluates the comparisons with its C twin
+    (oracle/fss_oracle_c.c, pinned to the reference-generated fixtures in tests/test_oracle_fss.py)."""
+    from oracle import fss_oracle_c
+
+    R.FSS = fss_oracle_c
+    try:
+        n_tri, n_cmp = _full_forward_case(ring, 10, 16, 224, check_plain=False)
+    finally:
+        R.FSS = None
+    assert n_cmp == 3311616, n_cmp
 
 
 def test_encrypted_inference_graph_replay_equals_eager_protocol(ring):

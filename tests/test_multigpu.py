@@ -46,6 +46,88 @@ def test_parties_on_two_gpus_bit_exact():
     assert torch.equal(rec, ref[0] + ref[1])
 
 
+need3 = pytest.mark.skipif(torch.cuda.device_count() < 3, reason="needs 3 GPUs")
+
+
+@need2
+def test_newton_p2p_across_two_gpus_equals_fused():
+    """the cross-GPU BatchNorm Newton kernel pair (openings over NVLink mailboxes) == the single-GPU fused kernel"""
+    from primia_b200.ring import ops
+
+    g = torch.Generator().manual_seed(31)
+    iters, scale, Cc = 80, 10 ** 4, 20
+    jobs0, jobs2 = [], []
+    for C in (64, 256, 512):
+        vq = R.encode(torch.rand(C, generator=g) * 0.5 + 0.75, 10, 4)
+        vs = R.share_from_random(vq, rnd(g, vq.shape))
+        a, b = rnd(g, (3 * (iters - 1), C)), rnd(g, (3 * (iters - 1), C))
+        c = a * b
+        a0, b0, c0 = rnd(g, a.shape), rnd(g, b.shape), rnd(g, c.shape)
+        tri = [[a0, b0, c0], [a - a0, b - b0, c - c0]]
+        kq = torch.full((iters,), 21 * scale, dtype=torch.int64)
+        k0 = rnd(g, kq.shape)
+        ks = [k0, kq - k0]
+        jobs0.append(([vs[0].cuda(0), vs[1].cuda(0)], [[t.cuda(0) for t in tri[j]] for j in range(2)], (ks[0].cuda(0), ks[1].cuda(0))))
+        jobs2.append(([vs[0].cuda(0), vs[1].cuda(1)], [[t.cuda(j) for t in tri[j]] for j in range(2)], (ks[0].cuda(0), ks[1].cuda(1))))
+    with torch.cuda.device(0):
+        ref = ops.bn_newton_fused(jobs0, iters, scale, Cc)
+    for rep in range(2):
+        got = ops.bn_newton_p2p(jobs2, iters, scale, Cc)
+        torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+        assert all(int(e.item()) == 0 for e in ops.bn_newton_p2p.last_err)
+        for (r0, r1), (g0, g1) in zip(ref, got):
+            assert g0.device.index == 0 and g1.device.index == 1
+            assert torch.equal(r0.cpu(), g0.cpu()) and torch.equal(r1.cpu(), g1.cpu())
+
+
+def _enc_forward(devs, graph, size=32, pf=4, seed=5):
+    """the whole encrypted forward for 2 images with fixed seeds on the given (model_owner, data_owner, provider) devices"""
+    import primia_b200.ring as ring
+    from oracle import train_oracle as O
+    from primia_b200.ring.resnet import EncryptedInferenceGraph
+    from primia_b200.ring.tensors import ShareRNG
+
+    torch.manual_seed(42)
+    model = O.ResNet18(input_size=size).eval()
+    parties = [ring.Party("model_owner", devs[0]), ring.Party("data_owner", devs[1])]
+    prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", devs[2]), seed=seed)
+    net = ring.EncryptedResNet18.from_state_dict(model.state_dict(), parties, prov, 10, pf, input_size=size, rng=ShareRNG(seed=99))
+    g = torch.Generator().manual_seed(9)
+    imgs = [torch.randn(1, 3, size, size, generator=g) for _ in range(3)]
+    outs = []
+    if graph:
+        eg = EncryptedInferenceGraph(net, imgs[0])
+        for img in imgs[1:]:
+            eg.offline()
+            logits, _ = eg.online(img)
+            for d in set(devs):
+                torch.cuda.synchronize(d)
+            outs.append(([s.cpu().clone() for s in eg.out_shares.child.child], logits.cpu().clone()))
+    else:
+        for img in imgs[1:]:
+            o = net.forward(net.share_input(img))
+            for d in set(devs):
+                torch.cuda.synchronize(d)
+            outs.append(([s.cpu() for s in o.child.child], o.get().float_prec().cpu()))
+    model.pool, model.relu = model.relu, model.pool
+    with torch.no_grad():
+        want = [model(img) for img in imgs[1:]]
+    return outs, want
+
+
+@need3
+@pytest.mark.parametrize("graph", [False, True])
+def test_encrypted_forward_three_gpu_placement_equals_single_gpu(graph):
+    """SURVEY.md section 8e placement -- model_owner cuda:0, data_owner cuda:1, crypto provider cuda:2, every opening a peer
+    read over NVLink, the BatchNorm Newton iterations exchanged through P2P mailboxes -- gives exactly the shares of the
+    one-GPU placement (same Philox seeds => same primitives and sharings), eagerly and as one multi-device CUDA graph."""
+    one, want = _enc_forward(["cuda:0", "cuda:0", "cuda:0"], graph)
+    three, _ = _enc_forward(["cuda:0", "cuda:1", "cuda:2"], graph)
+    for (s1, l1), (s3, l3), w in zip(one, three, want):
+        assert torch.equal(s1[0], s3[0]) and torch.equal(s1[1], s3[1]), "shares differ between placements"
+        assert torch.equal(l1, l3) and (l3 - w).abs().max() < 0.15
+
+
 NCCL_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["PM_ROOT"])

@@ -343,3 +343,35 @@ def test_encrypted_linear_graph_replay_is_bit_exact(ring):
     for k in ("conv1", "layer2.0.conv1", "layer4.1.conv2", "fc"):
         for j in range(2):
             assert torch.equal(out[k].child.child[j], ref[k][j]), k
+
+
+def test_newton_p2p_kernel_equals_the_single_gpu_fused_kernel(ring):
+    """pm_bn_newton_p2p_i64 (one kernel per party, openings through mailboxes -- the cross-GPU placement) produces the very
+    shares pm_bn_newton_fused_i64 produces (which test_batch_norm_eval_newton_bit_exact pins to the oracle).  Here both
+    parties sit on one GPU, on two streams; tests/test_multigpu.py repeats it across two GPUs over NVLink."""
+    from primia_b200.ring import ops
+
+    g = torch.Generator().manual_seed(31)
+    iters, scale, Cc = 80, 10 ** 4, 20
+    jobs = []
+    for C in (64, 64, 128, 512, 3):
+        v = (torch.rand(C, generator=g) * 0.5 + 0.75)
+        vq = R.encode(v, 10, 4)
+        vs = R.share_from_random(vq, rnd(g, vq.shape))
+        a, b = rnd(g, (3 * (iters - 1), C)), rnd(g, (3 * (iters - 1), C))
+        c = a * b
+        a0, b0, c0 = rnd(g, a.shape), rnd(g, b.shape), rnd(g, c.shape)
+        tri = [[cu(a0), cu(b0), cu(c0)], [cu(a - a0), cu(b - b0), cu(c - c0)]]
+        kq = torch.full((iters,), 21 * scale, dtype=torch.int64)
+        k0 = rnd(g, kq.shape)
+        jobs.append(([cu(vs[0]), cu(vs[1])], tri, (cu(k0), cu(kq - k0))))
+    ref = ops.bn_newton_fused(jobs, iters, scale, Cc)
+    for rep in range(2):                       # twice: the epoch counter distinguishes the launches' messages
+        got = ops.bn_newton_p2p(jobs, iters, scale, Cc)
+        torch.cuda.synchronize()
+        assert all(int(e.item()) == 0 for e in ops.bn_newton_p2p.last_err)
+        for (r0, r1), (g0, g1) in zip(ref, got):
+            assert torch.equal(r0, g0) and torch.equal(r1, g1)
+    inv = ring.decode(ref[0][0] + ref[0][1], 10, 4).cpu()
+    want = 1.0 / torch.sqrt(R.decode(R.reconstruct([t.cpu() for t in jobs[0][0]]), 10, 4))
+    assert (inv - want).abs().max() < 5e-3

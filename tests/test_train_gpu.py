@@ -142,6 +142,67 @@ def test_forward_backward_step_parity_fp32(B, size):
     assert worst[0] < 2e-6, worst
 
 
+class _ImposedReLU(torch.nn.Module):
+    """ReLU whose on/off decisions are dictated (the GPU engine's), in call order: x * mask instead of x * (x > 0)"""
+
+    def __init__(self, masks):
+        super().__init__()
+        self.masks, self.i = masks, 0
+
+    def forward(self, x):
+        m = self.masks[self.i]
+        self.i += 1
+        return x * m
+
+
+@pytest.mark.parametrize("B,size", [(8, 224), (32, 224)])
+def test_gradients_with_the_engines_relu_decisions_imposed_on_the_oracle(B, size):
+    """Closes the escape hatch of the test above at the reference's resolution and a BASELINE batch size: a ReLU net's backward
+    pass is discontinuous exactly where two fp32 forwards may disagree (pre-activations within rounding distance of 0).  Here
+    the oracle's ReLUs are replaced by multiplications with the ENGINE's decisions (a handful of elements with |x| < 1e-5
+    differ from its own), so both backward passes differentiate the same piecewise-linear function: every one of the 62
+    gradients must then meet 1e-5 (norm-wise) -- or, for the few ill-conditioned ones, be as close to the float64 evaluation
+    as the CPU fp32 oracle itself is."""
+    import copy
+
+    m, eng = make_pair(B, size)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, 3, size, size, generator=g)
+    y = torch.randint(0, 3, (B,), generator=g)
+    eng.forward(x.to(DEV))
+    l = eng.loss_and_backward(y.to(DEV))
+    torch.cuda.synchronize()
+    keys = ["a1"] + [k for pre, *_ in eng.blocks for k in (pre + ".a", pre + ".out")]
+    masks = [(eng.act[k] > 0).permute(0, 3, 1, 2).float().cpu() for k in keys]
+    relu = _ImposedReLU(masks)
+    m.relu = relu
+    for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+        for blk in layer:
+            blk.relu = relu
+    m64 = copy.deepcopy(m).double()
+    m64.relu.masks = [t.double() for t in masks]
+    for layer in (m64.layer1, m64.layer2, m64.layer3, m64.layer4):
+        for blk in layer:
+            blk.relu = m64.relu
+    loss_fn = O.make_loss()
+    m.train()
+    out = m(x)
+    loss = loss_fn(out, y)
+    loss.backward()
+    m64.train()
+    loss_fn(m64(x.double()), y).backward()
+    assert rel(eng.logits, out.detach()) < TOL and abs(l.item() - loss.item()) / abs(loss.item()) < TOL
+    gd = eng.grad_dict()
+    errs = {n: rel(gd[n], p.grad) for n, p in m.named_parameters()}
+    p64 = dict(m64.named_parameters())
+    for n, p in m.named_parameters():
+        if errs[n] >= TOL:
+            as_good_as_reference("grad " + n, gd[n], p.grad, p64[n].grad)
+    n_ok = sum(e < TOL for e in errs.values())
+    print(f"B={B} size={size}: {n_ok}/62 gradients within 1e-5 of the CPU fp32 oracle, worst {max(errs.items(), key=lambda kv: kv[1])}")
+    assert n_ok >= 56
+
+
 def test_two_steps_sgd_and_class_weights_and_soft_targets():
     cw = torch.tensor([0.2, 0.5, 0.3])
     m, eng = make_pair(4, 64, optimizer="SGD", class_weights=cw)
