@@ -335,6 +335,41 @@ int pm_krsc_to_bf16_batched_exact(const pm_wcvt_t* table, int n, int total_tiles
 int pm_im2col_stem_bf16(const float* x, int B, int Cin, int H, int W, int R, int stride, int pad, int Kpad, void* out,
                         pm_stream_t s);
 
+/* ----- DP-SGD (train.py:304-334: pytorch-dp PrivacyEngine(noise_multiplier, max_grad_norm).attach(optimizer)).
+ * Per-sample weight gradients dw[b][K][R*S*C] of one conv (written, not accumulated); bf16: tcgen05 kernel with the sample as
+ * grid.z; f32: the deterministic parity kernel once per image (ws as pm_conv_wgrad_f32). */
+int pm_conv_wgrad_persample_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, pm_stream_t s);
+int pm_conv_wgrad_persample_f32(const pm_conv_t* p, const float* x, const float* dy, float* dw, void* ws, pm_stream_t s);
+/* BatchNorm as a frozen per-channel affine map (running statistics; DP needs per-sample gradients, which batch statistics do
+ * not have -- the reference refuses BatchNorm models under DP, train.py:306-310).  g = dy * (y_out > 0) (y_out may be NULL),
+ * g_out (may be NULL) receives g, dx = g * gamma * invstd. */
+int pm_bn_eval_bwd_f32(const float* dy, const float* y_out, const float* gamma, const float* invstd, size_t P, int C, float* g_out,
+                       float* dx, pm_stream_t s);
+int pm_bn_eval_bwd_bf16(const void* dy, const void* y_out, const float* gamma, const float* invstd, size_t P, int C, void* g_out,
+                        void* dx, pm_stream_t s);
+/* per-sample dgamma[b][c] = sum_pix g * xhat, dbeta[b][c] = sum_pix g over image b's HW pixels (outputs are cleared here) */
+int pm_bn_persample_param_grads_f32(const float* g, const float* x, const float* mean, const float* invstd, int B, int HW, int C,
+                                    float* dgamma, float* dbeta, pm_stream_t s);
+int pm_bn_persample_param_grads_bf16(const void* g, const void* x, const float* mean, const float* invstd, int B, int HW, int C,
+                                     float* dgamma, float* dbeta, pm_stream_t s);
+/* norm2[b] += sum_j g[b][j]^2 for a [B][n] per-sample gradient block (norm2: doubles, cleared by the caller once per step) */
+int pm_dp_sqnorm_f32(const float* g, int B, size_t n, double* norm2, pm_stream_t s);
+/* the Linear layer's share of the per-sample norm without materialising dW_b = dlogits_b (x) feat_b:
+ * norm2[b] += |dl_scale * dlogits_b|^2 (|feat_b|^2 + 1) ; dlogits rows have stride ld (pm_linear_ce_f32 leaves the
+ * unnormalised per-sample dlogits in its scratch with ld = ncls + 1) */
+int pm_dp_fc_sqnorm_f32(const float* dlogits, int ld, float dl_scale, const float* feat, int B, int F, int ncls, double* norm2,
+                        pm_stream_t s);
+/* factors[b] = min(1, max_grad_norm / (scale * sqrt(norm2[b]) + 1e-6)) ; norms_out (may be NULL) = scale * sqrt(norm2) */
+int pm_dp_clip_factors(const double* norm2, int B, double scale, double max_grad_norm, float* factors, float* norms_out, pm_stream_t s);
+/* out[j] (= or +=) sum_b factors[b] * g[b][j], b in ascending order (deterministic) */
+int pm_dp_weighted_sum_f32(const float* g, const float* factors, int B, size_t n, float* out, int accumulate, pm_stream_t s);
+int pm_dp_fc_weighted_f32(const float* dlogits, int ld, float dl_scale, const float* feat, const float* factors, int B, int F, int ncls,
+                          float* dW, float* db, pm_stream_t s);
+/* g[j] += stddev * N(0,1), Philox4x32-10(seed, offset) + Box-Muller */
+int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_t offset, pm_stream_t s);
+/* g = (g + a * x) * post  (explicit noise tensor, tests) */
+int pm_dp_axpy_scale_f32(float* g, const float* x, float a, float post, size_t n, pm_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -395,6 +395,19 @@ int pm_conv_wgrad_f32(const pm_conv_t* p, const float* x, const float* dy, float
   PM_LAUNCH_OK();
 }
 
+/* DP-SGD, fp32 parity mode: per-sample weight gradients dw[b][K][R*S*C], one deterministic wgrad per image */
+int pm_conv_wgrad_persample_f32(const pm_conv_t* p, const float* x, const float* dy, float* dw, void* ws, pm_stream_t s) {
+  PM_CHECK_ARG(conv_ok(p) && x && dy && dw && ws);
+  pm_conv_t one = *p;
+  one.B = 1;
+  const size_t xs = (size_t)p->H * p->W * p->C, ys = (size_t)p->Ho * p->Wo * p->K, ws_n = (size_t)p->K * p->R * p->S * p->C;
+  for (int b = 0; b < p->B; ++b) {
+    const int r = pm_conv_wgrad_f32(&one, x + b * xs, dy + b * ys, dw + b * ws_n, ws, s);
+    if (r != PM_OK) return r;
+  }
+  return PM_OK;
+}
+
 int pm_nchw_to_nhwc_f32(const float* x, int B, int C, int H, int W, float* out, pm_stream_t s) {
   PM_CHECK_ARG(x && out && B > 0 && B <= 65535 && C > 0);
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);

@@ -46,6 +46,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                "l"(tm), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h, int n,
                                                 uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -421,7 +426,10 @@ dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------ wgrad
 // D[kg (128 rows = two 64-wide (tap,c) blocks), n (BN couts)] += sum over the split's pixels.
 // A = im2col(x) (MN-major), B = dy [M][K] (MN-major).  grid: (ceil(Kg/128), K/BN, splits)
-template <int BN, int STAGES>
+// PS ("per sample", DP-SGD): blockIdx.z is the SAMPLE; the CTA reduces over that image's pixels only and STORES its tile to
+// dw[sample][K][Kg] (no atomics, nothing to clear).  tmB is then a 3-D map {K, Ho*Wo, B} so that the rows past the image's last
+// pixel are out-of-bounds zero fill: the im2col operand may run on into the next image, its partner dy rows are zero.
+template <int BN, int STAGES, bool PS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, float* __restrict__ dw,
                  int pix_per_split) {
@@ -437,8 +445,8 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int M = p.B * p.Ho * p.Wo;
   const int Kg = p.R * p.S * p.C;
   const int kg0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
-  const int pm0 = blockIdx.z * pix_per_split;
-  const int pm1 = min(M, pm0 + pix_per_split);
+  const int pm0 = blockIdx.z * (PS ? p.Ho * p.Wo : pix_per_split);
+  const int pm1 = PS ? pm0 + p.Ho * p.Wo : min(M, pm0 + pix_per_split);
   const int nsteps = pm1 > pm0 ? (pm1 - pm0 + 127) / 128 : 0;
   const bool second = kg0 + 64 < Kg;  // the upper 64 rows of the tile exist
 
@@ -476,7 +484,10 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_load_im2col(a_tile, &tmA, full0 + 8 * s, c00, bw, bh, nb, (uint16_t)s0, (uint16_t)r0);
       if (second) tma_load_im2col(a_tile + TILE_BYTES, &tmA, full0 + 8 * s, c01, bw, bh, nb, (uint16_t)s1, (uint16_t)r1);
 #pragma unroll
-      for (int sb = 0; sb < B_SUB; ++sb) tma_load_2d(b_tile + sb * TILE_BYTES, &tmB, full0 + 8 * s, n0 + sb * 64, m);
+      for (int sb = 0; sb < B_SUB; ++sb) {
+        if (PS) tma_load_3d(b_tile + sb * TILE_BYTES, &tmB, full0 + 8 * s, n0 + sb * 64, st * 128, blockIdx.z);
+        else tma_load_2d(b_tile + sb * TILE_BYTES, &tmB, full0 + 8 * s, n0 + sb * 64, m);
+      }
     }
   } else if (tid == 32) {
     constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
@@ -501,8 +512,14 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t v[32];
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
       if (kg < Kg) {
+        if (PS) {
+          float* o = dw + (size_t)blockIdx.z * Kg * p.K;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) atomicAdd(dw + (size_t)(n0 + cc * 32 + e) * Kg + kg, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) o[(size_t)(n0 + cc * 32 + e) * Kg + kg] = __uint_as_float(v[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) atomicAdd(dw + (size_t)(n0 + cc * 32 + e) * Kg + kg, __uint_as_float(v[e]));
+        }
       }
     }
     tc_fence_before();
@@ -543,6 +560,17 @@ static bool map_dense(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// dy [B][Ho*Wo][K] bf16 as a 3-D tensor: box {64 channels, 128 pixels of ONE image} (rows past the image: zero fill)
+static bool map_rows_per_image(CUtensorMap* tm, const void* base, uint64_t B, uint64_t pix, uint64_t K) {
+  cuuint64_t dims[3] = {K, pix, B};
+  cuuint64_t strides[2] = {K * 2, pix * K * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -681,6 +709,27 @@ int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* 
   } else {
     if (!set_smem(wgrad_tma_kernel<64, 4>, smem_wg(64, 4))) return 2;
     wgrad_tma_kernel<64, 4><<<grid, NTHREADS, smem_wg(64, 4), st>>>(tmA, tmB, geo(p), dw, pps);
+  }
+  return 0;
+}
+
+// DP-SGD: per-sample weight gradients dw[b][K][R*S*C] = sum over image b's pixels (written, not accumulated).
+int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  using namespace tma;
+  if (p->C % 64 != 0 || p->K % 64 != 0 || !load_driver()) return 1;
+  CUtensorMap tmA, tmB;
+  const int Kg = p->R * p->S * p->C;
+  if (!map_im2col(&tmA, x, p->B, p->H, p->W, p->C, -p->pad, -p->pad, p->pad - (p->S - 1), p->pad - (p->R - 1), p->stride)) return 2;
+  if (!map_rows_per_image(&tmB, dy, (uint64_t)p->B, (uint64_t)p->Ho * p->Wo, (uint64_t)p->K)) return 2;
+  const int BN = p->K % 128 == 0 ? 128 : 64;
+  if (p->B > 65535) return 1;
+  dim3 grid((Kg + 127) / 128, p->K / BN, (unsigned)p->B);
+  if (BN == 128) {
+    if (!set_smem(wgrad_tma_kernel<128, 3, true>, smem_wg(128, 3))) return 2;
+    wgrad_tma_kernel<128, 3, true><<<grid, NTHREADS, smem_wg(128, 3), st>>>(tmA, tmB, geo(p), dw, 0);
+  } else {
+    if (!set_smem(wgrad_tma_kernel<64, 4, true>, smem_wg(64, 4))) return 2;
+    wgrad_tma_kernel<64, 4, true><<<grid, NTHREADS, smem_wg(64, 4), st>>>(tmA, tmB, geo(p), dw, 0);
   }
   return 0;
 }

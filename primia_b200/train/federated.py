@@ -25,13 +25,18 @@ from .resnet18 import ResNet18Engine
 class HospitalWorker:
     """A data owner: its engine (model + optimizer state) and its local batches."""
 
-    def __init__(self, id: str, engine: ResNet18Engine):
+    def __init__(self, id: str, engine: ResNet18Engine, dp: Optional[dict] = None):
         self.id = id
         self.engine = engine
         self.batches: List = []
+        self.dp = dp  # {"noise_multiplier": .., "max_grad_norm": ..}: the PrivacyEngine attached to this hospital's optimizer
 
     def local_step(self, data, target):
-        """utils.py:1168-1174"""
+        """utils.py:1168-1174 (with a privacy engine attached, train.py:326-334: the DP-SGD step of primia_b200/train/dp.py)"""
+        if self.dp is not None:
+            from .dp import dp_train_step
+
+            return dp_train_step(self.engine, data, target, **self.dp)
         return self.engine.train_step(data, target)
 
     def _slots(self, host_data, host_target):
@@ -204,8 +209,12 @@ def aggregation(workers: List[HospitalWorker], weights: Optional[Dict[str, float
         eng = workers[0].engine
         pre, post = fedavg_scales(workers[0].id, dist.get_world_size(group), weights)
         _scale(eng.flat, pre)
-        dist.all_reduce(eng.flat, op=dist.ReduceOp.SUM, group=group)
-        _scale(eng.flat, post)
+        if weights is None and dist.get_backend(group) == "nccl":
+            # sum / n inside the collective (ncclAvg): one pass less over the 44.75 MB state than all-reduce + pm_scale_f32
+            dist.all_reduce(eng.flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(eng.flat, op=dist.ReduceOp.SUM, group=group)
+            _scale(eng.flat, post)
         return
     n = len(workers)
     acc = workers[0].engine.flat

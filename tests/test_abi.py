@@ -29,9 +29,16 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
-    root = os.path.join(os.path.dirname(__file__), "..", "primia_b200")
-    for dp, _dn, fn in os.walk(root):
-        for f in fn:
-            if f.endswith(".py"):
-                src = open(os.path.join(dp, f)).read()
-                assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "").replace("CPU oracle", ""), f
+    """the oracle is test infrastructure: no product module (package, torchlib shim, entry points) imports it"""
+    import re
+
+    here = os.path.join(os.path.dirname(__file__), "..")
+    files = [os.path.join(here, f) for f in ("train.py", "inference.py", "train_federated.py")]
+    for pkg in ("primia_b200", "torchlib"):
+        for dp, _dn, fn in os.walk(os.path.join(here, pkg)):
+            files += [os.path.join(dp, f) for f in fn if f.endswith(".py")]
+    pat = re.compile(r"^\s*(from\s+\.*oracle[\s.]|import\s+oracle|from\s+\S*\s+import\s+.*\boracle\b|__import__\(.oracle)", re.M)
+    for f in files:
+        src = open(f).read()
+        assert not pat.search(src), f
+        assert "importlib" not in src or "oracle" not in src, f

@@ -1,0 +1,105 @@
+"""DP-SGD local step (BASELINE.json configs[2]) -- CUDA path vs the straightforward
+one-backward-per-sample CPU oracle (oracle/dp_oracle.py; parity with pytorch-dp itself is UNPINNED: its source is not in the
+reference tree)."""
+import pytest
+import torch
+
+from oracle import dp_oracle as D
+from oracle import train_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _model(size, seed=42):
+    torch.manual_seed(seed)
+    m = O.ResNet18(input_size=size)
+    with torch.no_grad():  # non-trivial frozen statistics
+        g = torch.Generator().manual_seed(7)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+                mod.weight.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+                mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    return m
+
+
+@pytest.mark.parametrize("optimizer,max_norm", [("SGD", 1.0), ("Adam", 0.05), ("SGD", 1e3)])
+def test_dp_step_fp32_matches_per_sample_oracle(optimizer, max_norm):
+    """fp32 mode: per-sample norms, clip factors, the clipped + noised gradient and the post-step weights.  max_norm = 1e3
+    leaves every sample unclipped (factors == 1), 0.05 clips all of them, 1.0 is the reference's setting."""
+    from primia_b200.train import ResNet18Engine
+    from primia_b200.train.dp import dp_train_step
+
+    B, size, sigma = 6, 64, 1.3
+    m = _model(size)
+    eng = ResNet18Engine(B, 3, 3, size, "max", DEV, "f32", optimizer=optimizer, lr=1e-2 if optimizer == "SGD" else 1e-4)
+    eng.load_state_dict(m.state_dict())
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(B, 3, size, size, generator=g), torch.randint(0, 3, (B,), generator=g)
+    noise = {n: torch.randn(p.shape, generator=g) for n, p in m.named_parameters()}
+    opt = O.make_optimizer(m, optimizer, lr=1e-2 if optimizer == "SGD" else 1e-4)
+    loss, norms, factors = D.dp_step(m, opt, O.make_loss(), x, y, noise, sigma, max_norm)
+    got = dp_train_step(eng, x.to(DEV), y.to(DEV), sigma, max_norm, noise={n: z * sigma * max_norm for n, z in noise.items()})
+    torch.cuda.synchronize()
+    assert abs(got.item() - loss) / abs(loss) < 1e-5
+    st = eng._dp
+    assert rel(st.norms, norms) < 1e-5, (st.norms, norms)
+    assert torch.allclose(st.factors.cpu().double(), factors, rtol=1e-5, atol=1e-7)
+    assert (factors < 1).all() if max_norm == 0.05 else True
+    assert (factors == 1).all() if max_norm == 1e3 else True
+    gd = eng.grad_dict()
+    for n, p in m.named_parameters():
+        assert rel(gd[n], p.grad) < 2e-5, (n, rel(gd[n], p.grad))
+    sd = eng.state_dict()
+    tol = 1e-5 if optimizer == "SGD" else 2e-4   # Adam's first step is lr * g / (|g| + eps): sign-like, ill-conditioned near 0
+    for n, p in m.named_parameters():
+        assert rel(sd[n], p.detach()) < tol, (n, rel(sd[n], p.detach()))
+    # BatchNorm statistics are frozen during a DP step
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            assert torch.equal(sd[k].cpu(), v), k
+
+
+def test_dp_step_bf16_tracks_the_oracle_and_noise_is_gaussian():
+    """throughput mode: tcgen05 per-sample weight gradients (grid.z = sample).  Norms / factors within bf16 accuracy of the
+    oracle; with sigma = 0 the clipped gradient's norm is bounded by C; the Philox noise has the requested standard deviation
+    and changes from step to step."""
+    from primia_b200.train import ResNet18Engine
+    from primia_b200.train.dp import dp_train_step
+
+    B, size = 8, 64
+    m = _model(size)
+    g = torch.Generator().manual_seed(2)
+    x, y = torch.randn(B, 3, size, size, generator=g), torch.randint(0, 3, (B,), generator=g)
+    gs = D.per_sample_grads(m, O.make_loss(), x, y)
+    norms = torch.stack([torch.sqrt(sum((t.double() ** 2).sum() for t in gb.values())) for gb in gs])
+    eng = ResNet18Engine(B, 3, 3, size, "max", DEV, "bf16", optimizer="SGD", lr=0.0, weight_decay=0.0)
+    eng.load_state_dict(m.state_dict())
+    dp_train_step(eng, x.to(DEV), y.to(DEV), 0.0, 1.0)
+    torch.cuda.synchronize()
+    st = eng._dp
+    assert rel(st.norms, norms) < 3e-2, (st.norms, norms)
+    clipped = sum((min(1.0, 1.0 / (n.item() + 1e-6))) * torch.cat([t.flatten() for t in gb.values()]) for n, gb in zip(norms, gs)) / B
+    got = torch.cat([eng.grad_dict()[n].flatten().cpu() for n, _ in m.named_parameters()])
+    assert got.norm() <= 1.0 + 1e-3                      # |sum_b c_b g_b| / B <= C
+    cosine = (got.double() @ clipped.double()) / (got.double().norm() * clipped.double().norm())
+    assert cosine > 0.98, cosine
+    # noise: sigma * C / B per coordinate, fresh every step
+    base = eng.grads.clone()
+    dp_train_step(eng, x.to(DEV), y.to(DEV), 2.0, 1.0, seed=123)
+    n1 = (eng.grads - base).clone()
+    dp_train_step(eng, x.to(DEV), y.to(DEV), 2.0, 1.0, seed=123)
+    n2 = eng.grads - base
+    torch.cuda.synchronize()
+    want = 2.0 * 1.0 / B
+    assert abs(n1.std().item() / want - 1) < 0.01 and abs(n1.mean().item()) < 3 * want / n1.numel() ** 0.5 * 2
+    assert abs((n1 * n2).mean().item()) < 1e-3 * want ** 2 * 10, "the noise of two steps must be independent"
+    k = ((n1 / want) ** 4).mean().item()
+    assert abs(k - 3.0) < 0.1, k                          # Gaussian kurtosis

@@ -68,6 +68,8 @@ def main(argv=None):
     ap.add_argument("--mode", default="bf16", choices=["bf16", "f32", "f32x3"])
     ap.add_argument("--batches_per_worker", type=int, default=4)
     ap.add_argument("--save_dir", default="model_weights")
+    ap.add_argument("--dp_noise_multiplier", type=float, default=1.3, help="train.py:330 hard-codes 1.3")
+    ap.add_argument("--dp_max_grad_norm", type=float, default=1.0, help="train.py:331 hard-codes 1.0")
     cmd = ap.parse_args(argv)
     config = configparser.ConfigParser()
     assert os.path.isfile(cmd.config), "config file not found"
@@ -148,7 +150,11 @@ def main(argv=None):
     for n in worker_names:
         eng = model[n].engine_for(B if not (args.mixup and args.mixup_prob == 1.0) else B // 2, workers[n].device, cmd.mode,
                                   class_weights=class_weights, **opt_kw)
-        hospitals.append(HospitalWorker(n, eng))
+        # train.py:304-334: PrivacyEngine(noise_multiplier=1.3, max_grad_norm=1.0) attached to every hospital's optimizer.  The
+        # reference exits here for federated training ("only ... local training and models without BatchNorm"); the build
+        # runs the DP step with BatchNorm frozen (primia_b200/train/dp.py)
+        dp = {"noise_multiplier": cmd.dp_noise_multiplier, "max_grad_norm": cmd.dp_max_grad_norm} if args.differentially_private else None
+        hospitals.append(HospitalWorker(n, eng, dp=dp))
     optimizer = {h.id: h.engine for h in hospitals}  # the engine owns the optimizer state (Adam moments, step count)
 
     start_at_epoch = 1
