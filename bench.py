@@ -448,8 +448,12 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         fed_round(i)
-    if args.graph and dp is None:   # the DP step draws fresh Philox noise every step (counter passed by value): launched eagerly
+    if args.graph and dp is None:
         eng.capture_graph(xs[0], ys[0])
+    elif args.graph:                # the DP step's Philox counter lives in device memory: every replay draws fresh noise
+        from primia_b200.train.dp import capture_dp_graph
+
+        capture_dp_graph(eng, xs[0], ys[0], **dp)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -537,7 +541,7 @@ def run_ours(args):
                                    if dp else "")), "workers": world,
                    "batch_per_worker": B, "global_batch": world * B, "parallelism": f"fed{world} (one hospital per GPU)",
                    "l2": "4 rotating input batches (154 MB) and ~1 GB of activations per step: working set >> 126 MB L2",
-                   "cuda_graph": bool(args.graph and dp is None), "mode": args.mode},
+                   "cuda_graph": bool(args.graph), "mode": args.mode},
         "clocks": clocks, "gpu_launches": launches * args.steps,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * (hx[0].numel() * 4 + hy[0].numel() * 8),
                 "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e / args.steps,

@@ -338,7 +338,8 @@ int pm_im2col_stem_bf16(const float* x, int B, int Cin, int H, int W, int R, int
 /* ----- DP-SGD (train.py:304-334: pytorch-dp PrivacyEngine(noise_multiplier, max_grad_norm).attach(optimizer)).
  * Per-sample weight gradients dw[b][K][R*S*C] of one conv (written, not accumulated); bf16: tcgen05 kernel with the sample as
  * grid.z; f32: the deterministic parity kernel once per image (ws as pm_conv_wgrad_f32). */
-int pm_conv_wgrad_persample_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, pm_stream_t s);
+/* norm2 (may be NULL): norm2[b] += |dw[b]|^2, accumulated in the epilogue (saves the separate pm_dp_sqnorm_f32 pass) */
+int pm_conv_wgrad_persample_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, double* norm2, pm_stream_t s);
 int pm_conv_wgrad_persample_f32(const pm_conv_t* p, const float* x, const float* dy, float* dw, void* ws, pm_stream_t s);
 /* BatchNorm as a frozen per-channel affine map (running statistics; DP needs per-sample gradients, which batch statistics do
  * not have -- the reference refuses BatchNorm models under DP, train.py:306-310).  g = dy * (y_out > 0) (y_out may be NULL),
@@ -365,8 +366,9 @@ int pm_dp_clip_factors(const double* norm2, int B, double scale, double max_grad
 int pm_dp_weighted_sum_f32(const float* g, const float* factors, int B, size_t n, float* out, int accumulate, pm_stream_t s);
 int pm_dp_fc_weighted_f32(const float* dlogits, int ld, float dl_scale, const float* feat, const float* factors, int B, int F, int ncls,
                           float* dW, float* db, pm_stream_t s);
-/* g[j] += stddev * N(0,1), Philox4x32-10(seed, offset) + Box-Muller */
-int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_t offset, pm_stream_t s);
+/* g[j] += stddev * N(0,1), Philox4x32-10(seed, offset + *counter_dev) + Box-Muller; counter_dev (device uint64, may be NULL) is
+ * incremented afterwards, so a captured CUDA graph draws fresh noise at every replay */
+int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_t offset, uint64_t* counter_dev, pm_stream_t s);
 /* g = (g + a * x) * post  (explicit noise tensor, tests) */
 int pm_dp_axpy_scale_f32(float* g, const float* x, float a, float post, size_t n, pm_stream_t s);
 

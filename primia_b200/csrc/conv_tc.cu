@@ -459,7 +459,7 @@ int pm_halo_conv(const pm_conv_t* p, const void* src, const void* wmat, void* ds
 int pm_s2p_conv_dgrad(const pm_conv_t* p, const void* dy, const void* wt, void* dx, int accumulate, cudaStream_t st);
 // experimental halo-strip weight gradient (wgrad_halo.cu; only when PRIMIA_HALO_WGRAD=1), same return convention
 int pm_halo_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
-int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st);
+int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* dy, float* dw, double* norm2, cudaStream_t st);
 static bool use_tma() {
   const char* e = getenv("PRIMIA_NO_TMA");
   return !(e && e[0] == '1');
@@ -529,9 +529,9 @@ int pm_conv_wgrad_bf16(const pm_conv_t* p, const void* x, const void* dy, float*
 }
 
 /* DP-SGD: per-sample weight gradients (TMA / tcgen05 path only: there is no fallback kernel for other channel counts) */
-int pm_conv_wgrad_persample_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, pm_stream_t s) {
+int pm_conv_wgrad_persample_bf16(const pm_conv_t* p, const void* x, const void* dy, float* dw, double* norm2, pm_stream_t s) {
   PM_CHECK_ARG(tc_ok(p) && x && dy && dw);
-  const int r = pm_tma_conv_wgrad_persample(p, x, dy, dw, S(s));
+  const int r = pm_tma_conv_wgrad_persample(p, x, dy, dw, norm2, S(s));
   if (r == 1) return pm_set_err(__FILE__, __LINE__, "per-sample wgrad: channel counts must be multiples of 64");
   if (r == 2) return pm_set_err(__FILE__, __LINE__, "per-sample wgrad setup failed");
   PM_LAUNCH_OK();

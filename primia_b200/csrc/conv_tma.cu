@@ -432,7 +432,7 @@ dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, int STAGES, bool PS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, float* __restrict__ dw,
-                 int pix_per_split) {
+                 int pix_per_split, double* __restrict__ norm2 = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = 2 * TILE_BYTES, B_SUB = BN / 64, B_BYTES = B_SUB * TILE_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -507,6 +507,7 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int kg = kg0 + quad * 32 + (tid & 31);
+    float sq = 0.f;  // PS: this thread's share of |dw_sample|^2 (DP-SGD per-sample norm), reduced per warp below
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       uint32_t v[32];
@@ -515,12 +516,22 @@ wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (PS) {
           float* o = dw + (size_t)blockIdx.z * Kg * p.K;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) o[(size_t)(n0 + cc * 32 + e) * Kg + kg] = __uint_as_float(v[e]);
+          for (int e = 0; e < 32; ++e) {
+            const float f = __uint_as_float(v[e]);
+            o[(size_t)(n0 + cc * 32 + e) * Kg + kg] = f;
+            sq = fmaf(f, f, sq);
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) atomicAdd(dw + (size_t)(n0 + cc * 32 + e) * Kg + kg, __uint_as_float(v[e]));
         }
       }
+    }
+    if (PS && norm2) {
+      double d = (double)sq;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if ((tid & 31) == 0 && d != 0.0) atomicAdd(norm2 + blockIdx.z, d);
     }
     tc_fence_before();
   }
@@ -714,7 +725,7 @@ int pm_tma_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* 
 }
 
 // DP-SGD: per-sample weight gradients dw[b][K][R*S*C] = sum over image b's pixels (written, not accumulated).
-int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st) {
+int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* dy, float* dw, double* norm2, cudaStream_t st) {
   using namespace tma;
   if (p->C % 64 != 0 || p->K % 64 != 0 || !load_driver()) return 1;
   CUtensorMap tmA, tmB;
@@ -726,10 +737,10 @@ int pm_tma_conv_wgrad_persample(const pm_conv_t* p, const void* x, const void* d
   dim3 grid((Kg + 127) / 128, p->K / BN, (unsigned)p->B);
   if (BN == 128) {
     if (!set_smem(wgrad_tma_kernel<128, 3, true>, smem_wg(128, 3))) return 2;
-    wgrad_tma_kernel<128, 3, true><<<grid, NTHREADS, smem_wg(128, 3), st>>>(tmA, tmB, geo(p), dw, 0);
+    wgrad_tma_kernel<128, 3, true><<<grid, NTHREADS, smem_wg(128, 3), st>>>(tmA, tmB, geo(p), dw, 0, norm2);
   } else {
     if (!set_smem(wgrad_tma_kernel<64, 4, true>, smem_wg(64, 4))) return 2;
-    wgrad_tma_kernel<64, 4, true><<<grid, NTHREADS, smem_wg(64, 4), st>>>(tmA, tmB, geo(p), dw, 0);
+    wgrad_tma_kernel<64, 4, true><<<grid, NTHREADS, smem_wg(64, 4), st>>>(tmA, tmB, geo(p), dw, 0, norm2);
   }
   return 0;
 }

@@ -79,7 +79,15 @@ __global__ void dp_weighted_sum_kernel(const float* __restrict__ g, const float*
                                        int accumulate) {
   for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
     float acc = accumulate ? out[j] : 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(c[b], g[(size_t)b * n + j], acc);   // fixed order: deterministic
+    int b = 0;
+    for (; b + 8 <= B; b += 8) {   // 8 independent loads in flight; the accumulation order over b stays fixed (deterministic)
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = g[(size_t)(b + u) * n + j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(c[b + u], v[u], acc);
+    }
+    for (; b < B; ++b) acc = fmaf(c[b], g[(size_t)b * n + j], acc);
     out[j] = acc;
   }
 }
@@ -108,7 +116,10 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
-__global__ void dp_noise_kernel(float* __restrict__ out, size_t n, float stddev, uint64_t seed, uint64_t offset) {
+__global__ void dp_counter_bump_kernel(unsigned long long* c) { *c += 1ull; }
+__global__ void dp_noise_kernel(float* __restrict__ out, size_t n, float stddev, uint64_t seed, uint64_t offset,
+                                const unsigned long long* __restrict__ counter_dev) {
+  if (counter_dev) offset += *counter_dev;   // device-side step counter: a captured CUDA graph draws fresh noise at every replay
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q * 4 < n; q += (size_t)gridDim.x * blockDim.x) {
     uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -239,10 +250,11 @@ int pm_dp_fc_weighted_f32(const float* dlogits, int ld, float dl_scale, const fl
   dp_fc_weighted_kernel<<<(n + 127) / 128, 128, 0, S(s)>>>(dlogits, ld, dl_scale, feat, factors, B, F, ncls, dW, db);
   PM_LAUNCH_OK();
 }
-int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_t offset, pm_stream_t s) {
+int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_t offset, uint64_t* counter_dev, pm_stream_t s) {
   PM_CHECK_ARG(g);
   if (!n || stddev == 0.f) return PM_OK;
-  dp_noise_kernel<<<pm_grid((n + 3) / 4, 256), 256, 0, S(s)>>>(g, n, stddev, seed, offset);
+  dp_noise_kernel<<<pm_grid((n + 3) / 4, 256), 256, 0, S(s)>>>(g, n, stddev, seed, offset, (const unsigned long long*)counter_dev);
+  if (counter_dev) dp_counter_bump_kernel<<<1, 1, 0, S(s)>>>((unsigned long long*)counter_dev);
   PM_LAUNCH_OK();
 }
 int pm_dp_axpy_scale_f32(float* g, const float* x, float a, float post, size_t n, pm_stream_t s) {

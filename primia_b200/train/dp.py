@@ -50,7 +50,8 @@ class DPState:
             self.x0 = torch.empty((B, c1.Ho, c1.Wo, eng.stem_kpad), dtype=torch.bfloat16, device=dev)
             self.w_stem = torch.empty((64, 1, 1, eng.stem_kpad), dtype=torch.bfloat16, device=dev)
             self.dw_stem = torch.empty((64, eng.stem_kpad), dtype=torch.float32, device=dev)
-        self.counter = 0
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)  # device-side noise counter (bumped by the noise launch)
+        self.seed = None
 
     def nbytes(self):
         return sum(t.numel() * 4 for t in self.ps.values())
@@ -70,14 +71,50 @@ def _wgrad_ps(eng, st, c, x, dy, name=None):
     out = st.ps[name or (c.name + ".weight")]
     if eng.mode == "f32":
         call("pm_conv_wgrad_persample_f32", ctypes.byref(c.desc), ptr(x), ptr(dy), ptr(out), ptr(eng.wgrad_ws), stream())
-    else:
-        call("pm_conv_wgrad_persample_bf16", ctypes.byref(c.desc), ptr(x), ptr(dy), ptr(out), stream())
+    else:  # the epilogue also accumulates |dw_b|^2 into the per-sample norms
+        call("pm_conv_wgrad_persample_bf16", ctypes.byref(c.desc), ptr(x), ptr(dy), ptr(out), ptr(st.norm2), stream())
+
+
+def _graph_key(eng, noise_multiplier, max_grad_norm, seed):
+    return (eng.step_count + 1, float(noise_multiplier), float(max_grad_norm), seed, eng._hyper_key())
 
 
 def dp_train_step(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, max_grad_norm=1.0, noise=None, seed=None):
     """one DP-SGD local step; returns the loss (device scalar).  ``noise``: explicit {name: N(0, (sigma C)^2) tensor in the
     reference layout} (tests); otherwise Philox noise from ``seed`` (default: a per-engine secret drawn from the OS) and a
-    counter that advances every step."""
+    device-side counter that advances every step.  Replays the graph captured by ``capture_dp_graph`` when one matches."""
+    gr = getattr(eng, "_dp_graph", None)
+    if gr is not None and noise is None and gr["key"] == _graph_key(eng, noise_multiplier, max_grad_norm, seed):
+        gr["x"].copy_(x_nchw, non_blocking=True)
+        gr["y"].copy_(target, non_blocking=True)
+        gr["graph"].replay()
+        eng.step_count += 1
+        return eng.loss
+    return _dp_step_eager(eng, x_nchw, target, noise_multiplier, max_grad_norm, noise, seed)
+
+
+def capture_dp_graph(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, max_grad_norm=1.0, seed=None):
+    """capture one DP step (~450 launches) in a CUDA graph; the Philox counter lives in device memory, so replays draw fresh
+    noise.  Valid at the captured optimizer step index / hyper-parameters (see ResNet18Engine.capture_graph)."""
+    with torch.cuda.device(eng.device):
+        snap = (eng.flat.clone(), eng.adam_m.clone(), eng.adam_v.clone(), eng.step_count)
+        gx, gy = x_nchw.clone(), target.clone()
+        side = torch.cuda.Stream(eng.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _dp_step_eager(eng, gx, gy, noise_multiplier, max_grad_norm, None, seed)  # warm-up: allocates every buffer
+        torch.cuda.current_stream().wait_stream(side)
+        eng.flat.copy_(snap[0]); eng.adam_m.copy_(snap[1]); eng.adam_v.copy_(snap[2]); eng.step_count = snap[3]
+        torch.cuda.synchronize(eng.device)
+        key = _graph_key(eng, noise_multiplier, max_grad_norm, seed)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            _dp_step_eager(eng, gx, gy, noise_multiplier, max_grad_norm, None, seed)
+        eng.step_count = snap[3]
+        eng._dp_graph = {"graph": graph, "x": gx, "y": gy, "key": key}
+
+
+def _dp_step_eager(eng: ResNet18Engine, x_nchw, target, noise_multiplier, max_grad_norm, noise, seed):
     if eng.class_weights is not None or target.dtype != torch.int64:
         raise PrimiaError("DP-SGD step: hard labels without class weights (the per-sample loss must be a plain cross-entropy)")
     st = getattr(eng, "_dp", None)
@@ -91,6 +128,7 @@ def dp_train_step(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, max
             eng.forward(x_nchw)
         finally:
             eng.training = was_training
+        st.norm2.zero_()
         target = target.contiguous()
         call("pm_linear_ce_f32", ptr(eng.feat), ptr(eng.p["fc.weight"]), ptr(eng.p["fc.bias"]), ptr(target), None, None, B, 512,
              eng.ncls, ptr(eng.logits), ptr(eng.loss), ptr(eng.dfeat), ptr(eng.g["fc.weight"]), ptr(eng.g["fc.bias"]),
@@ -139,8 +177,9 @@ def dp_train_step(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, max
                  7, 2, 3, eng.stem_kpad, ptr(st.x0), stream())
             _wgrad_ps(eng, st, eng.c1_gemm, st.x0, dc1, "conv1.weight")
         # ---- per-sample norms over the WHOLE parameter vector, clip factors, clipped sum
-        st.norm2.zero_()
         for name, blk in st.ps.items():
+            if eng.mode == "bf16" and len(eng.offsets[name][2]) == 4:
+                continue   # conv weights: already accumulated by the per-sample weight-gradient epilogue
             call("pm_dp_sqnorm_f32", ptr(blk), B, blk.shape[1], ptr(st.norm2), stream())
         ld, inv = eng.ncls + 1, 1.0 / B   # pm_linear_ce_f32 left the unnormalised per-sample dlogits in head_ws
         call("pm_dp_fc_sqnorm_f32", ptr(eng.head_ws), ld, ctypes.c_float(inv), ptr(eng.feat), B, 512, eng.ncls, ptr(st.norm2), stream())
@@ -165,13 +204,12 @@ def dp_train_step(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, max
             call("pm_dp_axpy_scale_f32", ptr(eng.grads), ptr(st.noise_flat), ctypes.c_float(inv), ctypes.c_float(1.0), n, stream())
         elif noise_multiplier > 0:
             if seed is None:
-                if getattr(st, "seed", None) is None:
+                if st.seed is None:
                     import secrets
 
                     st.seed = secrets.randbits(63)
                 seed = st.seed
-            st.counter += 1
-            call("pm_dp_add_noise_f32", ptr(eng.grads), n, ctypes.c_float(noise_multiplier * max_grad_norm * inv), seed, st.counter,
-                 stream())
+            call("pm_dp_add_noise_f32", ptr(eng.grads), n, ctypes.c_float(noise_multiplier * max_grad_norm * inv), seed, 1,
+                 ptr(st.counter), stream())
         eng.optimizer_step()
     return eng.loss

@@ -79,7 +79,7 @@ class HospitalWorker:
         self._pending = None
         with torch.cuda.device(eng.device):
             torch.cuda.current_stream().wait_event(self._ready[slot])
-            loss = eng.train_step(self._stage[slot][0], self._stage[slot][1])
+            loss = self.local_step(self._stage[slot][0], self._stage[slot][1])
             ev = torch.cuda.Event()
             ev.record()
             self._consumed[slot] = ev
