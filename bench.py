@@ -523,6 +523,7 @@ def run_ours(args):
                             "profiles/r01b_launch_summary.csv (1.274 GB read + 0.046 GB written; write-back of the outputs is not "
                             "attributed to the producing kernel by ncu); algorithmic operand + output bytes ~1.6 GB",
             "conv_ms_per_step": conv_ms, "conv_ms_by_kind": getattr(eng, "conv_ms_by_kind", None),
+            "step_ms_by_family": getattr(eng, "step_ms_by_family", None),
             "step_share": conv_ms / (ms / args.steps),
             "timing": "CUDA events on the launching stream around each of the 59 conv launches of an eager step (a spin kernel queued "
                       "before each bracket keeps host launch latency out of it); in the timed CUDA-graph step the 20 wgrad launches run "

@@ -48,13 +48,15 @@ __device__ int halo_trace_n;
 #define PROF_T(var) const long long var = g.prof ? clock64() : 0
 #define PROF_ADD(acc, t0) if (g.prof) acc += clock64() - (t0)
 
-constexpr int SSTAGES = 2;
 constexpr int BSTAGES = 4;
 
-template <int MT, int BN, bool FLIP, bool RB>
+// SSTAGES: depth of the activation-strip ring (3 when shared memory allows: the producer then runs two strips ahead of the MMA
+// warp across tile boundaries); ACC: the data gradient adds into dst (identity branch) -- a template parameter so that the
+// unpack / add / repack of the old values is not even compiled into the forward and the plain data gradients.
+template <int MT, int BN, bool FLIP, bool RB, int SSTAGES, bool ACC>
 __global__ void __launch_bounds__(128 + MT, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HGeo g, bf16* __restrict__ dst,
-                 int accumulate, double* __restrict__ stats) {
+                 double* __restrict__ stats) {
   constexpr int NH = MT / 128;
   constexpr int NTHR = 128 + MT;
   constexpr int B_BYTES = BN * 128;
@@ -62,7 +64,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   const uint32_t strip0 = smem_u32(smem);
   const uint32_t b_base = strip0 + SSTAGES * g.strip_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SSTAGES * g.strip_bytes + g.b_bytes);
@@ -273,7 +277,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         PROF_ADD(pe0, e0);
         PROF_T(e1);
-        epilogue_chunk32(v, valid, out + cc * 32, accumulate != 0, do_stats, epi_scr, lane, st[cc]);
+        epilogue_chunk32(v, valid, out + cc * 32, ACC, do_stats, epi_scr, lane, st[cc]);
         PROF_ADD(pe1, e1);
         ++pe3;
       }
@@ -347,19 +351,45 @@ static bool map_rows(CUtensorMap* tm, const void* base, int B, int H, int W, int
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int MT, int BN, bool FLIP, bool RB>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* dst, int accumulate, double* stats, cudaStream_t st) {
+static int strip_stages() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("PRIMIA_HALO_SSTAGES");
+    v = (e && e[0] == '2') ? 2 : 3;
+  }
+  return v;
+}
+
+template <int MT, int BN, bool FLIP, bool RB, int SSTAGES, bool ACC>
+static int launch_ss(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* dst, double* stats, cudaStream_t st) {
   const int max_rows = (g.Wp - 1 + MT + 2 * g.Wp + 1) / g.Wp + 1;
   g.strip_bytes = (max_rows * g.Wp * 128 + 1023) / 1024 * 1024;
   g.b_bytes = RB ? 9 * (g.Cin / 64) * BN * 128 : BSTAGES * BN * 128;
   const int smem = SSTAGES * g.strip_bytes + g.b_bytes + 256 + (MT / 32) * 2 * g.N * 4 + (MT / 32) * 2048 + 1024;
   if (smem > 227 * 1024) return 1;
-  auto kern = conv_halo_kernel<MT, BN, FLIP, RB>;
+  auto kern = conv_halo_kernel<MT, BN, FLIP, RB, SSTAGES, ACC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 2;
   const int ntiles = ((g.V + MT - 1) / MT) * (g.N / BN);
   dim3 grid(std::min(pm_num_sms(), ntiles));
-  if (pm_launch(kern, grid, dim3(128 + MT), (size_t)smem, st, tmA, tmB, g, (bf16*)dst, accumulate, stats) != cudaSuccess) return 2;
+  if (pm_launch(kern, grid, dim3(128 + MT), (size_t)smem, st, tmA, tmB, g, (bf16*)dst, stats) != cudaSuccess) return 2;
   return 0;
+}
+
+template <int MT, int BN, bool FLIP, bool RB>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, HGeo g, void* dst, int accumulate, double* stats, cudaStream_t st) {
+  // deepest strip ring that fits; the forward never accumulates
+  if (FLIP && accumulate) {
+    if (strip_stages() == 3) {
+      const int r = launch_ss<MT, BN, FLIP, RB, 3, FLIP>(tmA, tmB, g, dst, stats, st);
+      if (r != 1) return r;
+    }
+    return launch_ss<MT, BN, FLIP, RB, 2, FLIP>(tmA, tmB, g, dst, stats, st);
+  }
+  if (strip_stages() == 3) {
+    const int r = launch_ss<MT, BN, FLIP, RB, 3, false>(tmA, tmB, g, dst, stats, st);
+    if (r != 1) return r;
+  }
+  return launch_ss<MT, BN, FLIP, RB, 2, false>(tmA, tmB, g, dst, stats, st);
 }
 
 }  // namespace halo

@@ -83,7 +83,9 @@ stem_kernel(const __grid_constant__ CUtensorMap tmW /* fwd: weights [64][192]; w
   constexpr int W_BYTES = WGRAD ? 2 * BLK : 3 * 8192;  // wgrad: two dy tiles [128 px][64] ; fwd: 3 blocks [64 n][64 k]
   constexpr int TMEM_COLS = 128;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_buf = smem;                        // [2][A_BYTES]
   uint8_t* w_buf = smem + 2 * A_BYTES;          // weights / dy tiles
   uint8_t* patch = w_buf + W_BYTES;             // [2][PATCH_BYTES] fp32

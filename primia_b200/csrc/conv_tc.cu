@@ -179,7 +179,9 @@ template <int MODE, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(TcP p, const bf16* __restrict__ src, const bf16* __restrict__ wmat, bf16* __restrict__ dst, int accumulate) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t s_base = smem_u32(smem);
@@ -301,7 +303,9 @@ template <int BN, int WSTAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(TcP p, const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int pix_per_split) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = 2 * TILE_BYTES, B_SUB = BN / 64, B_BYTES = B_SUB * TILE_BYTES;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t s_base = smem_u32(smem);

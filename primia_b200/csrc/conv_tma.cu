@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, bf16* __restrict__ dst,
                 int accumulate, double* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = RB ? A_BYTES : A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: 128 or 256)
   const uint32_t s_base = smem_u32(smem);
@@ -306,7 +308,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, bf16* __restrict__ dst,
                     int accumulate) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = TILE_BYTES, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t s_base = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -434,7 +438,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Geo p, float* __restrict__ dw,
                  int pix_per_split, double* __restrict__ norm2 = nullptr) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = 2 * TILE_BYTES, B_SUB = BN / 64, B_BYTES = B_SUB * TILE_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t s_base = smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);

@@ -93,7 +93,9 @@ ring_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int nseg, int R, int N, int Kp,
                     int splitK, const u64* __restrict__ Cinit, u64* __restrict__ Cout) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t b_base = s_base + ASTAGES * A_TILE;  // 2 x 8 x B_TILE
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ASTAGES * A_TILE + 2 * 8 * B_TILE);

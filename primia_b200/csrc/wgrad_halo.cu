@@ -1,6 +1,6 @@
 // Path T, throughput mode: weight gradient of the 3x3 / stride-1 / pad-1 convolutions as a HALO-STRIP implicit GEMM.
-// EXPERIMENTAL in round 1: off unless PRIMIA_HALO_WGRAD=1 (correctness is covered by tests/test_conv_tc_gpu.py when the
-// variable is set; it has not been benchmarked inside the training step yet -- DESIGN.md section 7).
+// Default path for the 128-multiple channel counts since round 2 (PRIMIA_HALO_WGRAD=0 falls back to wgrad_tma_kernel):
+// weight-gradient family 0.565 -> 0.519 ms per step at B = 64 (tests/test_conv_tc_gpu.py covers it).
 //
 //   dw[n][r][s][c] = sum over pixels  dy[pix][n] * x[pix + (r-1, s-1)][c]
 //
@@ -38,7 +38,9 @@ constexpr int NTHR = 256;
 __global__ void __launch_bounds__(NTHR, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, WGeo g, float* __restrict__ dw) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET from the __shared__ array: the pointer keeps its address space, so the epilogue scratch
+  // compiles to STS / LDS (a round trip through uintptr_t made nvcc emit generic ST.E / LD.E)
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   // stage = [x half 0][x half 1][dy half 0][dy half 1], each half_bytes
   const uint32_t s_base = smem_u32(smem);
   const uint32_t stage_bytes = 4u * (uint32_t)g.half_bytes;
@@ -189,8 +191,8 @@ static bool map_rows(CUtensorMap* tm, const void* base, int B, int H, int W, int
 // 0 = launched, 1 = not eligible / not enabled (caller uses wgrad_tma_kernel), 2 = CUDA / driver error.  dw accumulates.
 int pm_halo_conv_wgrad(const pm_conv_t* p, const void* x, const void* dy, float* dw, cudaStream_t st) {
   using namespace wgh;
-  const char* e = getenv("PRIMIA_HALO_WGRAD");
-  if (!(e && e[0] == '1')) return 1;
+  const char* e = getenv("PRIMIA_HALO_WGRAD");   // default on since round 2 (1.94 vs 1.97 ms per step); "0" switches it off
+  if (e && e[0] == '0') return 1;
   if (p->R != 3 || p->S != 3 || p->stride != 1 || p->pad != 1 || p->Ho != p->H || p->Wo != p->W) return 1;
   if (p->C % 128 != 0 || p->K % 128 != 0 || p->W + 1 > 256 || !load_driver()) return 1;
   WGeo g;

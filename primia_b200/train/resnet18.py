@@ -366,6 +366,16 @@ class ResNet18Engine:
         return self.stats[idx * 1024:(idx + 1) * 1024]
 
     def _bn_fwd(self, bn, idx, x, y, residual, relu, P, stats_done=False):
+        e0 = self._prof_begin("bn_fwd")
+        self._bn_fwd_impl(bn, idx, x, y, residual, relu, P, stats_done)
+        self._prof_end(e0)
+
+    def _bn_bwd(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
+        e0 = self._prof_begin("bn_bwd")
+        self._bn_bwd_impl(bn, idx, dy, y_out, x, dx, P, g_out)
+        self._prof_end(e0)
+
+    def _bn_fwd_impl(self, bn, idx, x, y, residual, relu, P, stats_done=False):
         C = self.bns[bn]
         st = self._stat_slot(idx)
         if self.training:
@@ -383,7 +393,7 @@ class ResNet18Engine:
         call("pm_bn_apply" + self.sfx, ptr(x), ptr(self.bn_mean[bn]), ptr(self.bn_invstd[bn]), ptr(self.p[bn + ".weight"]),
              ptr(self.p[bn + ".bias"]), ptr(residual) if residual is not None else None, int(relu), P, C, ptr(y), stream())
 
-    def _bn_bwd(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
+    def _bn_bwd_impl(self, bn, idx, dy, y_out, x, dx, P, g_out=None):
         C = self.bns[bn]
         if self.fuse_bn_bwd and self.bn_xmask and self.mode == "bf16" and y_out is not None and g_out is None and self.training:
             # BN -> ReLU with no residual: the mask is recomputed from x (two fewer passes over an activation-sized tensor)
@@ -432,7 +442,9 @@ class ResNet18Engine:
             if self.training:
                 self.stats.zero_()
             if self.mode == "bf16":
+                e0 = self._prof_begin("weight_cast")
                 self.refresh_bf16_weights()
+                self._prof_end(e0)
             bn_ids = {bn: i for i, bn in enumerate(self.bns)}
             fuse = self.mode == "bf16" and self.training and self.fuse_stats
             c1 = self.convs["conv1"]
@@ -449,10 +461,12 @@ class ResNet18Engine:
             if self._stem_pool_fused:
                 if not fuse:
                     call("pm_bn_stats_bf16", ptr(self.act["conv1"]), c1.P, 64, ptr(self._stat_slot(bn_ids["bn1"])), stream())
+                e0 = self._prof_begin("stem_bn_pool")
                 call("pm_bn_relu_maxpool_fwd_bf16", ptr(self.act["conv1"]), ptr(self._stat_slot(bn_ids["bn1"])), self.B, c1.Ho,
                      c1.Wo, 64, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM), ptr(self.p["bn1.weight"]),
                      ptr(self.p["bn1.bias"]), ptr(self.act["p1"]), ptr(self.pool_idx), ptr(self.bn_mean["bn1"]),
                      ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.running_mean"]), ptr(self.p["bn1.running_var"]), stream())
+                self._prof_end(e0)
             else:
                 self._bn_fwd("bn1", bn_ids["bn1"], self.act["conv1"], self.act["a1"], None, True, c1.P, fuse)
                 if self.pooling == "avg":
@@ -495,6 +509,7 @@ class ResNet18Engine:
                     self.dw_stem.zero_()
                 if self.overlap_wgrad and self._side is None:
                     self._side = torch.cuda.Stream(self.device)
+            e0 = self._prof_begin("head")
             call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
                  ptr(target) if hard else None, None if hard else ptr(target),
                  ptr(self.class_weights) if self.class_weights is not None else None, self.B, 512, self.ncls,
@@ -505,6 +520,7 @@ class ResNet18Engine:
             d_out = self._gbuf(("d", last.shape, 0), last)
             hw = self.final_hw * self.final_hw
             call("pm_gap_bwd" + self.sfx, ptr(self.dfeat), self.B, hw, 512, ptr(d_out), stream())
+            self._prof_end(e0)
             for bi in range(len(self.blocks) - 1, -1, -1):
                 pre, ca, cb, ds = self.blocks[bi]
                 xin = self.act[self.blocks[bi - 1][0] + ".out"] if bi > 0 else self.act["p1"]
@@ -534,10 +550,12 @@ class ResNet18Engine:
             if getattr(self, "_stem_pool_fused", False):
                 # the argmax table already encodes the ReLU decision (255 = no gradient): neither the 112x112 activation nor a
                 # full-resolution gradient is ever materialised; reduce + apply launches over 2x2 input blocks
+                e0 = self._prof_begin("stem_bn_pool")
                 call("pm_stem_pool_bn_bwd_bf16", ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["conv1"]),
                      ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
                      ptr(self._stat_slot(len(self.bns) + bn_ids["bn1"])), ptr(dc1), ptr(self.g["bn1.weight"]),
                      ptr(self.g["bn1.bias"]), stream())
+                self._prof_end(e0)
             elif self.pooling == "avg":
                 d_a1 = self._gbuf(("da1",), self.act["a1"])
                 call("pm_avgpool3s2_bwd" + self.sfx, ptr(d_out), self.B, c1.Ho, c1.Wo, 64, ptr(d_a1), stream())
@@ -581,6 +599,7 @@ class ResNet18Engine:
         with torch.cuda.device(self.device):
             self.step_count += 1
             n = self.n_param_flat
+            e0 = self._prof_begin("optimizer")
             if self.opt_name == "Adam":
                 call("pm_adam_step_f32", ptr(self.flat), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), n,
                      ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
@@ -590,6 +609,7 @@ class ResNet18Engine:
                      stream())
             else:
                 raise NotImplementedError("only Adam or SGD supported.")  # utils.py:1141
+            self._prof_end(e0)
 
     def reset_optimizer(self):
         """utils.py:1131-1145,1209-1218: optimizers are re-created (state zeroed) after every aggregation."""
@@ -664,10 +684,13 @@ class ResNet18Engine:
                 self._train_step_eager(x_nchw, target)
             torch.cuda.synchronize(self.device)
             launches = (_lib.launch_counter - n0) // steps + 1
-            ms = sum(a.elapsed_time(b) for a, b, _ in self._prof) / steps
-            self.conv_ms_by_kind = {}
+            conv_tags = ("fwd", "dgrad", "wgrad")
+            ms = sum(a.elapsed_time(b) for a, b, t in self._prof if t in conv_tags) / steps
+            self.conv_ms_by_kind, self.step_ms_by_family = {}, {}
             for a, b, tag in self._prof:
-                self.conv_ms_by_kind[tag] = self.conv_ms_by_kind.get(tag, 0.0) + a.elapsed_time(b) / steps
+                d = self.conv_ms_by_kind if tag in conv_tags else self.step_ms_by_family
+                d[tag] = d.get(tag, 0.0) + a.elapsed_time(b) / steps
+            self.step_ms_by_family["conv (fwd + dgrad + wgrad)"] = ms
             self._prof = None
             self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
         return ms, launches

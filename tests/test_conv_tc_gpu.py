@@ -182,13 +182,12 @@ def test_direct_stem_conv_fwd_and_wgrad(B, H, W):
     assert rel(dw.permute(0, 3, 1, 2), wr.grad) < 1e-3, "stem wgrad"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PRIMIA_TEST_HALO_WGRAD") != "1",
-                    reason="experimental halo-strip weight gradient (wgrad_halo.cu): opt-in, PRIMIA_TEST_HALO_WGRAD=1")
-@pytest.mark.parametrize("B,H,W,C,K", [(3, 28, 28, 128, 128), (5, 14, 14, 256, 256), (9, 7, 7, 512, 256), (2, 9, 13, 128, 128)])
-def test_halo_wgrad_experimental(B, H, W, C, K, monkeypatch):
+@pytest.mark.parametrize("B,H,W,C,K", [(3, 28, 28, 128, 128), (5, 14, 14, 256, 256), (9, 7, 7, 512, 256), (2, 9, 13, 128, 128),
+                                       (64, 14, 14, 256, 256)])
+def test_halo_wgrad(B, H, W, C, K):
+    """halo-strip weight gradient (wgrad_halo.cu): the default kernel for 3x3 / stride-1 layers with 128-multiple channels"""
     from primia_b200._lib import ConvDesc, call, ptr, stream
 
-    monkeypatch.setenv("PRIMIA_HALO_WGRAD", "1")
     g = torch.Generator().manual_seed(B + H + W + C + K)
     d = ConvDesc(B, H, W, C, K, 3, 3, 1, 1, H, W)
     x = bf(torch.randn(B, H, W, C, generator=g))
