@@ -423,9 +423,14 @@ def run_ours(args):
     hx = [x.cpu().pin_memory() for x in xs]
     hy = [y.cpu().pin_memory() for y in ys]
 
+    overlap = bool(args.overlap and world > 1 and dp is None and args.graph)
+
     def fed_round(i):
-        worker.local_step(xs[i % nbuf], ys[i % nbuf])
-        aggregation([worker], None, group)
+        if overlap:   # FedAvg of the layer4 bucket overlaps the backward of layers 3..1 (two-graph step)
+            worker.local_step_and_fedavg(xs[i % nbuf], ys[i % nbuf], group)
+        else:
+            worker.local_step(xs[i % nbuf], ys[i % nbuf])
+            aggregation([worker], None, group)
         eng.reset_optimizer()
 
     def barrier():
@@ -448,7 +453,9 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         fed_round(i)
-    if args.graph and dp is None:
+    if overlap:
+        eng.capture_graph_overlap(xs[0], ys[0])
+    elif args.graph and dp is None:
         eng.capture_graph(xs[0], ys[0])
     elif args.graph:                # the DP step's Philox counter lives in device memory: every replay draws fresh noise
         from primia_b200.train.dp import capture_dp_graph
@@ -489,7 +496,10 @@ def run_ours(args):
     seen = []
 
     def fed_round_host(i):
-        loss = worker.local_step_host(hx[i % nbuf], hy[i % nbuf])           # H2D of this step's batch (pinned -> device)
+        if overlap:
+            loss = worker.local_step_and_fedavg(hx[i % nbuf], hy[i % nbuf], group, host=True)
+        else:
+            loss = worker.local_step_host(hx[i % nbuf], hy[i % nbuf])       # H2D of this step's batch (pinned -> device)
         worker.prefetch_host(hx[(i + 1) % nbuf], hy[(i + 1) % nbuf])        # loader look-ahead: next batch's H2D overlaps
         slot = i % (LAG + 1)
         ring[slot].copy_(loss, non_blocking=True)                           # D2H of this step's loss
@@ -500,7 +510,8 @@ def run_ours(args):
         if i >= LAG and ring_ev[old] is not None:
             ring_ev[old].synchronize()                                      # step i - LAG has long finished
             seen.append(float(ring[old]))
-        aggregation([worker], None, group)
+        if not overlap:
+            aggregation([worker], None, group)
         eng.reset_optimizer()
 
     for i in range(LAG + 1):
@@ -542,7 +553,9 @@ def run_ours(args):
                                    if dp else "")), "workers": world,
                    "batch_per_worker": B, "global_batch": world * B, "parallelism": f"fed{world} (one hospital per GPU)",
                    "l2": "4 rotating input batches (154 MB) and ~1 GB of activations per step: working set >> 126 MB L2",
-                   "cuda_graph": bool(args.graph), "mode": args.mode},
+                   "cuda_graph": bool(args.graph), "mode": args.mode,
+                   "fedavg": ("two buckets (layer4+fc+BN statistics 33.6 MB, rest 11.1 MB), the first all-reduce overlapped with the backward "
+                              "of layers 3..1, ncclAvg") if overlap else "one all-reduce of the flat state after the step (ncclAvg)"},
         "clocks": clocks, "gpu_launches": launches * args.steps,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * (hx[0].numel() * 4 + hy[0].numel() * 8),
                 "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e / args.steps,
@@ -606,6 +619,7 @@ def main():
     ap.add_argument("--dp-sigma", type=float, default=1.0)
     ap.add_argument("--ref-batch", type=int, default=None, help="images per hospital per step for the bounded CPU reference sample")
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--overlap", type=int, default=1, help="N > 1: all-reduce of the layer4 bucket overlapped with the rest of the backward")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--enc-gpus", type=int, default=None, help="path E placement: 1, or 3 = parties on two GPUs + provider on a third "
                                                                 "(default: 3 when three GPUs are visible)")

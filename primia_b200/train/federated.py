@@ -39,6 +39,37 @@ class HospitalWorker:
             return dp_train_step(self.engine, data, target, **self.dp)
         return self.engine.train_step(data, target)
 
+    def local_step_and_fedavg(self, data, target, group, host=False):
+        """utils.py:1168-1201 for the reference's default schedule (sync after every batch, unweighted, plain aggregation) with the
+        all-reduce OVERLAPPED with the backward pass: the engine's two-graph step (``capture_graph_overlap``) finishes layer4's
+        gradients and optimizer step first; that bucket (75 % of the 44.75 MB state, plus the BatchNorm running statistics) is
+        averaged over NVLink (ncclAvg) on NCCL's stream while the rest of the backward runs; the small remainder follows."""
+        import torch.distributed as dist
+
+        eng = self.engine
+        off = eng.split_offset
+        works = []
+        if host:
+            self._slots(data, target)
+            if self._pending is None or self._pending[1] is not data:
+                self.prefetch_host(data, target)
+            slot = self._pending[0]
+            self._pending = None
+            torch.cuda.current_stream(eng.device).wait_event(self._ready[slot])
+            data, target = self._stage[slot]
+        with torch.cuda.device(eng.device):
+            loss = eng.train_step_overlapped(
+                data, target,
+                lambda: works.append(dist.all_reduce(eng.flat[off:], op=dist.ReduceOp.AVG, group=group, async_op=True)),
+                lambda: works.append(dist.all_reduce(eng.flat[:off], op=dist.ReduceOp.AVG, group=group, async_op=True)))
+            if host:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._consumed[slot] = ev
+            for w in works:
+                w.wait()   # stream-level wait: the next kernels on this stream see the averaged state
+        return loss
+
     def _slots(self, host_data, host_target):
         eng = self.engine
         if getattr(self, "_stage", None) is None or self._stage[0][0].shape != host_data.shape:

@@ -45,6 +45,7 @@ class _Conv:
 class ResNet18Engine:
     BN_EPS = 1e-5
     BN_MOMENTUM = 0.1
+    SPLIT_BLOCK = 6  # blocks[6:] = layer4: 75 % of the parameters, and the FIRST gradients the backward pass finishes
 
     def __init__(self, batch, num_classes=3, in_channels=3, input_size=224, pooling="max", device="cuda:0", mode="f32",
                  optimizer="Adam", lr=1e-4, betas=(0.5, 0.99), weight_decay=5e-4, eps=1e-8, class_weights=None, adptpool=False):
@@ -76,6 +77,8 @@ class ResNet18Engine:
                             and os.environ.get("PRIMIA_NO_DIRECT_STEM", "0") != "1")
         self._x_in = None
         self._side = None
+        self._split_cb = None
+        self._graph2 = None
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -523,6 +526,12 @@ class ResNet18Engine:
             self._prof_end(e0)
             for bi in range(len(self.blocks) - 1, -1, -1):
                 pre, ca, cb, ds = self.blocks[bi]
+                if self._split_cb is not None and bi == self.SPLIT_BLOCK - 1:
+                    # every gradient of layer4 + fc exists once the side stream has joined: the caller takes over here
+                    # (optimizer step on that segment, start of its all-reduce, graph boundary)
+                    if self._side is not None:
+                        torch.cuda.current_stream().wait_stream(self._side)
+                    self._split_cb()
                 xin = self.act[self.blocks[bi - 1][0] + ".out"] if bi > 0 else self.act["p1"]
                 out = self.act[pre + ".out"]
                 # out = relu(bn2(cB) + idn).  g = d_out * (out > 0) may alias d_out (element-wise in place).
@@ -595,17 +604,21 @@ class ResNet18Engine:
                 torch.cuda.current_stream().wait_stream(self._side)  # join: the optimizer needs every weight gradient
         return self.loss
 
-    def optimizer_step(self):
+    def optimizer_step(self, lo=0, hi=None, bump=True):
+        """the optimizer on flat[lo:hi] (default: all parameters); ``bump`` advances the step index (once per step)"""
         with torch.cuda.device(self.device):
-            self.step_count += 1
-            n = self.n_param_flat
+            if bump:
+                self.step_count += 1
+            hi = self.n_param_flat if hi is None else hi
+            n = hi - lo
+            sl = lambda t: ctypes.c_void_p(t.data_ptr() + 4 * lo)
             e0 = self._prof_begin("optimizer")
             if self.opt_name == "Adam":
-                call("pm_adam_step_f32", ptr(self.flat), ptr(self.grads), ptr(self.adam_m), ptr(self.adam_v), n,
+                call("pm_adam_step_f32", sl(self.flat), sl(self.grads), sl(self.adam_m), sl(self.adam_v), n,
                      ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
                      ctypes.c_float(self.opt_eps), ctypes.c_float(self.wd), self.step_count, stream())
             elif self.opt_name == "SGD":
-                call("pm_sgd_step_f32", ptr(self.flat), ptr(self.grads), n, ctypes.c_float(self.lr), ctypes.c_float(self.wd),
+                call("pm_sgd_step_f32", sl(self.flat), sl(self.grads), n, ctypes.c_float(self.lr), ctypes.c_float(self.wd),
                      stream())
             else:
                 raise NotImplementedError("only Adam or SGD supported.")  # utils.py:1141
@@ -668,6 +681,72 @@ class ResNet18Engine:
             self._graph = {"graph": graph, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype, "launches": launches,
                            "hyper": self._hyper_key()}
         return launches
+
+    # ------------------------------------------------------------------ FedAvg overlapped with the backward pass
+    @property
+    def split_offset(self):
+        """flat[split_offset:] = layer4 + fc parameters followed by ALL BatchNorm running statistics (33.6 MB of the 44.75 MB
+        state); flat[:split_offset] = stem + layer1-3 parameters"""
+        return self.offsets[self.blocks[self.SPLIT_BLOCK][1].name + ".weight"][0]
+
+    def capture_graph_overlap(self, x_nchw, target):
+        """The local step as TWO CUDA graphs, so that the all-reduce of most of the state overlaps the rest of the backward:
+
+          graph A: forward, backward of layer4, optimizer step on flat[split_offset:n_param]    -> all-reduce flat[split_offset:]
+          graph B: backward of layer3..1 + stem, optimizer step on flat[:split_offset]          -> all-reduce flat[:split_offset]
+
+        The running statistics (end of the flat buffer) are final after the forward, so they travel with the first bucket.
+        Same replay conditions as ``capture_graph`` (optimizer step index, hyper-parameters)."""
+        with torch.cuda.device(self.device):
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            gx, gy = x_nchw.clone(), target.clone()
+            off = self.split_offset
+            cap = torch.cuda.Stream(self.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                self._train_step_eager(gx, gy)  # warm-up: allocates every lazily created buffer
+            torch.cuda.current_stream().wait_stream(cap)
+            self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+            torch.cuda.synchronize(self.device)
+            gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+
+            def boundary():
+                self.optimizer_step(off, self.n_param_flat, bump=True)
+                gA.capture_end()
+                gB.capture_begin(pool=gA.pool())
+
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                self._split_cb = boundary
+                try:
+                    gA.capture_begin()
+                    self.forward(gx)
+                    self.loss_and_backward(gy)
+                    self.optimizer_step(0, off, bump=False)
+                    gB.capture_end()
+                finally:
+                    self._split_cb = None
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize(self.device)
+            self.step_count = snap[3]
+            self._graph2 = {"A": gA, "B": gB, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype,
+                            "hyper": self._hyper_key(), "off": off}
+
+    def train_step_overlapped(self, x_nchw, target, after_a, after_b):
+        """replay graph A, call ``after_a()`` (start the first bucket's all-reduce), replay graph B, call ``after_b()``"""
+        gr = self._graph2
+        if not (gr is not None and gr["step"] == self.step_count + 1 and gr["tdtype"] == target.dtype
+                and gr["hyper"] == self._hyper_key()):
+            raise PrimiaError("no overlap graphs valid for this step: capture_graph_overlap first (same optimizer step index and "
+                              "hyper-parameters)")
+        gr["x"].copy_(x_nchw, non_blocking=True)
+        gr["y"].copy_(target, non_blocking=True)
+        gr["A"].replay()
+        after_a()
+        gr["B"].replay()
+        self.step_count += 1
+        after_b()
+        return self.loss
 
     def profile_conv_time(self, x_nchw, target, steps=2):
         """Device time of the convolution kernels per local step (CUDA events on the launching stream around each of the

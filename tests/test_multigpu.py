@@ -160,6 +160,22 @@ for weights in (None, {"alice": 0.25, "bob": 0.75}):
         ref = O.secure_aggregation_value(ts, [weights[w] for w in ids] if weights else [1, 1], 10, 16)
         if weights is None: ref = ref / 2
         assert torch.equal(sd[k].cpu(), ref.reshape(sd[k].shape)), k
+# the overlapped schedule (two-graph step, layer4 bucket all-reduced during the rest of the backward) == step, then FedAvg
+B, size = 8, 64
+torch.manual_seed(5)
+base = O.ResNet18(input_size=size).state_dict()
+g = torch.Generator().manual_seed(10 + rank)
+x, y = torch.randn(B, 3, size, size, generator=g).cuda(), torch.randint(0, 3, (B,), generator=g).cuda()
+a = ResNet18Engine(B, 3, 3, size, "max", f"cuda:{rank}", "bf16"); a.load_state_dict(base)
+b = ResNet18Engine(B, 3, 3, size, "max", f"cuda:{rank}", "bf16"); b.load_state_dict(base)
+a.train_step(x, y); aggregation([HospitalWorker(ids[rank], a)], None, dist.group.WORLD)
+b.capture_graph_overlap(x, y)
+HospitalWorker(ids[rank], b).local_step_and_fedavg(x, y, dist.group.WORLD)
+torch.cuda.synchronize()
+err = ((a.flat - b.flat).norm() / a.flat.norm()).item()
+assert err < 1e-5, err
+chk = b.flat.clone(); dist.all_reduce(chk, op=dist.ReduceOp.AVG)
+assert torch.allclose(chk, b.flat, rtol=0, atol=1e-7), "ranks must hold the same averaged state"
 dist.barrier()
 if rank == 0: print("NCCL_FEDAVG_OK")
 dist.destroy_process_group()

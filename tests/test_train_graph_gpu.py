@@ -80,6 +80,38 @@ def test_graph_replay_equals_eager_step(B, size):
     assert graph.step_count == 1 and eager.step_count == 1
 
 
+def test_two_graph_overlap_step_equals_eager_step():
+    """capture_graph_overlap: graph A (forward, layer4 backward, optimizer on flat[split:]) + graph B (rest of the backward,
+    optimizer on flat[:split]) == one eager step; the callbacks fire after A and after B (where bench.py / local_step_and_fedavg
+    start the two all-reduces)"""
+    B, size = 16, 96
+    torch.manual_seed(42)
+    sd = O.ResNet18(input_size=size).state_dict()
+    batches = _batches(B, size, 2)
+    eager, two = _engine(B, size, sd), _engine(B, size, sd)
+    two.capture_graph_overlap(batches[0][0].to(DEV), batches[0][1].to(DEV))
+    assert torch.equal(eager.flat, two.flat)
+    off = two.split_offset
+    assert off == two.offsets["layer4.0.conv1.weight"][0] and two.n_flat - off > 3 * off   # 75 % of the state goes first
+    for x, y in batches:
+        for eng in (eager, two):
+            eng.reset_optimizer()
+        two.flat.copy_(eager.flat)
+        le = eager._train_step_eager(x.to(DEV), y.to(DEV)).item()
+        seen = []
+        snap = {}
+
+        def after_a():
+            seen.append("A")
+            snap["tail"] = two.flat[off:two.n_param_flat].clone()   # layer4 + fc already stepped when the first all-reduce starts
+
+        lt = two.train_step_overlapped(x.to(DEV), y.to(DEV), after_a, lambda: seen.append("B")).item()
+        torch.cuda.synchronize()
+        assert seen == ["A", "B"]
+        _assert_same_step((le, eager.grads, eager.flat), (lt, two.grads, two.flat), "two-graph step")
+        assert torch.equal(snap["tail"], two.flat[off:two.n_param_flat]), "graph B must not touch the first bucket"
+
+
 def test_graph_is_not_replayed_when_the_optimizer_step_or_hyperparameters_differ():
     """Adam's bias correction and lr are baked into the captured launches: a replay is only legal at the captured step index
     with the captured hyper-parameters; otherwise the engine must launch eagerly."""
