@@ -420,13 +420,19 @@ def run_ours(args):
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     xs = [torch.randn(B, 3, 224, 224, device=dev, generator=g) for _ in range(nbuf)]
     ys = [torch.randint(0, 3, (B,), device=dev, generator=g) for _ in range(nbuf)]
-    hx = [x.cpu().pin_memory() for x in xs]
+    # host staging of the e2e leg: the loader's pinned batches.  bf16 mode stages bf16 pixels (half the PCIe bytes): the stem
+    # rounds every pixel to bf16 before its MMA anyway, so the step is bit-identical to shipping fp32
+    # (tests/test_train_graph_gpu.py::test_bf16_staged_batch_gives_the_identical_step)
+    stage_bf16 = args.mode == "bf16" and args.e2e_dtype == "bf16"
+    if stage_bf16:
+        xs = [x.bfloat16().float() for x in xs]      # the device-resident leg runs on the very same pixel values
+    hx = [(x.bfloat16() if stage_bf16 else x).cpu().pin_memory() for x in xs]
     hy = [y.cpu().pin_memory() for y in ys]
 
     overlap = bool(args.overlap and world > 1 and dp is None and args.graph)
 
     def fed_round(i):
-        if overlap:   # FedAvg of the layer4 bucket overlaps the backward of layers 3..1 (two-graph step)
+        if overlap and eng._graph2 is not None:   # FedAvg of the layer4 bucket overlaps the backward of layers 3..1 (two-graph step)
             worker.local_step_and_fedavg(xs[i % nbuf], ys[i % nbuf], group)
         else:
             worker.local_step(xs[i % nbuf], ys[i % nbuf])
@@ -557,10 +563,13 @@ def run_ours(args):
                    "fedavg": ("two buckets (layer4+fc+BN statistics 33.6 MB, rest 11.1 MB), the first all-reduce overlapped with the backward "
                               "of layers 3..1, ncclAvg") if overlap else "one all-reduce of the flat state after the step (ncclAvg)"},
         "clocks": clocks, "gpu_launches": launches * args.steps,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": world * (hx[0].numel() * 4 + hy[0].numel() * 8),
+        "e2e": {"value": e2e_value, "unit": "images/s",
+                "h2d_bytes_per_step": world * (hx[0].numel() * hx[0].element_size() + hy[0].numel() * 8),
+                "host_batch_dtype": str(hx[0].dtype),
                 "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e / args.steps,
-                "note": f"pinned fp32 batch -> H2D on a copy stream (one batch of look-ahead) -> step -> loss D2H into a pinned ring, read "
-                        f"{LAG} steps later"},
+                "note": f"pinned {'bf16' if stage_bf16 else 'fp32'} batch -> H2D on a copy stream (one batch of look-ahead) -> step -> loss D2H "
+                        f"into a pinned ring, read {LAG} steps later"
+                        + ("; bf16 staging is bit-identical for this mode (the stem rounds pixels to bf16 before its MMA)" if stage_bf16 else "")},
         "roofline": roof,
     }
     par = os.path.join(ROOT, "profiles", "r02_bf16_c2_errors.json")
@@ -619,6 +628,7 @@ def main():
     ap.add_argument("--dp-sigma", type=float, default=1.0)
     ap.add_argument("--ref-batch", type=int, default=None, help="images per hospital per step for the bounded CPU reference sample")
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--e2e-dtype", default="bf16", choices=["bf16", "f32"], help="dtype of the pinned host batches of the e2e leg (bf16 mode)")
     ap.add_argument("--overlap", type=int, default=1, help="N > 1: all-reduce of the layer4 bucket overlapped with the rest of the backward")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--enc-gpus", type=int, default=None, help="path E placement: 1, or 3 = parties on two GPUs + provider on a third "

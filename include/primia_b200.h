@@ -257,15 +257,16 @@ int pm_bn_bwd_fused_xmask_bf16(const void* dy, const void* x, const float* mean,
 /* Stem forward in one pass (bf16 mode): BatchNorm2d (batch statistics from `stats`, running stats updated, mean/invstd
  * written) + ReLU + MaxPool2d(3,2,1) of x [B,H,W,C] -> y [B,Ho,Wo,C]; the full-resolution activation is not materialised.
  * idx: argmax per output (first strict maximum of the raw conv outputs, sign-adjusted per channel: BN+ReLU is monotonic), or
- * 255 where the maximum is not positive (no gradient passes the ReLU there). */
+ * 255 where the maximum is not positive (no gradient passes the ReLU there).  xmax (bf16 [B,Ho,Wo,C], may be NULL): the RAW
+ * conv output at each window's argmax, kept so that the backward's batch sums are a reduction over the pooled tensors only. */
 int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H, int W, int C, float eps, float momentum,
-                                const float* gamma, const float* beta, void* y, uint8_t* idx, float* mean, float* invstd,
+                                const float* gamma, const float* beta, void* y, uint8_t* idx, void* xmax, float* mean, float* invstd,
                                 float* running_mean, float* running_var, pm_stream_t s);
 
 /* Backward of pm_bn_relu_maxpool_fwd_bf16 (H, W even): max-pool backward gathered from (dpool, pool_idx) + BatchNorm backward
  * as a reduce launch and an apply launch over 2x2 input blocks; sums: [2*C] doubles ZEROED by the caller; dx [B,H,W,C]. */
-int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* x, const float* mean,
-                             const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
+int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, const void* xmax, int B, int H, int W, const void* x,
+                             const float* mean, const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
                              float* dbeta, pm_stream_t s);
 
 /* Stem variant: the BN input gradient is MaxPool2d(3,2,1)'s backward of `dpool` [B,Ho,Wo,C], gathered from the stored

@@ -834,7 +834,8 @@ __global__ void __launch_bounds__(BT)
 bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats, double Pd, float eps,
                            float momentum, float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ rm,
                            float* __restrict__ rv, const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W,
-                           int C, int Ho, int Wo, size_t total, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx) {
+                           int C, int Ho, int Wo, size_t total, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+                           __nv_bfloat16* __restrict__ xmax) {
   constexpr int V = 8;
   extern __shared__ float sp[];  // [3][C]: mu, invstd*gamma, beta
   pm_pdl_sync();
@@ -922,6 +923,63 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __
     const size_t o = i * V;
     Vec<__nv_bfloat16>::store(y + o, out);
     *reinterpret_cast<uint2*>(idx + o) = *reinterpret_cast<const uint2*>(id);
+    // the RAW conv output at the window's argmax: with it the backward's batch sums (sum g, sum g*xhat) become a reduction over
+    // the POOLED tensors only (each pooled gradient reaches exactly one input position -- the one whose raw value this is)
+    if (xmax) *reinterpret_cast<uint4*>(xmax + o) = make_uint4(best[0] ^ flip[0], best[1] ^ flip[1], best[2] ^ flip[2], best[3] ^ flip[3]);
+  }
+}
+
+// PHASE 0 of the stem backward when the forward kept `xmax`: sum g and sum g*xhat over the pooled positions (g = dpool where the
+// ReLU is open, idx != 255; xhat from the raw value at the argmax).  Reads 64 MB instead of the 141 MB of the routed scan.
+__global__ void __launch_bounds__(BT)
+stem_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ xmax,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, int C, size_t total, double* __restrict__ sums) {
+  constexpr int V = 8;
+  const int CV = C / V;
+  const int cv = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CV);
+  pm_pdl_sync();
+  float mu[V], is[V], s0[V], s1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = mean[cv * V + k]; is[k] = invstd[cv * V + k]; s0[k] = s1[k] = 0.f; }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    uint4 D[2], X[2];
+    uint2 I[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t o = (i + u * stride) * V;
+      if (i + u * stride < total) {
+        D[u] = *reinterpret_cast<const uint4*>(dpool + o);
+        X[u] = *reinterpret_cast<const uint4*>(xmax + o);
+        I[u] = *reinterpret_cast<const uint2*>(idx + o);
+      } else {
+        D[u] = X[u] = make_uint4(0, 0, 0, 0);
+        I[u] = make_uint2(0xffffffffu, 0xffffffffu);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float d[V], x[V];
+      bf8_unpack(D[u], d);
+      bf8_unpack(X[u], x);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const uint32_t byte = ((k < 4 ? I[u].x : I[u].y) >> (8 * (k & 3))) & 0xffu;
+        const float g = byte != 255u ? d[k] : 0.f;
+        s0[k] += g;
+        s1[k] = fmaf(g, (x[k] - mu[k]) * is[k], s1[k]);
+      }
+    }
+  }
+  __shared__ float red[2][BT][V + 1];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s0[k]; red[1][threadIdx.x][k] = s1[k]; }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 2 * C; q += BT) {
+    const int which = q / C, ch = q % C, vv = ch / V, kk = ch % V;
+    double acc = 0.0;
+    for (int tdx = vv; tdx < BT; tdx += CV) acc += (double)red[which][tdx][kk];
+    atomicAdd(sums + q, acc);
   }
 }
 
@@ -932,7 +990,7 @@ bn_relu_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const double* __
 // never matches a tap.  PHASE 0: s0 += g, s1 += g * xhat (double atomics per block).  PHASE 1: dx = gamma*invstd *
 // (g - mean(g) - xhat * mean(g*xhat)).
 template <int PHASE>
-__global__ void __launch_bounds__(BT, 2)
+__global__ void __launch_bounds__(BT, 3)
 stem_pool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ idx,
                         const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, double* __restrict__ sums, double invP, int H, int W, int C, size_t total,
@@ -985,30 +1043,53 @@ stem_pool_bn_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* 
 #pragma unroll
     for (int p = 0; p < 4; ++p)
       X[p] = *reinterpret_cast<const uint4*>(x + ((b * H + 2 * k2 + (p >> 1)) * W + 2 * j + (p & 1)) * C + c);
+    // Routing with byte-SIMD compares: the eight argmax bytes of a window are tested against a tap with two __vcmpeq4, each
+    // byte mask is widened to a bf16x2 lane mask with one PRMT and ANDed onto the packed gradients; the (at most four)
+    // contributions of a position are added as packed bf16 (the unfused path rounds the routed gradient to bf16 too).  Nine
+    // (window, tap) pairs: 0->(w0,4) | 1->(w0,5),(w1,3) | 2->(w0,7),(w2,1) | 3->(w0,8),(w1,6),(w2,2),(w3,0)
+    uint32_t G[4][4];  // [position][channel pair] packed bf16x2
+    {
+      auto masked = [&](int w, uint32_t tap, uint32_t (&out)[4]) {
+        const uint32_t t4 = tap * 0x01010101u;
+        const uint32_t mlo = __vcmpeq4(I[w].x, t4), mhi = __vcmpeq4(I[w].y, t4);  // 0xFF per matching channel byte
+        out[0] = D[w].x & __byte_perm(mlo, 0, 0x1100);
+        out[1] = D[w].y & __byte_perm(mlo, 0, 0x3322);
+        out[2] = D[w].z & __byte_perm(mhi, 0, 0x1100);
+        out[3] = D[w].w & __byte_perm(mhi, 0, 0x3322);
+      };
+      auto add2 = [](uint32_t a, uint32_t b2) {
+        const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b2));
+        return *reinterpret_cast<const uint32_t*>(&r);
+      };
+      uint32_t t[4];
+      masked(0, 4, G[0]);
+      masked(0, 5, G[1]); masked(1, 3, t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) G[1][q] = add2(G[1][q], t[q]);
+      masked(0, 7, G[2]); masked(2, 1, t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) G[2][q] = add2(G[2][q], t[q]);
+      masked(0, 8, G[3]); masked(1, 6, t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) G[3][q] = add2(G[3][q], t[q]);
+      masked(2, 2, t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) G[3][q] = add2(G[3][q], t[q]);
+      masked(3, 0, t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) G[3][q] = add2(G[3][q], t[q]);
+    }
     uint4 O[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // channel pair (2kk, 2kk+1)
-      float2 d[4], xv[4];
-      uint32_t id[4];  // the two index bytes of this pair
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t dw = kk == 0 ? D[w].x : kk == 1 ? D[w].y : kk == 2 ? D[w].z : D[w].w;
-        const uint32_t xw = kk == 0 ? X[w].x : kk == 1 ? X[w].y : kk == 2 ? X[w].z : X[w].w;
-        d[w] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw));
-        xv[w] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
-        const uint32_t iw = kk < 2 ? I[w].x : I[w].y;
-        id[w] = (iw >> ((kk & 1) * 16)) & 0xffffu;
-      }
+      float2 xv[4];
       float g[4][2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t i0 = (id[0] >> (8 * h)) & 0xffu, i1 = (id[1] >> (8 * h)) & 0xffu, i2 = (id[2] >> (8 * h)) & 0xffu,
-                       i3 = (id[3] >> (8 * h)) & 0xffu;
-        const float d0 = h ? d[0].y : d[0].x, d1 = h ? d[1].y : d[1].x, d2 = h ? d[2].y : d[2].x, d3 = h ? d[3].y : d[3].x;
-        g[0][h] = i0 == 4 ? d0 : 0.f;
-        g[1][h] = (i0 == 5 ? d0 : 0.f) + (i1 == 3 ? d1 : 0.f);
-        g[2][h] = (i0 == 7 ? d0 : 0.f) + (i2 == 1 ? d2 : 0.f);
-        g[3][h] = (i0 == 8 ? d0 : 0.f) + (i1 == 6 ? d1 : 0.f) + (i2 == 2 ? d2 : 0.f) + (i3 == 0 ? d3 : 0.f);
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t xw = kk == 0 ? X[w].x : kk == 1 ? X[w].y : kk == 2 ? X[w].z : X[w].w;
+        xv[w] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw));
+        const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&G[w][kk]));
+        g[w][0] = gf.x; g[w][1] = gf.y;
       }
       if (PHASE == 0) {
 #pragma unroll
@@ -1362,7 +1443,7 @@ int pm_bn_bwd_fused_xmask_bf16(const void* dy, const void* x, const float* mean,
 }
 
 int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H, int W, int C, float eps, float momentum,
-                                const float* gamma, const float* beta, void* y, uint8_t* idx, float* mean, float* invstd,
+                                const float* gamma, const float* beta, void* y, uint8_t* idx, void* xmax, float* mean, float* invstd,
                                 float* running_mean, float* running_var, pm_stream_t s) {
   PM_CHECK_ARG(x && stats && gamma && beta && y && idx && mean && invstd && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
   PM_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
@@ -1371,19 +1452,23 @@ int pm_bn_relu_maxpool_fwd_bf16(const void* x, const double* stats, int B, int H
   PM_CHECK_ARG(BT % (C / 8) == 0);
   PM_CUDA(pm_launch(bn_relu_maxpool_fwd_kernel, dim3(pm_grid(total, BT, 1, 16)), dim3(BT), 3 * C * sizeof(float), S(s), (const bf16*)x, stats,
                     (double)B * H * W, eps, momentum, mean, invstd, running_mean, running_var, gamma, beta, H, W, C, Ho, Wo, total,
-                    (bf16*)y, idx));
+                    (bf16*)y, idx, (bf16*)xmax));
   PM_LAUNCH_OK();
 }
 
-int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, int B, int H, int W, const void* x, const float* mean,
-                             const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
+int pm_stem_pool_bn_bwd_bf16(const void* dpool, const uint8_t* pool_idx, const void* xmax, int B, int H, int W, const void* x,
+                             const float* mean, const float* invstd, const float* gamma, int C, double* sums, void* dx, float* dgamma,
                              float* dbeta, pm_stream_t s) {
   PM_CHECK_ARG(dpool && pool_idx && x && mean && invstd && gamma && sums && dx && B > 0 && H > 0 && W > 0);
   PM_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && BT % (C / 8) == 0 && ((dgamma == nullptr) == (dbeta == nullptr)));
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
   const int grid = pm_grid(total, BT, 1, 8);
   const double invP = 1.0 / ((double)B * H * W);
-  PM_CUDA(pm_launch(stem_pool_bn_bwd_kernel<0>, dim3(grid), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd,
+  if (xmax)
+    PM_CUDA(pm_launch(stem_pool_reduce_kernel, dim3(pm_grid(total, BT, 2, 8)), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx,
+                      (const bf16*)xmax, mean, invstd, C, total, sums));
+  else
+    PM_CUDA(pm_launch(stem_pool_bn_bwd_kernel<0>, dim3(grid), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd,
                     gamma, sums, invP, H, W, C, total, (bf16*)nullptr, (float*)nullptr, (float*)nullptr));
   PM_CUDA(pm_launch(stem_pool_bn_bwd_kernel<1>, dim3(grid), dim3(BT), 0, S(s), (const bf16*)dpool, pool_idx, (const bf16*)x, mean, invstd,
                     gamma, sums, invP, H, W, C, total, (bf16*)dx, dgamma, dbeta));

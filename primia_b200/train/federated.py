@@ -57,15 +57,21 @@ class HospitalWorker:
             self._pending = None
             torch.cuda.current_stream(eng.device).wait_event(self._ready[slot])
             data, target = self._stage[slot]
-        with torch.cuda.device(eng.device):
-            loss = eng.train_step_overlapped(
-                data, target,
-                lambda: works.append(dist.all_reduce(eng.flat[off:], op=dist.ReduceOp.AVG, group=group, async_op=True)),
-                lambda: works.append(dist.all_reduce(eng.flat[:off], op=dist.ReduceOp.AVG, group=group, async_op=True)))
-            if host:
+
+            def staged():
                 ev = torch.cuda.Event()
                 ev.record()
                 self._consumed[slot] = ev
+
+            eng.on_inputs_staged = staged
+        with torch.cuda.device(eng.device):
+            try:
+                loss = eng.train_step_overlapped(
+                    data, target,
+                    lambda: works.append(dist.all_reduce(eng.flat[off:], op=dist.ReduceOp.AVG, group=group, async_op=True)),
+                    lambda: works.append(dist.all_reduce(eng.flat[:off], op=dist.ReduceOp.AVG, group=group, async_op=True)))
+            finally:
+                eng.on_inputs_staged = None
             for w in works:
                 w.wait()   # stream-level wait: the next kernels on this stream see the averaged state
         return loss
@@ -110,10 +116,20 @@ class HospitalWorker:
         self._pending = None
         with torch.cuda.device(eng.device):
             torch.cuda.current_stream().wait_event(self._ready[slot])
-            loss = self.local_step(self._stage[slot][0], self._stage[slot][1])
-            ev = torch.cuda.Event()
-            ev.record()
-            self._consumed[slot] = ev
+            self._consumed[slot] = None
+
+            def staged():   # graph replays copy the batch into their static input first: the slot is free from then on
+                ev = torch.cuda.Event()
+                ev.record()
+                self._consumed[slot] = ev
+
+            eng.on_inputs_staged = staged
+            try:
+                loss = self.local_step(self._stage[slot][0], self._stage[slot][1])
+            finally:
+                eng.on_inputs_staged = None
+            if self._consumed[slot] is None:   # eager step: the stem reads the batch until the end of the backward pass
+                staged()
         return loss
 
 

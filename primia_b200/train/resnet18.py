@@ -79,6 +79,7 @@ class ResNet18Engine:
         self._side = None
         self._split_cb = None
         self._graph2 = None
+        self.on_inputs_staged = None
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -175,6 +176,8 @@ class ResNet18Engine:
         self.act["a1"] = A(B, c1.Ho, c1.Wo, 64)
         self.act["p1"] = A(B, self.pool_out, self.pool_out, 64)
         self.pool_idx = torch.empty((B, self.pool_out, self.pool_out, 64), dtype=torch.uint8, device=dev)
+        # raw conv1 output at each pooling window's argmax (fused stem pool, bf16 mode): the stem's BN backward sums read it
+        self.stem_xmax = torch.empty((B, self.pool_out, self.pool_out, 64), dtype=adt, device=dev) if self.mode == "bf16" else None
         for pre, ca, cb, ds in self.blocks:
             self.act[ca.name] = A(B, ca.Ho, ca.Wo, ca.K)
             self.act[pre + ".a"] = A(B, ca.Ho, ca.Wo, ca.K)
@@ -423,6 +426,10 @@ class ResNet18Engine:
         if tuple(x_nchw.shape) != (self.B, self.cin, self.size, self.size):
             raise PrimiaError(f"expected input {(self.B, self.cin, self.size, self.size)}, got {tuple(x_nchw.shape)}")
         x_nchw = x_nchw.contiguous()
+        if x_nchw.dtype == torch.bfloat16:
+            # a loader may stage the batch as bf16 (half the PCIe bytes): in bf16 mode the stem rounds every pixel to bf16 anyway,
+            # so the step is bit-identical to shipping fp32; the expansion is a device-side copy
+            x_nchw = x_nchw.float()
         if self.mode == "f32":
             call("pm_nchw_to_nhwc_f32", ptr(x_nchw), self.B, self.cin, self.size, self.size, ptr(self.x0), stream())
         elif self.direct_stem:
@@ -467,7 +474,7 @@ class ResNet18Engine:
                 e0 = self._prof_begin("stem_bn_pool")
                 call("pm_bn_relu_maxpool_fwd_bf16", ptr(self.act["conv1"]), ptr(self._stat_slot(bn_ids["bn1"])), self.B, c1.Ho,
                      c1.Wo, 64, ctypes.c_float(self.BN_EPS), ctypes.c_float(self.BN_MOMENTUM), ptr(self.p["bn1.weight"]),
-                     ptr(self.p["bn1.bias"]), ptr(self.act["p1"]), ptr(self.pool_idx), ptr(self.bn_mean["bn1"]),
+                     ptr(self.p["bn1.bias"]), ptr(self.act["p1"]), ptr(self.pool_idx), ptr(self.stem_xmax), ptr(self.bn_mean["bn1"]),
                      ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.running_mean"]), ptr(self.p["bn1.running_var"]), stream())
                 self._prof_end(e0)
             else:
@@ -560,7 +567,8 @@ class ResNet18Engine:
                 # the argmax table already encodes the ReLU decision (255 = no gradient): neither the 112x112 activation nor a
                 # full-resolution gradient is ever materialised; reduce + apply launches over 2x2 input blocks
                 e0 = self._prof_begin("stem_bn_pool")
-                call("pm_stem_pool_bn_bwd_bf16", ptr(d_out), ptr(self.pool_idx), self.B, c1.Ho, c1.Wo, ptr(self.act["conv1"]),
+                call("pm_stem_pool_bn_bwd_bf16", ptr(d_out), ptr(self.pool_idx), ptr(self.stem_xmax), self.B, c1.Ho, c1.Wo,
+                     ptr(self.act["conv1"]),
                      ptr(self.bn_mean["bn1"]), ptr(self.bn_invstd["bn1"]), ptr(self.p["bn1.weight"]), 64,
                      ptr(self._stat_slot(len(self.bns) + bn_ids["bn1"])), ptr(dc1), ptr(self.g["bn1.weight"]),
                      ptr(self.g["bn1.bias"]), stream())
@@ -642,8 +650,10 @@ class ResNet18Engine:
         gr = self._graph
         if (gr is not None and gr["step"] == self.step_count + 1 and gr["tdtype"] == target.dtype
                 and gr["hyper"] == self._hyper_key()):
-            gr["x"].copy_(x_nchw, non_blocking=True)
+            gr["x"].copy_(x_nchw, non_blocking=True)   # (also expands a bf16-staged batch to the fp32 the stem's TMA boxes read)
             gr["y"].copy_(target, non_blocking=True)
+            if self.on_inputs_staged is not None:
+                self.on_inputs_staged()                # the caller's staging slot is free again: the next H2D copy may start
             gr["graph"].replay()
             self.step_count += 1
             return self.loss
@@ -741,6 +751,8 @@ class ResNet18Engine:
                               "hyper-parameters)")
         gr["x"].copy_(x_nchw, non_blocking=True)
         gr["y"].copy_(target, non_blocking=True)
+        if self.on_inputs_staged is not None:
+            self.on_inputs_staged()
         gr["A"].replay()
         after_a()
         gr["B"].replay()

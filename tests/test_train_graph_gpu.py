@@ -163,6 +163,21 @@ def test_local_step_host_equals_local_step():
                           f"host-fed step {i}")
 
 
+def test_bf16_staged_batch_gives_the_identical_step():
+    """bench.py's e2e leg ships bf16 pixels over PCIe: in bf16 mode the stem rounds every pixel to bf16 before its MMA, so a batch
+    staged as bf16 and the same batch shipped as fp32 (already bf16-representable or not) give the bit-identical forward"""
+    B, size = 16, 96
+    torch.manual_seed(42)
+    sd = O.ResNet18(input_size=size).state_dict()
+    (x, y), = _batches(B, size, 1)
+    a, b = _engine(B, size, sd), _engine(B, size, sd)
+    la = a.train_step(x.to(DEV), y.to(DEV)).item()                      # fp32 pixels, rounded inside the stem
+    lb = b.train_step(x.bfloat16().to(DEV), y.to(DEV)).item()           # the loader already rounded them
+    torch.cuda.synchronize()
+    assert la == lb and torch.equal(a.act["conv1"], b.act["conv1"]) and torch.equal(a.logits, b.logits)
+    assert rel(b.grads, a.grads) < 1e-5
+
+
 _WORKER = r"""
 import sys, torch
 sys.path.insert(0, {root!r})
