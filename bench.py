@@ -27,6 +27,22 @@ GFLOP_PER_IMAGE = 10.645  # fwd + bwd conv/fc work, SURVEY.md section 8d (5.3227
 METRIC = "federated_round_images_per_sec"
 
 
+def conv_traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step, from the committed ncu launch list of
+    this very command (profiles/r02_launches_one_step.csv, written by scripts/ncu_r02.sh + scripts/ncu_extract.py)"""
+    import csv
+
+    p = os.path.join(ROOT, "profiles", "r02_launches_one_step.csv")
+    if not os.path.exists(p):
+        return None, "no ncu launch list committed"
+    tot, n = 0.0, 0
+    for r in csv.DictReader(open(p)):
+        if any(k in r["kernel"] for k in ("conv_halo_kernel", "conv_tma_kernel", "wgrad_", "stem::stem_kernel", "dgrad_s2")):
+            tot += float(r["dram_read_MB"]) + float(r["dram_write_MB"])
+            n += 1
+    return tot * 1e6, f"profiles/r02_launches_one_step.csv: {n} conv launches of one step (B = 64); ncu does not attribute the write-back of a kernel's outputs to it, so this is mostly operand reads; algorithmic operand + output bytes ~1.6 GB"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -532,13 +548,12 @@ def run_ours(args):
     achieved = GFLOP_PER_IMAGE * B / conv_ms  # GFLOP / ms == TFLOP/s
     roof = {"bound": "tensor", "kernel": "conv family, tcgen05/TMEM implicit GEMMs: halo::conv_halo_kernel (3x3/s1 fwd + dgrad, one TMA strip "
                                          "serves all 9 taps), stem::stem_kernel (7x7/s2 fwd + wgrad straight from the fp32 NCHW batch), "
-                                         "tma::conv_tma_kernel / dgrad_s2_tma_kernel (1x1 and stride-2), tma::wgrad_tma_kernel: "
-                                         "20 fwd + 19 dgrad + 20 wgrad launches per step",
+                                         "tma::conv_tma_kernel / s2p::dgrad_s2_kernel (1x1 and stride-2), wgh::wgrad_halo_kernel + "
+                                         "tma::wgrad_tma_kernel: 20 fwd + 19 dgrad + 20 wgrad launches per step",
             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
-            "traffic": 1.320e9 if args.mode == "bf16" and B == 64 else None,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 59 conv launches of one step, ncu pass "
-                            "profiles/r01b_launch_summary.csv (1.274 GB read + 0.046 GB written; write-back of the outputs is not "
-                            "attributed to the producing kernel by ncu); algorithmic operand + output bytes ~1.6 GB",
+            "frac_of_burst_peak": achieved / pk["bf16_tflops"],
+            "traffic": conv_traffic_from_profile()[0] if args.mode == "bf16" and B == 64 else None,
+            "traffic_note": conv_traffic_from_profile()[1],
             "conv_ms_per_step": conv_ms, "conv_ms_by_kind": getattr(eng, "conv_ms_by_kind", None),
             "step_ms_by_family": getattr(eng, "step_ms_by_family", None),
             "step_share": conv_ms / (ms / args.steps),

@@ -533,7 +533,7 @@ __device__ __forceinline__ uint4 bf8_pack(const float (&v)[8]) {
 
 // bf16 BatchNorm forward apply (training; mean / invstd finalised from the batch statistics in the prologue exactly as
 // bn_apply_kernel<T, true> does): y = act((x - mu) * (invstd * gamma) + beta (+ residual)), four raw 16-byte rows in flight.
-__global__ void __launch_bounds__(BT, 2)
+__global__ void __launch_bounds__(BT, 3)
 bn_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats, double Pd, float eps, float momentum,
                    float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ rm, float* __restrict__ rv,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const __nv_bfloat16* __restrict__ res, int relu,
@@ -1243,7 +1243,7 @@ int bn_fwd_fused_t(const T* x, const double* stats, size_t P, int C, float eps, 
     if (!bn_bwd_generic()) {
       typedef __nv_bfloat16 b16;
       int grid = row_grid<T>(P, C, 8);
-      if (grid > 2 * pm_num_sms()) grid = 2 * pm_num_sms();
+      if (grid > 3 * pm_num_sms()) grid = 3 * pm_num_sms();   // three resident blocks per SM (<= 85 registers)
       PM_CUDA(pm_launch(bn_fwd_bf16_kernel, dim3(grid), dim3(BT), 3 * C * sizeof(float), S(s), (const b16*)x, stats, (double)P, eps, momentum,
                         mean, invstd, rm, rv, gamma, beta, (const b16*)res, relu, P, C, (b16*)y));
       PM_LAUNCH_OK();
