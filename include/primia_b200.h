@@ -38,11 +38,14 @@ int pm_encode_f32_i64(const float* x, float scale, int64_t* q, size_t n, int* ov
 int pm_decode_i64_f32(const int64_t* q, float scale, float* x, size_t n, pm_stream_t s);
 
 /* AdditiveSharingTensor.generate_shares (n_workers == 2)  additive_shared.py:336-365
- * s0 ~ Philox4x32-10(seed, offset) over [-2^63, 2^63-2]; s1 = q - s0 (wraps). */
-int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, int64_t* s0, int64_t* s1, size_t n,
+ * s0 ~ Philox4x32-10(seed, offset) over [-2^63, 2^63-2]; s1 = q - s0 (wraps).
+ * epoch (device uint64, may be NULL): the stream actually used is offset + (*epoch << 32) -- a generation captured in a CUDA
+ * graph then draws fresh randomness at every replay once a pm_epoch_bump node precedes it. */
+int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, const uint64_t* epoch, int64_t* s0, int64_t* s1, size_t n,
                      pm_stream_t s);
 /* randint(-2^63, 2^63-1) of build_triple  syft/frameworks/torch/mpc/beaver.py:32-34 */
-int pm_random_i64(uint64_t seed, uint64_t offset, int64_t* out, size_t n, pm_stream_t s);
+int pm_random_i64(uint64_t seed, uint64_t offset, const uint64_t* epoch, int64_t* out, size_t n, pm_stream_t s);
+int pm_epoch_bump(uint64_t* epoch, pm_stream_t s);
 
 /* _pre_conv im2col  syft/frameworks/torch/nn/functional.py:79-166 (groups==1)
  * x [B,C,H,W] -> im [B, M=Ho*Wo, K=C*kh*kw], k = ch*kh*kw + r*kw + c, zero padding. */

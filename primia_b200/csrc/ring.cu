@@ -52,9 +52,14 @@ __device__ __forceinline__ int64_t clamp_share_range(u64 r) {
   return v == INT64_MAX ? (int64_t)0 : v;
 }
 
+__global__ void epoch_bump_kernel(unsigned long long* e) { *e += 1ull; }
+
+// `epoch` (device uint64, may be NULL): added to the high half of the Philox offset, so that a CAPTURED generation graph draws a
+// fresh stream at every replay (the host-side offset is baked into the launch; the epoch is bumped by a node of the graph).
 template <bool SHARE>
-__global__ void philox_kernel(const int64_t* __restrict__ q, u64 seed, u64 offset, int64_t* __restrict__ s0,
-                              int64_t* __restrict__ s1, size_t n) {
+__global__ void philox_kernel(const int64_t* __restrict__ q, u64 seed, u64 offset, const unsigned long long* __restrict__ epoch,
+                              int64_t* __restrict__ s0, int64_t* __restrict__ s1, size_t n) {
+  if (epoch) offset += (u64)(*epoch) << 32;
   size_t pairs = (n + 1) / 2;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -554,18 +559,24 @@ int pm_decode_i64_f32(const int64_t* q, float scale, float* x, size_t n, pm_stre
   PM_LAUNCH_OK();
 }
 
-int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, int64_t* s0, int64_t* s1, size_t n,
+int pm_share_gen_i64(const int64_t* q, uint64_t seed, uint64_t offset, const uint64_t* epoch, int64_t* s0, int64_t* s1, size_t n,
                      pm_stream_t s) {
   if (n == 0) return PM_OK;
   PM_CHECK_ARG(q && s0 && s1);
-  philox_kernel<true><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(q, seed, offset, s0, s1, n);
+  philox_kernel<true><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(q, seed, offset, (const unsigned long long*)epoch, s0, s1, n);
   PM_LAUNCH_OK();
 }
 
-int pm_random_i64(uint64_t seed, uint64_t offset, int64_t* out, size_t n, pm_stream_t s) {
+int pm_random_i64(uint64_t seed, uint64_t offset, const uint64_t* epoch, int64_t* out, size_t n, pm_stream_t s) {
   if (n == 0) return PM_OK;
   PM_CHECK_ARG(out);
-  philox_kernel<false><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(nullptr, seed, offset, out, nullptr, n);
+  philox_kernel<false><<<pm_grid((n + 1) / 2, 256), 256, 0, S(s)>>>(nullptr, seed, offset, (const unsigned long long*)epoch, out, nullptr, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_epoch_bump(uint64_t* epoch, pm_stream_t s) {
+  PM_CHECK_ARG(epoch);
+  epoch_bump_kernel<<<1, 1, 0, S(s)>>>((unsigned long long*)epoch);
   PM_LAUNCH_OK();
 }
 

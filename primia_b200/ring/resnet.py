@@ -241,22 +241,71 @@ class EncryptedResNet18:
         return out, out.argmax(dim=1)
 
 
-class EncryptedInferenceGraph:
-    """The ONLINE phase of one encrypted image (share input -> forward on shares -> reconstruct -> decode) captured once in a
-    CUDA graph: ~1.4 k launches of mostly tiny kernels are launch-bound when issued eagerly from Python.  Every primitive the
-    forward consumes (Beaver triples, FSS keys, sharings of the Newton constant) lives in static buffers; ``offline()`` has
-    the crypto provider generate a fresh set and copies it over them, ``online(img)`` is one graph replay.  The crypto-store
-    bookkeeping (peek / pop, primitives.py:52-102) runs on the host at capture time.
+class _MultiDeviceCapture:
+    """Capture ``fn()`` into ONE CUDA graph that spans several GPUs.  The capture runs on ``devices[0]``; every other device
+    gets (a) a private memory pool that lives as long as the graph (replays reuse the addresses) and (b) a capturable side
+    stream, forked from the capture stream by an event and made that device's current stream for the duration, joined again
+    before the capture ends.  Cross-device edges inside ``fn`` are ordinary event waits between the devices' current streams."""
 
-    Placement (SURVEY.md section 8e): with the two share holders on different GPUs (model_owner cuda:0, data_owner cuda:1,
-    crypto provider cuda:2) the capture is ONE multi-device graph: the second party's stream is forked from the capture stream
-    with an event, every opening is a kernel on the consuming GPU that loads the peer's share through its peer-mapped pointer
-    behind a cross-stream event edge, and the stream joins again before the capture ends.  Each party's FSS evaluation -- the
-    dominant cost -- then runs on its own GPU concurrently with the other's."""
+    def __init__(self, devices):
+        self.devices = list(devices)
+        self.graph = torch.cuda.CUDAGraph()
+        self.pools = {d: torch.cuda.MemPool() for d in self.devices[1:]}
+        self.streams = {d: torch.cuda.Stream(d) for d in self.devices[1:]}
 
-    def __init__(self, net: EncryptedResNet18, example: torch.Tensor):
+    def capture(self, fn):
         import contextlib
 
+        dev, others = self.devices[0], self.devices[1:]
+        with contextlib.ExitStack() as es:
+            for d in others:
+                es.enter_context(torch.cuda.use_mem_pool(self.pools[d], device=d))
+            with torch.cuda.device(dev), torch.cuda.graph(self.graph, capture_error_mode="relaxed" if others else "global"):
+                main = torch.cuda.current_stream(dev)
+                prev = {}
+                for d in others:
+                    prev[d] = torch.cuda.current_stream(d)
+                    self.streams[d].wait_stream(main)          # fork: the stream joins the capture
+                    with torch.cuda.device(d):
+                        torch.cuda.set_stream(self.streams[d])
+                try:
+                    out = fn()
+                finally:
+                    for d in others:
+                        main.wait_stream(self.streams[d])      # join
+                        with torch.cuda.device(d):
+                            torch.cuda.set_stream(prev[d])
+        return out
+
+    def replay(self):
+        dev = self.devices[0]
+        for d in self.devices[1:]:                              # the replay (launched on dev) must see the other GPUs' pending work
+            torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
+        with torch.cuda.device(dev):
+            self.graph.replay()
+        for d in self.devices[1:]:                              # ... and their later work must see the replay's results
+            torch.cuda.current_stream(d).wait_stream(torch.cuda.current_stream(dev))
+
+
+class EncryptedInferenceGraph:
+    """One encrypted image as TWO CUDA-graph replays:
+
+      offline()    the crypto provider regenerates every primitive the forward consumes -- 8.85 GB of Beaver triples, FSS keys
+                   and sharings of the Newton constant -- IN PLACE: the generating launches (Philox, ring GEMM c = a@b, DIF
+                   keygen) were captured once, their output tensors are the graph's own allocations, and a device-side epoch
+                   added to every Philox offset (pm_epoch_bump is the graph's first node) makes each replay draw fresh
+                   randomness.  No host bookkeeping, no staging copy.
+      online(img)  share input -> forward on shares -> reconstruct -> decode: ~1.4 k launches of mostly tiny kernels that are
+                   launch-bound when issued eagerly from Python.  The crypto-store bookkeeping (peek / pop,
+                   primitives.py:52-102) ran on the host at capture time.
+
+    Placement (SURVEY.md section 8e): with the two share holders on different GPUs (model_owner cuda:0, data_owner cuda:1,
+    crypto provider cuda:2) both graphs are multi-device graphs: every opening is a kernel on the consuming GPU that loads the
+    peer's share through its peer-mapped pointer behind a cross-stream event edge, the provider's primitives travel to the
+    parties as peer copies, and each party's FSS evaluation -- the dominant cost -- runs on its own GPU concurrently with the
+    other's."""
+
+    def __init__(self, net: EncryptedResNet18, example: torch.Tensor):
         self.net = net
         dev = net.parties[0].device
         others = []
@@ -264,99 +313,74 @@ class EncryptedInferenceGraph:
             if p.device != dev and p.device not in others:
                 others.append(p.device)
         self.devices = [dev] + others
+        pdev = net.provider.provider.device
+        self.off_devices = [pdev] + [d for d in self.devices if d != pdev]
         assert net.rng is not None, "build the model with from_state_dict (it owns the share RNG)"
         x = net.share_input(example)
-        net.trace(x)                                   # warm-up + primitive schedule
+        net.trace(x)                                   # warm-up + primitive schedule (primitives on demand, consumed)
         self.x_static = x
+        # a recording pass: which constants get freshly shared during a forward (additive_shared.py:473-487), into static buffers
         net.preprocess(1)
-        self.static_state = [p.crypto_store.export_state() for p in net.parties]
-        self.static_tensors = self._unique(self.static_state)
         self._sync()
         net.rng.mode, net.rng.static = "record", []
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            net.forward(x)                             # consumes the static primitives once; records the constant sharings
+            net.forward(x)
         torch.cuda.current_stream(dev).wait_stream(side)
         self._sync()
-        for p, st in zip(net.parties, self.static_state):
-            p.crypto_store.import_state(st)
+        net.rng.mode = "live"
+        for p in net.parties:
+            p.crypto_store.clear()
+        # ---- offline graph: generation straight into the tensors the online graph will read
+        b0 = net.provider.generated_bytes
+        self._off = _MultiDeviceCapture(self.off_devices)
+
+        def generate():
+            for d in self.off_devices:
+                ops.bump_epoch(d)
+            net.preprocess(1)
+            net.rng.refresh_static()
+
+        self._off.capture(generate)
+        self.bytes_per_image = net.provider.generated_bytes - b0
+        self.static_state = [p.crypto_store.export_state() for p in net.parties]
+        self._off.replay()                             # the capture itself executed nothing: fill the buffers once
+        self._sync()
+        # ---- online graph
         net.rng.mode, net.rng.cursor = "replay", 0
         from .. import _lib
 
         l0 = _lib.launch_counter
-        self.graph = torch.cuda.CUDAGraph()
-        # other devices: their allocations during the capture go to private pools that live as long as the graph (the replay
-        # reuses the addresses), and their current stream becomes a capturable (non-default) stream forked from the capture
-        self._pools = {d: torch.cuda.MemPool() for d in others}
-        self._streams = {d: torch.cuda.Stream(d) for d in others}
-        with contextlib.ExitStack() as es:
-            for d in others:
-                es.enter_context(torch.cuda.use_mem_pool(self._pools[d], device=d))
-            with torch.cuda.device(dev), torch.cuda.graph(self.graph, capture_error_mode="relaxed" if others else "global"):
-                main = torch.cuda.current_stream(dev)
-                prev = {}
-                for d in others:
-                    prev[d] = torch.cuda.current_stream(d)
-                    self._streams[d].wait_stream(main)         # fork: the stream joins the capture
-                    with torch.cuda.device(d):
-                        torch.cuda.set_stream(self._streams[d])
-                try:
-                    self.out_shares = net.forward(x)
-                    self.logits = self.out_shares.get().float_prec()
-                finally:
-                    for d in others:
-                        main.wait_stream(self._streams[d])     # join
-                        with torch.cuda.device(d):
-                            torch.cuda.set_stream(prev[d])
+        self._on = _MultiDeviceCapture(self.devices)
+
+        def forward():
+            self.out_shares = net.forward(x)
+            self.logits = self.out_shares.get().float_prec()
+
+        self._on.capture(forward)
+        self.graph = self._on.graph
         self.kernels_in_graph = _lib.launch_counter - l0
         net.rng.mode = "live"
         for p in net.parties:
             p.crypto_store.clear()
 
     def _sync(self):
-        for d in self.devices:
+        for d in set(self.devices) | set(self.off_devices):
             torch.cuda.synchronize(d)
 
-    @staticmethod
-    def _unique(states):
-        """one uint8 view per distinct allocation behind the primitives of both parties, in deterministic order"""
-        from .spdz import PrimitiveStorage
-
-        seen, out = set(), []
-        for st in states:
-            for t in PrimitiveStorage.state_tensors(st):
-                stor = t.untyped_storage()
-                if stor.data_ptr() not in seen:
-                    seen.add(stor.data_ptr())
-                    out.append(torch.empty(0, dtype=torch.uint8, device=t.device).set_(stor))
-        return out
-
     def offline(self):
-        """fresh triples, FSS keys and constant sharings for the next image, written into the static buffers"""
-        net = self.net
-        net.preprocess(1)
-        fresh_state = [p.crypto_store.export_state() for p in net.parties]
-        fresh = self._unique(fresh_state)
-        assert len(fresh) == len(self.static_tensors)
-        for dst, src in zip(self.static_tensors, fresh):
-            dst.copy_(src, non_blocking=True)
-        dev = self.devices[0]
-        for d in self.devices[1:]:
-            torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
-        for p in net.parties:
-            p.crypto_store.clear()
-        net.rng.mode = "live"
-        net.rng.refresh_static()
+        """fresh triples, FSS keys and constant sharings for the next image: one replay of the generation graph"""
+        self._off.replay()
+        for d in self.devices:                          # the online replay (launched on devices[0]) must see the new primitives
+            if d != self.off_devices[0]:
+                torch.cuda.current_stream(d).wait_stream(torch.cuda.current_stream(self.off_devices[0]))
+        self.net.provider.generated_bytes += self.bytes_per_image
 
     def online(self, img: torch.Tensor):
         """inference.py:307-317 for one image: returns (logits, argmax) -- device tensors owned by the graph"""
         s = self.net.share_input(img)
         for dst, src in zip(self.x_static.child.child, s.child.child):
             dst.copy_(src, non_blocking=True)
-        dev = self.devices[0]
-        for d in self.devices[1:]:                      # the replay (launched on dev) must see the other GPUs' pending copies
-            torch.cuda.current_stream(dev).wait_stream(torch.cuda.current_stream(d))
-        with torch.cuda.device(dev):
-            self.graph.replay()
+        self._on.replay()
         return self.logits, self.logits.argmax(dim=1)

@@ -186,8 +186,7 @@ class TripleProvider:
                 k = keys[j] if p.device == self.provider.device else keys[j].to(p.device)
                 self.generated_bytes += k.nbytes()
                 p.crypto_store.add_fss_keys(k)
-            if any(p.device != self.provider.device for p in parties):
-                torch.cuda.synchronize(self.provider.device)
+            self._settle(parties)
             return
         if op == "mul" and n_instances > 1 and tuple(shapes[0]) == tuple(shapes[1]):
             # build_triple with a leading n_instances axis (beaver.py:23-31), split into per-instance views
@@ -207,7 +206,13 @@ class TripleProvider:
                 moved = tuple(t.to(p.device, non_blocking=True) for t in tri[j])
                 self.generated_bytes += sum(t.numel() * 8 for t in moved)
                 p.crypto_store.add_primitives(op, shapes, [moved])
-        if any(p.device != self.provider.device for p in parties):
+        self._settle(parties)
+
+    def _settle(self, parties):
+        """the freshly generated tensors die on the provider's GPU as soon as this returns; the copies to the parties must have
+        read them first.  (Inside a CUDA-graph capture the copies are graph nodes ordered before anything that reuses the
+        memory, and a device synchronisation would be illegal.)"""
+        if any(p.device != self.provider.device for p in parties) and not torch.cuda.is_current_stream_capturing():
             torch.cuda.synchronize(self.provider.device)
 
 

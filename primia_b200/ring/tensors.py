@@ -40,9 +40,7 @@ class ShareRNG:
     def refresh_static(self):
         for q, s0, s1 in self.static:
             self.counter += 1
-            n0, n1 = ops.share_gen(q, self.seed, self.counter)
-            s0.copy_(n0)
-            s1.copy_(n1)
+            ops.share_gen(q, self.seed, self.counter, out=(s0, s1))   # straight into the static buffers
         self.cursor = 0
 
 
