@@ -313,7 +313,7 @@ def encrypted_inference_block(steps=3, devs=None, label=None):
             if it >= 2:                                             # two warm-up images (allocator growth)
                 off.append(e[0].elapsed_time(e[1]))
                 on.append(e[1].elapsed_time(e[2]))
-    gb = prov.generated_bytes / (steps + 4) / 1e9
+    gb = eg.bytes_per_image / 1e9
     launches = eg.kernels_in_graph
     del eg, net, parties, prov
     torch.cuda.empty_cache()
