@@ -252,6 +252,9 @@ class _MultiDeviceCapture:
         self.graph = torch.cuda.CUDAGraph()
         self.pools = {d: torch.cuda.MemPool() for d in self.devices[1:]}
         self.streams = {d: torch.cuda.Stream(d) for d in self.devices[1:]}
+        # torch.cuda.graph's default capture stream is a process-wide singleton living on whichever device captured first:
+        # a capture on another GPU must bring its own stream or nothing is recorded
+        self.capture_stream = torch.cuda.Stream(self.devices[0])
 
     def capture(self, fn):
         import contextlib
@@ -260,7 +263,8 @@ class _MultiDeviceCapture:
         with contextlib.ExitStack() as es:
             for d in others:
                 es.enter_context(torch.cuda.use_mem_pool(self.pools[d], device=d))
-            with torch.cuda.device(dev), torch.cuda.graph(self.graph, capture_error_mode="relaxed" if others else "global"):
+            with torch.cuda.device(dev), torch.cuda.graph(self.graph, stream=self.capture_stream,
+                                                          capture_error_mode="relaxed" if others else "global"):
                 main = torch.cuda.current_stream(dev)
                 prev = {}
                 for d in others:
