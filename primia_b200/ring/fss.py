@@ -148,13 +148,13 @@ def slice_lastdim(t, start, length):
 
 
 # ------------------------------------------------------------------------------------------ provider side
-def build_fss_keys(n_instances: int, device, seed: int, counter: int):
+def build_fss_keys(n_instances: int, device, seed: int, counter: int, epoch=None):
     """build_separate_fss_keys (primitives.py:237-253): DIF.keygen on the crypto provider's GPU from Philox randomness,
     alpha split additively mod 2^32.  Returns [keys of party 0, keys of party 1] (sharing the correction words)."""
     n = int(n_instances)
-    alpha = ops.random_i64((n,), seed, counter, device)
-    mask = ops.random_i64((n,), seed, counter + 1, device)
-    seeds = ops.random_i64((2, 2, n), seed, counter + 2, device)
+    alpha = ops.random_i64((n,), seed, counter, device, epoch)
+    mask = ops.random_i64((n,), seed, counter + 1, device, epoch)
+    seeds = ops.random_i64((2, 2, n), seed, counter + 2, device, epoch)
     alpha0 = torch.empty((n,), dtype=torch.int64, device=device)
     with torch.cuda.device(device):
         call("pm_fss_condition_randomness", ptr(alpha), ptr(mask), ptr(seeds), ptr(alpha0), n, stream())

@@ -16,7 +16,7 @@ I64 = torch.int64
 __all__ = [
     "encode", "decode", "share_gen", "random_i64", "im2col", "mask", "mask_im2col", "mask_wt", "open_add",
     "combine_matmul", "combine_mul", "matmul", "trunc_div", "trunc_post_conv", "axpby", "avgpool",
-    "nchw_to_pc", "pc_to_nchw", "conv_out_size", "stack", "bn_newton_fused", "bn_newton_p2p", "philox_epoch", "bump_epoch",
+    "nchw_to_pc", "pc_to_nchw", "conv_out_size", "stack", "bn_newton_fused", "bn_newton_p2p", "new_epoch", "bump_epoch",
 ]
 
 
@@ -54,39 +54,31 @@ def decode(q: torch.Tensor, base: int = 10, precision_fractional: int = 16):
     return x
 
 
-_EPOCH = {}
+def new_epoch(device):
+    """a device-side Philox epoch (uint64, starts at 0) owned by ONE generator: its value is added to the high half of every
+    offset that generator uses, and ``bump_epoch`` advances it with a kernel -- so a generation captured in a CUDA graph draws a
+    fresh stream at every replay while staying a pure function of (seed, number of bumps)"""
+    return torch.zeros(1, dtype=I64, device=torch.device(device))
 
 
-def philox_epoch(device):
-    """per-GPU device-side epoch added to every Philox offset on that GPU (0 until a captured generation graph bumps it)"""
-    device = torch.device(device)
-    t = _EPOCH.get(device)
-    if t is None:
-        t = _EPOCH[device] = torch.zeros(1, dtype=I64, device=device)
-    return t
+def bump_epoch(epoch):
+    with torch.cuda.device(epoch.device):
+        call("pm_epoch_bump", ptr(epoch), stream())
 
 
-def bump_epoch(device):
-    t = philox_epoch(device)
-    with torch.cuda.device(t.device):
-        call("pm_epoch_bump", ptr(t), stream())
-
-
-def share_gen(q: torch.Tensor, seed: int, offset: int, out=None):
+def share_gen(q: torch.Tensor, seed: int, offset: int, out=None, epoch=None):
     """additive_shared.py:336-365 (2 parties); ``out`` = (s0, s1) writes into existing tensors"""
     q = _chk(q)
     s0, s1 = out if out is not None else (torch.empty_like(q), torch.empty_like(q))
     with torch.cuda.device(q.device):
-        call("pm_share_gen_i64", ptr(q), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(philox_epoch(q.device)), ptr(s0), ptr(s1),
-             q.numel(), stream())
+        call("pm_share_gen_i64", ptr(q), seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(epoch), ptr(s0), ptr(s1), q.numel(), stream())
     return s0, s1
 
 
-def random_i64(shape, seed: int, offset: int, device):
+def random_i64(shape, seed: int, offset: int, device, epoch=None):
     out = torch.empty(shape, dtype=I64, device=device)
     with torch.cuda.device(out.device):
-        call("pm_random_i64", seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(philox_epoch(out.device)), ptr(out), out.numel(),
-             stream())
+        call("pm_random_i64", seed & (2 ** 64 - 1), offset & (2 ** 64 - 1), ptr(epoch), ptr(out), out.numel(), stream())
     return out
 
 

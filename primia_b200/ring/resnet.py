@@ -341,8 +341,8 @@ class EncryptedInferenceGraph:
         self._off = _MultiDeviceCapture(self.off_devices)
 
         def generate():
-            for d in self.off_devices:
-                ops.bump_epoch(d)
+            net.provider.bump_epoch()      # graph nodes: every replay draws from a fresh Philox stream
+            net.rng.bump_epoch()
             net.preprocess(1)
             net.rng.refresh_static()
 

@@ -149,10 +149,22 @@ class TripleProvider:
         self.counter = 0
         self.generated_bytes = 0
         self.request_log = []  # (op, shapes, n_instances) of every provide_primitives call, in order
+        self._epoch = None
+
+    @property
+    def epoch(self):
+        """device-side Philox epoch of THIS provider (ops.new_epoch): bumped by the captured offline graph of
+        EncryptedInferenceGraph so that every replay generates fresh primitives"""
+        if self._epoch is None:
+            self._epoch = ops.new_epoch(self.provider.device)
+        return self._epoch
+
+    def bump_epoch(self):
+        ops.bump_epoch(self.epoch)
 
     def _rand(self, shape):
         self.counter += 1
-        return ops.random_i64(shape, self.seed, self.counter, self.provider.device)
+        return ops.random_i64(shape, self.seed, self.counter, self.provider.device, self.epoch)
 
     def build_triple(self, op: str, shapes):
         ls, rs = shapes
@@ -164,7 +176,7 @@ class TripleProvider:
         out = [[None] * 3, [None] * 3]
         for i, t in enumerate((a, b, c)):
             self.counter += 1
-            s0, s1 = ops.share_gen(t, self.seed, self.counter)
+            s0, s1 = ops.share_gen(t, self.seed, self.counter, epoch=self.epoch)
             out[0][i], out[1][i] = s0, s1
         return out
 
@@ -176,7 +188,7 @@ class TripleProvider:
         from .fss import build_fss_keys
 
         self.counter += 3
-        return build_fss_keys(n_instances, self.provider.device, self.seed, self.counter - 2)
+        return build_fss_keys(n_instances, self.provider.device, self.seed, self.counter - 2, self.epoch)
 
     def provide_primitives(self, op: str, shapes=None, parties=None, n_instances: int = 1, **_):
         self.request_log.append((op, shapes, n_instances))

@@ -25,6 +25,16 @@ class ShareRNG:
         self.counter = 0
         self.mode = "live"
         self.static, self.cursor = [], 0
+        self.epoch = None   # device-side Philox epoch (ops.new_epoch), created with the first sharing
+
+    def _ep(self, q):
+        if self.epoch is None or self.epoch.device != q.device:
+            self.epoch = ops.new_epoch(q.device)
+        return self.epoch
+
+    def bump_epoch(self):
+        if self.epoch is not None:
+            ops.bump_epoch(self.epoch)
 
     def share(self, q: torch.Tensor):
         if self.mode == "replay":
@@ -32,7 +42,7 @@ class ShareRNG:
             self.cursor += 1
             return s0, s1
         self.counter += 1
-        s0, s1 = ops.share_gen(q, self.seed, self.counter)
+        s0, s1 = ops.share_gen(q, self.seed, self.counter, epoch=self._ep(q))
         if self.mode == "record":
             self.static.append((q, s0, s1))
         return s0, s1
@@ -40,7 +50,7 @@ class ShareRNG:
     def refresh_static(self):
         for q, s0, s1 in self.static:
             self.counter += 1
-            ops.share_gen(q, self.seed, self.counter, out=(s0, s1))   # straight into the static buffers
+            ops.share_gen(q, self.seed, self.counter, out=(s0, s1), epoch=self._ep(q))   # straight into the static buffers
         self.cursor = 0
 
 
