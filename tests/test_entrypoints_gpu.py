@@ -93,7 +93,7 @@ def test_train_writes_reference_format_checkpoint_and_inference_reads_it(tmp_pat
     assert list(state["model_state_dict"].keys()) == list(ref.state_dict().keys())
     ref.load_state_dict(state["model_state_dict"])                            # loads into the reference architecture
     # all hospitals hold the aggregate after the final FedAvg
-    assert torch.equal(hospitals[0].engine.flat, hospitals[2].engine.flat)
+    assert torch.equal(hospitals[0].engine.flat.cpu(), hospitals[2].engine.flat.cpu())   # (hospitals round-robin over the visible GPUs)
     # plain inference on the checkpoint == the oracle's eval forward on the same synthetic images
     preds = inference.main(["--model_weights", ck, "--num_images", "3"])
     g = torch.Generator().manual_seed(42)
@@ -145,7 +145,7 @@ def test_resume_checkpoint_restores_model_and_optimizer(tmp_path):
     h1 = train.main(["--config", ini, "--train_federated", "--unencrypted_aggregation", "--mode", "f32", "--batches_per_worker", "2",
                      "--save_dir", str(tmp_path / "a")])
     ck = train.main.last_checkpoint
-    flat, m, steps = h1[0].engine.flat.clone(), h1[0].engine.adam_m.clone(), h1[0].engine.step_count
+    flat, m, steps = h1[0].engine.flat.cpu().clone(), h1[0].engine.adam_m.cpu().clone(), h1[0].engine.step_count
     assert steps == 2 and m.abs().sum() > 0
     ini2 = write_ini(tmp_path, res=64, epochs=1, keep="yes", name="c2.ini")   # start_at_epoch == epochs: one more epoch runs
     import primia_b200.train.federated as F
@@ -154,8 +154,8 @@ def test_resume_checkpoint_restores_model_and_optimizer(tmp_path):
     orig = F.federated_round
 
     def spy(workers, *a, **k):
-        seen["flat"] = workers[0].engine.flat.clone()
-        seen["m"] = workers[0].engine.adam_m.clone()
+        seen["flat"] = workers[0].engine.flat.cpu().clone()
+        seen["m"] = workers[0].engine.adam_m.cpu().clone()
         seen["steps"] = workers[0].engine.step_count
         return orig(workers, *a, **k)
 
