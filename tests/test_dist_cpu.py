@@ -52,6 +52,47 @@ def test_fedavg_plan_world_size_2_gloo(tmp_path):
     assert "DIST_OK" in r.stdout
 
 
+WEIGHTS_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PM_ROOT"])
+from train import global_batch_counts
+from primia_b200.train.federated import fedavg_scales
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+# one hospital per rank, loaders of different length (utils.py:953-957: w_i = len(tl_i) / sum_j len(tl_j) over ALL hospitals)
+local = {["alice", "bob"][rank]: [3, 5][rank]}
+counts = global_batch_counts(local, dist.group.WORLD)
+assert counts == {"alice": 3, "bob": 5}, counts
+total = sum(counts.values())
+weights = {n: c / total for n, c in counts.items()}
+x = torch.full((4,), float(rank + 1))
+pre, post = fedavg_scales(["alice", "bob"][rank], world, weights)
+y = x * pre
+dist.all_reduce(y, op=dist.ReduceOp.SUM)
+y = y * post
+assert torch.allclose(y, torch.full((4,), 1 * 3 / 8 + 2 * 5 / 8)), y      # the weighted mean, not n times the parameters
+# number of rounds of the epoch = the MAXIMUM batch count over the ranks (exhausted hospitals keep joining the collectives)
+t = torch.tensor([[3, 5][rank]]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert int(t) == 5
+dist.barrier()
+if rank == 0:
+    print("WEIGHTS_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_weighted_averaging_denominator_is_global_world_size_2_gloo(tmp_path):
+    """ADVICE r1: under torchrun every rank holds one hospital, so the weights of torchlib/utils.py:953-957 need the batch counts
+    of ALL ranks (train.global_batch_counts); with rank-local counts every weight was 1.0 and FedAvg returned n x the parameters"""
+    script = tmp_path / "w.py"
+    script.write_text(WEIGHTS_WORKER)
+    env = dict(os.environ, PM_ROOT=ROOT, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29535", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "WEIGHTS_OK" in r.stdout
+
+
 def test_reference_arm_prints_one_json_line_rank0_only():
     env = dict(os.environ, OMP_NUM_THREADS="4")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
