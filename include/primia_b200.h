@@ -314,6 +314,11 @@ int pm_linear_fwd_f32(const float* feat, const float* W, const float* bias, int 
 /* torch.optim.Adam.step (train.py:280-303; L2 weight decay added to grad) on the flat parameter buffer */
 int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int step, pm_stream_t s);
+/* the same step for a freshly created optimizer (step index 1, m = v = 0: the reference re-creates the optimizers after every
+ * aggregation, utils.py:1209-1218): bit-identical to pm_adam_step_f32 on zeroed moments, but m and v are only WRITTEN, so the
+ * caller never has to clear them */
+int pm_adam_first_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, pm_stream_t s);
 /* torch.optim.SGD.step (no momentum; weight decay) */
 int pm_sgd_step_f32(float* p, const float* g, size_t n, float lr, float weight_decay, pm_stream_t s);
 /* FedAvg tail (torchlib/utils.py:1078-1090): x *= scale (after the NCCL sum) ; and pre-scale for weighted averaging */

@@ -105,6 +105,9 @@ __global__ void head_bwd_kernel(const float* __restrict__ feat, const float* __r
   }
 }
 
+// FIRST: the optimizer was (re-)created since the last step, i.e. m = v = 0 (the reference does this after every aggregation,
+// utils.py:1209-1218): the moments are not read -- identical arithmetic with the zeros folded in -- and nobody has to clear them.
+template <bool FIRST>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             float bc1, float bc2_sqrt) {
@@ -115,8 +118,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = fmaf(wd, pi, g[i]);
-    const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // lerp_(grad, 1-beta1)
-    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    const float m0 = FIRST ? 0.f : m[i], v0 = FIRST ? 0.f : v[i];
+    const float mi = m0 + (1.f - b1) * (gi - m0);  // lerp_(grad, 1-beta1)
+    const float vi = fmaf(b2, v0, (1.f - b2) * gi * gi);
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -333,15 +337,27 @@ int pm_linear_fwd_f32(const float* feat, const float* W, const float* bias, int 
   PM_LAUNCH_OK();
 }
 
-int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, int step, pm_stream_t s) {
+static int adam_launch(bool first, float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, pm_stream_t s) {
   PM_CHECK_ARG(p && g && m && v && step >= 1);
   if (n == 0) return PM_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  PM_CUDA(pm_launch(adam_kernel, dim3(pm_grid(n, 256, 1, 16)), dim3(256), 0, S(s), p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                    (float)bc1, (float)sqrt(bc2)));
+  if (first)
+    PM_CUDA(pm_launch(adam_kernel<true>, dim3(pm_grid(n, 256, 1, 16)), dim3(256), 0, S(s), p, g, m, v, n, lr, beta1, beta2, eps,
+                      weight_decay, (float)bc1, (float)sqrt(bc2)));
+  else
+    PM_CUDA(pm_launch(adam_kernel<false>, dim3(pm_grid(n, 256, 1, 16)), dim3(256), 0, S(s), p, g, m, v, n, lr, beta1, beta2, eps,
+                      weight_decay, (float)bc1, (float)sqrt(bc2)));
   PM_LAUNCH_OK();
+}
+int pm_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, pm_stream_t s) {
+  return adam_launch(false, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, s);
+}
+int pm_adam_first_step_f32(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, pm_stream_t s) {
+  return adam_launch(true, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1, s);
 }
 
 int pm_sgd_step_f32(float* p, const float* g, size_t n, float lr, float weight_decay, pm_stream_t s) {

@@ -97,7 +97,7 @@ def capture_dp_graph(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, 
     """capture one DP step (~450 launches) in a CUDA graph; the Philox counter lives in device memory, so replays draw fresh
     noise.  Valid at the captured optimizer step index / hyper-parameters (see ResNet18Engine.capture_graph)."""
     with torch.cuda.device(eng.device):
-        snap = (eng.flat.clone(), eng.adam_m.clone(), eng.adam_v.clone(), eng.step_count)
+        snap = (eng.flat.clone(), eng.adam_m.clone(), eng.adam_v.clone(), eng.step_count, eng._mv_zero)
         gx, gy = x_nchw.clone(), target.clone()
         side = torch.cuda.Stream(eng.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -105,12 +105,14 @@ def capture_dp_graph(eng: ResNet18Engine, x_nchw, target, noise_multiplier=1.3, 
             _dp_step_eager(eng, gx, gy, noise_multiplier, max_grad_norm, None, seed)  # warm-up: allocates every buffer
         torch.cuda.current_stream().wait_stream(side)
         eng.flat.copy_(snap[0]); eng.adam_m.copy_(snap[1]); eng.adam_v.copy_(snap[2]); eng.step_count = snap[3]
+        eng._mv_zero = snap[4]
         torch.cuda.synchronize(eng.device)
         key = _graph_key(eng, noise_multiplier, max_grad_norm, seed)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             _dp_step_eager(eng, gx, gy, noise_multiplier, max_grad_norm, None, seed)
         eng.step_count = snap[3]
+        eng._mv_zero = snap[4]
         eng._dp_graph = {"graph": graph, "x": gx, "y": gy, "key": key}
 
 

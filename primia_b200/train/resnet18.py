@@ -80,6 +80,7 @@ class ResNet18Engine:
         self._split_cb = None
         self._graph2 = None
         self.on_inputs_staged = None
+        self._mv_zero = True
         self._build_graph()
         self._alloc()
         self.class_weights = None
@@ -441,9 +442,31 @@ class ResNet18Engine:
                  stream())
 
     def refresh_bf16_weights(self):
-        call("pm_krsc_to_bf16_batched_exact", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_total, stream())
+        """bf16 copies of the fp32 master weights for this step.  The stem's operand first (its conv is the first kernel); the
+        44.7 MB batched cast of every other layer -- and the clearing of the flat gradient buffer the split-K weight gradients
+        accumulate into -- run on the side stream underneath the stem conv / BN / pool and join before layer1."""
         if self.direct_stem:
             call("pm_stem_prep_w_bf16", ptr(self.p["conv1.weight"]), ptr(self.w_stem), stream())
+        side = self._get_side() if (self.overlap_wgrad and self._prof is None and self.direct_stem) else None
+        if side is None:
+            call("pm_krsc_to_bf16_batched_exact", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_total, stream())
+            self._cast_done = None
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            call("pm_krsc_to_bf16_batched_exact", ptr(self.wcvt_table), self.wcvt_n, self.wcvt_total, stream())
+            if self.training:
+                self.grads.zero_()
+                self._grads_cleared = True
+            self._cast_done = torch.cuda.Event()
+            self._cast_done.record()
+
+    def _get_side(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     def forward(self, x_nchw=None):
         with torch.cuda.device(self.device):
@@ -485,6 +508,9 @@ class ResNet18Engine:
                     call("pm_maxpool3s2_fwd" + self.sfx, ptr(self.act["a1"]), self.B, c1.Ho, c1.Wo, 64, ptr(self.act["p1"]),
                          ptr(self.pool_idx), stream())
             xin = self.act["p1"]
+            if getattr(self, "_cast_done", None) is not None:
+                torch.cuda.current_stream().wait_event(self._cast_done)   # layer1 onwards reads the freshly cast weights
+                self._cast_done = None
             for pre, ca, cb, ds in self.blocks:
                 ia, ib = bn_ids[pre + ".bn1"], bn_ids[pre + ".bn2"]
                 self._conv_fwd(ca, xin, self.act[ca.name], self._stat_slot(ia) if fuse else None)
@@ -514,11 +540,13 @@ class ResNet18Engine:
             hard = target.dtype == torch.int64
             target = target.contiguous()
             if self.mode == "bf16":
-                self.grads.zero_()  # the tensor-core wgrad accumulates (split over pixels) into a cleared buffer
+                if not getattr(self, "_grads_cleared", False):
+                    self.grads.zero_()  # the tensor-core wgrad accumulates (split over pixels) into a cleared buffer
+                self._grads_cleared = False
                 if not self.direct_stem:
                     self.dw_stem.zero_()
-                if self.overlap_wgrad and self._side is None:
-                    self._side = torch.cuda.Stream(self.device)
+                if self.overlap_wgrad:
+                    self._get_side()
             e0 = self._prof_begin("head")
             call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
                  ptr(target) if hard else None, None if hard else ptr(target),
@@ -617,11 +645,18 @@ class ResNet18Engine:
         with torch.cuda.device(self.device):
             if bump:
                 self.step_count += 1
+                if self.step_count > 1:
+                    self._mv_zero = False   # the moments now hold what the first step wrote
             hi = self.n_param_flat if hi is None else hi
             n = hi - lo
             sl = lambda t: ctypes.c_void_p(t.data_ptr() + 4 * lo)
             e0 = self._prof_begin("optimizer")
-            if self.opt_name == "Adam":
+            if self.opt_name == "Adam" and self._mv_zero and self.step_count == 1:
+                # freshly (re-)created optimizer: the moments are logically zero and are not even read
+                call("pm_adam_first_step_f32", sl(self.flat), sl(self.grads), sl(self.adam_m), sl(self.adam_v), n,
+                     ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
+                     ctypes.c_float(self.opt_eps), ctypes.c_float(self.wd), stream())
+            elif self.opt_name == "Adam":
                 call("pm_adam_step_f32", sl(self.flat), sl(self.grads), sl(self.adam_m), sl(self.adam_v), n,
                      ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
                      ctypes.c_float(self.opt_eps), ctypes.c_float(self.wd), self.step_count, stream())
@@ -633,10 +668,16 @@ class ResNet18Engine:
             self._prof_end(e0)
 
     def reset_optimizer(self):
-        """utils.py:1131-1145,1209-1218: optimizers are re-created (state zeroed) after every aggregation."""
-        self.adam_m.zero_()
-        self.adam_v.zero_()
+        """utils.py:1131-1145,1209-1218: optimizers are re-created (state zeroed) after every aggregation.  Lazily: the next
+        step runs pm_adam_first_step_f32, which treats the moments as zero without reading them, so nothing is cleared here."""
+        self._mv_zero = True
         self.step_count = 0
+
+    def adam_moments(self):
+        """(m, v) as the optimizer state really is (zeros right after a reset)"""
+        if self._mv_zero and self.step_count == 0:
+            return torch.zeros_like(self.adam_m), torch.zeros_like(self.adam_v)
+        return self.adam_m, self.adam_v
 
     def _train_step_eager(self, x_nchw, target):
         self.forward(x_nchw)
@@ -664,7 +705,7 @@ class ResNet18Engine:
         none of it changed (train.py:433-440 adjusts lr per epoch; class weights / eval mode switch kernels)"""
         cw = None if self.class_weights is None else self.class_weights.data_ptr()
         return (self.opt_name, float(self.lr), tuple(float(b) for b in self.betas), float(self.wd), float(self.opt_eps), cw,
-                bool(self.training))
+                bool(self.training), bool(self._mv_zero))
 
     def capture_graph(self, x_nchw, target):
         """Capture one local step (all ~190 kernel launches) in a CUDA graph.  Adam's bias correction bakes the step
@@ -673,7 +714,7 @@ class ResNet18Engine:
         from .. import _lib
 
         with torch.cuda.device(self.device):
-            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count, self._mv_zero)
             gx, gy = x_nchw.clone(), target.clone()
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream())
@@ -681,6 +722,7 @@ class ResNet18Engine:
                 self._train_step_eager(gx, gy)  # warm-up on the capture stream: allocates every lazily created buffer
             torch.cuda.current_stream().wait_stream(side)
             self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+            self._mv_zero = snap[4]
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_counter
@@ -688,6 +730,7 @@ class ResNet18Engine:
                 self._train_step_eager(gx, gy)
             launches = _lib.launch_counter - n0 + 1  # + stats.zero_()
             self.step_count = snap[3]
+            self._mv_zero = snap[4]
             self._graph = {"graph": graph, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype, "launches": launches,
                            "hyper": self._hyper_key()}
         return launches
@@ -708,7 +751,7 @@ class ResNet18Engine:
         The running statistics (end of the flat buffer) are final after the forward, so they travel with the first bucket.
         Same replay conditions as ``capture_graph`` (optimizer step index, hyper-parameters)."""
         with torch.cuda.device(self.device):
-            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count, self._mv_zero)
             gx, gy = x_nchw.clone(), target.clone()
             off = self.split_offset
             cap = torch.cuda.Stream(self.device)
@@ -717,6 +760,7 @@ class ResNet18Engine:
                 self._train_step_eager(gx, gy)  # warm-up: allocates every lazily created buffer
             torch.cuda.current_stream().wait_stream(cap)
             self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+            self._mv_zero = snap[4]
             torch.cuda.synchronize(self.device)
             gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
 
@@ -739,6 +783,7 @@ class ResNet18Engine:
             torch.cuda.current_stream().wait_stream(cap)
             torch.cuda.synchronize(self.device)
             self.step_count = snap[3]
+            self._mv_zero = snap[4]
             self._graph2 = {"A": gA, "B": gB, "x": gx, "y": gy, "step": snap[3] + 1, "tdtype": target.dtype,
                             "hyper": self._hyper_key(), "off": off}
 
@@ -766,7 +811,7 @@ class ResNet18Engine:
         from .. import _lib
 
         with torch.cuda.device(self.device):
-            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count)
+            snap = (self.flat.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count, self._mv_zero)
             self._train_step_eager(x_nchw, target)
             torch.cuda.synchronize(self.device)
             self._prof = []
@@ -784,6 +829,7 @@ class ResNet18Engine:
             self.step_ms_by_family["conv (fwd + dgrad + wgrad)"] = ms
             self._prof = None
             self.flat.copy_(snap[0]); self.adam_m.copy_(snap[1]); self.adam_v.copy_(snap[2]); self.step_count = snap[3]
+            self._mv_zero = snap[4]
         return ms, launches
 
     def init_random(self, seed=42):

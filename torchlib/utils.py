@@ -199,7 +199,7 @@ def optimizer_state_dict(engine):
     if engine.opt_name == "Adam":
         group.update({"betas": tuple(engine.betas), "eps": engine.opt_eps, "amsgrad": False})
         if engine.step_count > 0:
-            m, v = engine.flat_to_torch_layout(engine.adam_m), engine.flat_to_torch_layout(engine.adam_v)
+            m, v = engine.flat_to_torch_layout(engine.adam_m), engine.flat_to_torch_layout(engine.adam_v)  # real after >= 1 step
             for i, n in enumerate(names):
                 state[i] = {"step": engine.step_count, "exp_avg": m[n].cpu(), "exp_avg_sq": v[n].cpu()}
     else:
@@ -222,6 +222,7 @@ def load_optimizer_state_dict(engine, sd):
         engine.torch_layout_to_flat({n: sd["state"][i]["exp_avg"] for i, n in enumerate(names)}, engine.adam_m)
         engine.torch_layout_to_flat({n: sd["state"][i]["exp_avg_sq"] for i, n in enumerate(names)}, engine.adam_v)
         engine.step_count = steps.pop()
+        engine._mv_zero = False
     else:
         engine.reset_optimizer()
 
