@@ -307,6 +307,18 @@ int pm_gap_bwd_bf16(const float* dy, int B, int HW, int C, void* dx, pm_stream_t
 int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const int64_t* labels, const float* soft,
                      const float* class_w, int B, int F, int ncls, float* logits, float* loss, float* dfeat,
                      float* dW, float* db, float* ws, pm_stream_t s);
+/* The head of a training step split by what the backward chain needs.  pm_head_fused_*: one launch (one block per sample) does
+ * AvgPool2d(HW) of the last activation x [B,HW,F] -> feat, logits, the per-sample CE gradient (left unnormalised in ws, as
+ * pm_linear_ce_f32 leaves it: ws[b*(ncls+1) + j], nll in slot ncls, denominator in ws[B*(ncls+1)]), dfeat and the gradient of the
+ * average pool written straight into d_out [B,HW,F].  pm_head_grads_f32: the batch reductions dW, db, loss from (ws, feat) -- not
+ * on the critical path, the engine issues it on its side stream.  ws: B*(ncls+1)+1 floats. */
+int pm_head_fused_f32(const float* x, int HW, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                      const float* class_w, int B, int F, int ncls, float* feat, float* logits, float* ws, float* dfeat, float* d_out,
+                      pm_stream_t s);
+int pm_head_fused_bf16(const void* x, int HW, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                       const float* class_w, int B, int F, int ncls, float* feat, float* logits, float* ws, float* dfeat, void* d_out,
+                       pm_stream_t s);
+int pm_head_grads_f32(const float* feat, int B, int F, int ncls, const float* ws, float* loss, float* dW, float* db, pm_stream_t s);
 /* inference-only head: logits = feat @ W^T + bias */
 int pm_linear_fwd_f32(const float* feat, const float* W, const float* bias, int B, int F, int ncls, float* logits,
                       pm_stream_t s);

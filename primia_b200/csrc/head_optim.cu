@@ -105,6 +105,126 @@ __global__ void head_bwd_kernel(const float* __restrict__ feat, const float* __r
   }
 }
 
+// ---- the whole classifier head of one sample in ONE launch (critical path of a step: forward tail -> backward head):
+//   AvgPool2d(HW) of the last activation -> feat ; logits = feat W^T + b ; per-sample CE gradient dl (unnormalised, into ws as
+//   head_fwd_kernel leaves it) ; dfeat = (dl / denom) W ; gradient of the average pool written straight into d_out [B,HW,F].
+// The batch-reduced quantities (dW, db, loss) are NOT needed by the backward chain: head_grads_kernel computes them from
+// (ws, feat) afterwards, on the side stream.  denom = sum_b wgt_b is recomputed by every block from the labels (B <= a few
+// hundred) so that no grid-wide step is needed; block 0 also stores it in ws[B*(ncls+1)].
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fused_kernel(const T* __restrict__ x, int HW, const float* __restrict__ W, const float* __restrict__ bias,
+                  const int64_t* __restrict__ labels, const float* __restrict__ soft, const float* __restrict__ cw, int B, int F, int ncls,
+                  float* __restrict__ feat, float* __restrict__ logits, float* __restrict__ ws, float* __restrict__ dfeat,
+                  T* __restrict__ d_out) {
+  const int b = blockIdx.x;
+  extern __shared__ float sh[];          // [F] feat, then [MAXC][8] warp partials
+  float* sfeat = sh;
+  float (*red)[8] = reinterpret_cast<float (*)[8]>(sh + F);
+  __shared__ float lg[MAXC], dl[MAXC];
+  __shared__ float s_inv;
+  const float invHW = 1.f / (float)HW;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += to_f<T>(x[((size_t)b * HW + p) * F + f]);
+    const float v = acc / (float)HW;       // == gap_fwd_kernel
+    sfeat[f] = v;
+    feat[(size_t)b * F + f] = v;
+  }
+  __syncthreads();
+  float part[MAXC];
+  for (int j = 0; j < ncls; ++j) part[j] = 0.f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float v = sfeat[i];
+    for (int j = 0; j < ncls; ++j) part[j] = fmaf(v, W[(size_t)j * F + i], part[j]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j = 0; j < ncls; ++j) {
+    const float v = warp_sum(part[j]);
+    if (lane == 0) red[j][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ncls) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+    v += bias[threadIdx.x];
+    lg[threadIdx.x] = v;
+    logits[(size_t)b * ncls + threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = lg[0];
+    for (int j = 1; j < ncls; ++j) mx = fmaxf(mx, lg[j]);
+    float se = 0.f;
+    for (int j = 0; j < ncls; ++j) se += expf(lg[j] - mx);
+    const float lse = mx + logf(se);
+    float* out = ws + (size_t)b * (ncls + 1);
+    float denom = 0.f;
+    if (labels) {
+      const int y = (int)labels[b];
+      const float wgt = cw ? cw[y] : 1.f;
+      for (int j = 0; j < ncls; ++j) { dl[j] = wgt * (expf(lg[j] - lse) - (j == y ? 1.f : 0.f)); out[j] = dl[j]; }
+      out[ncls] = wgt * (lse - lg[y]);
+      if (cw) { for (int q = 0; q < B; ++q) denom += cw[(int)labels[q]]; } else denom = (float)B;
+    } else {
+      const float* t = soft + (size_t)b * ncls;
+      float wsum = 1.f, tsum = 0.f, nll = 0.f;
+      if (cw) { wsum = 0.f; for (int j = 0; j < ncls; ++j) wsum += cw[j] * t[j]; }
+      for (int j = 0; j < ncls; ++j) { tsum += t[j]; nll += -t[j] * (lg[j] - lse); }
+      for (int j = 0; j < ncls; ++j) { dl[j] = wsum * (expf(lg[j] - lse) * tsum - t[j]); out[j] = dl[j]; }
+      out[ncls] = wsum * nll;
+      denom = (float)B;
+    }
+    s_inv = 1.f / denom;
+    if (b == 0) ws[(size_t)B * (ncls + 1)] = denom;
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float df = 0.f;
+    for (int j = 0; j < ncls; ++j) df = fmaf(dl[j] * inv, W[(size_t)j * F + f], df);   // == head_bwd_kernel
+    dfeat[(size_t)b * F + f] = df;
+    const T g = from_f<T>(df / (float)HW);                                            // == gap_bwd_kernel
+    for (int p = 0; p < HW; ++p) d_out[((size_t)b * HW + p) * F + f] = g;
+  }
+  (void)invHW;
+}
+
+// dW, db, loss from (ws, feat) -- the batch reductions of the head, off the critical path.  grid (ceil(F/64)), block 64.
+__global__ void head_grads_kernel(const float* __restrict__ feat, int B, int F, int ncls, const float* __restrict__ ws,
+                                  float* __restrict__ loss, float* __restrict__ dW, float* __restrict__ db) {
+  const float inv = 1.f / ws[(size_t)B * (ncls + 1)];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) {
+    float dw[MAXC];
+    for (int j = 0; j < ncls; ++j) dw[j] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+      float xs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xs[u] = b0 + u < B ? feat[(size_t)(b0 + u) * F + f] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u;
+        if (b < B) {
+          const float* dl = ws + (size_t)b * (ncls + 1);
+          for (int j = 0; j < ncls; ++j) dw[j] = fmaf(dl[j] * inv, xs[u], dw[j]);
+        }
+      }
+    }
+    for (int j = 0; j < ncls; ++j) dW[(size_t)j * F + f] = dw[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ncls) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += ws[(size_t)b * (ncls + 1) + threadIdx.x];
+    db[threadIdx.x] = s * inv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += ws[(size_t)b * (ncls + 1) + ncls];
+    loss[0] = s * inv;
+  }
+}
+
 // FIRST: the optimizer was (re-)created since the last step, i.e. m = v = 0 (the reference does this after every aggregation,
 // utils.py:1209-1218): the moments are not read -- identical arithmetic with the zeros folded in -- and nobody has to clear them.
 template <bool FIRST>
@@ -317,6 +437,18 @@ im2col_stem_kernel(const float* __restrict__ x, int Cin, int H, int W, int R, in
 
 }  // namespace
 
+template <typename T>
+static int head_fused_t(const T* x, int HW, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                        const float* class_w, int B, int F, int ncls, float* feat, float* logits, float* ws, float* dfeat, T* d_out,
+                        pm_stream_t s) {
+  PM_CHECK_ARG(x && W && bias && feat && logits && ws && dfeat && d_out && B > 0 && F > 0 && HW > 0 && ncls > 0 && ncls <= MAXC);
+  PM_CHECK_ARG((labels != nullptr) != (soft != nullptr));
+  const size_t smem = ((size_t)F + MAXC * 8) * sizeof(float);
+  PM_CUDA(pm_launch(head_fused_kernel<T>, dim3(B), dim3(256), smem, S(s), x, HW, W, bias, labels, soft, class_w, B, F, ncls, feat, logits, ws,
+                    dfeat, d_out));
+  PM_LAUNCH_OK();
+}
+
 extern "C" {
 
 int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const int64_t* labels, const float* soft,
@@ -327,6 +459,23 @@ int pm_linear_ce_f32(const float* feat, const float* W, const float* bias, const
   PM_CUDA(cudaMemsetAsync(ws + (size_t)B * (ncls + 1), 0, sizeof(float), S(s)));
   head_fwd_kernel<<<B, 128, 0, S(s)>>>(feat, W, bias, labels, soft, class_w, F, ncls, logits, ws);
   head_bwd_kernel<<<(F + 63) / 64, 64, 0, S(s)>>>(feat, W, B, F, ncls, ws, loss, dfeat, dW, db);  // thread 32 of block 0 writes the loss
+  PM_LAUNCH_OK();
+}
+
+int pm_head_fused_f32(const float* x, int HW, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                      const float* class_w, int B, int F, int ncls, float* feat, float* logits, float* ws, float* dfeat, float* d_out,
+                      pm_stream_t s) {
+  return head_fused_t<float>(x, HW, W, bias, labels, soft, class_w, B, F, ncls, feat, logits, ws, dfeat, d_out, s);
+}
+int pm_head_fused_bf16(const void* x, int HW, const float* W, const float* bias, const int64_t* labels, const float* soft,
+                       const float* class_w, int B, int F, int ncls, float* feat, float* logits, float* ws, float* dfeat, void* d_out,
+                       pm_stream_t s) {
+  return head_fused_t<__nv_bfloat16>((const __nv_bfloat16*)x, HW, W, bias, labels, soft, class_w, B, F, ncls, feat, logits, ws, dfeat,
+                                     (__nv_bfloat16*)d_out, s);
+}
+int pm_head_grads_f32(const float* feat, int B, int F, int ncls, const float* ws, float* loss, float* dW, float* db, pm_stream_t s) {
+  PM_CHECK_ARG(feat && ws && loss && dW && db && B > 0 && F > 0 && ncls > 0 && ncls <= MAXC);
+  head_grads_kernel<<<(F + 63) / 64, 64, 0, S(s)>>>(feat, B, F, ncls, ws, loss, dW, db);
   PM_LAUNCH_OK();
 }
 

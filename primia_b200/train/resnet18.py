@@ -66,6 +66,7 @@ class ResNet18Engine:
         self._graph = None
         self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
         self.fuse_bn_bwd = True  # BN backward as one launch with a grid barrier
+        self.fuse_head = True    # pool + Linear + CE + their gradients as one launch per step (batch reductions on the side stream)
         self.overlap_wgrad = mode == "bf16"
         # bf16 throughput mode: the stem's BN + ReLU + max-pool run as one pass (the 112x112 activation is never written) and
         # BN backward recomputes the ReLU decision from x instead of reading the stored activation where no residual is added
@@ -525,7 +526,8 @@ class ResNet18Engine:
                 self._bn_fwd(pre + ".bn2", ib, self.act[cb.name], self.act[pre + ".out"], idn, True, cb.P, fuse)
                 xin = self.act[pre + ".out"]
             hw = self.final_hw * self.final_hw
-            call("pm_gap_fwd" + self.sfx, ptr(xin), self.B, hw, 512, ptr(self.feat), stream())
+            if not (self.training and self.fuse_head):   # a training step pools inside its fused head kernel (loss_and_backward)
+                call("pm_gap_fwd" + self.sfx, ptr(xin), self.B, hw, 512, ptr(self.feat), stream())
             return xin
 
     def logits_only(self):
@@ -548,16 +550,36 @@ class ResNet18Engine:
                 if self.overlap_wgrad:
                     self._get_side()
             e0 = self._prof_begin("head")
-            call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
-                 ptr(target) if hard else None, None if hard else ptr(target),
-                 ptr(self.class_weights) if self.class_weights is not None else None, self.B, 512, self.ncls,
-                 ptr(self.logits), ptr(self.loss), ptr(self.dfeat), ptr(self.g["fc.weight"]), ptr(self.g["fc.bias"]),
-                 ptr(self.head_ws), stream())
             bn_ids = {bn: i for i, bn in enumerate(self.bns)}
             last = self.act[self.blocks[-1][0] + ".out"]
             d_out = self._gbuf(("d", last.shape, 0), last)
             hw = self.final_hw * self.final_hw
-            call("pm_gap_bwd" + self.sfx, ptr(self.dfeat), self.B, hw, 512, ptr(d_out), stream())
+            cwp = ptr(self.class_weights) if self.class_weights is not None else None
+            if self.training and self.fuse_head:
+                # ONE launch on the critical path: average pool, logits, per-sample CE gradient, dfeat, gradient of the pool;
+                # the batch reductions (dW, db, loss) are not needed by the backward chain and go to the side stream
+                call("pm_head_fused" + self.sfx, ptr(last), hw, ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
+                     ptr(target) if hard else None, None if hard else ptr(target), cwp, self.B, 512, self.ncls, ptr(self.feat),
+                     ptr(self.logits), ptr(self.head_ws), ptr(self.dfeat), ptr(d_out), stream())
+
+                def head_grads():
+                    call("pm_head_grads_f32", ptr(self.feat), self.B, 512, self.ncls, ptr(self.head_ws), ptr(self.loss),
+                         ptr(self.g["fc.weight"]), ptr(self.g["fc.bias"]), stream())
+
+                if self._side is not None and self._prof is None:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self._side.wait_event(ev)
+                    with torch.cuda.stream(self._side):
+                        head_grads()
+                else:
+                    head_grads()
+            else:
+                call("pm_linear_ce_f32", ptr(self.feat), ptr(self.p["fc.weight"]), ptr(self.p["fc.bias"]),
+                     ptr(target) if hard else None, None if hard else ptr(target), cwp, self.B, 512, self.ncls,
+                     ptr(self.logits), ptr(self.loss), ptr(self.dfeat), ptr(self.g["fc.weight"]), ptr(self.g["fc.bias"]),
+                     ptr(self.head_ws), stream())
+                call("pm_gap_bwd" + self.sfx, ptr(self.dfeat), self.B, hw, 512, ptr(d_out), stream())
             self._prof_end(e0)
             for bi in range(len(self.blocks) - 1, -1, -1):
                 pre, ca, cb, ds = self.blocks[bi]
