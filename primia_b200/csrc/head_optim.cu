@@ -123,7 +123,7 @@ head_fused_kernel(const T* __restrict__ x, int HW, const float* __restrict__ W, 
   float (*red)[8] = reinterpret_cast<float (*)[8]>(sh + F);
   __shared__ float lg[MAXC], dl[MAXC];
   __shared__ float s_inv;
-  const float invHW = 1.f / (float)HW;
+  pm_pdl_sync();
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     float acc = 0.f;
     for (int p = 0; p < HW; ++p) acc += to_f<T>(x[((size_t)b * HW + p) * F + f]);
@@ -187,12 +187,12 @@ head_fused_kernel(const T* __restrict__ x, int HW, const float* __restrict__ W, 
     const T g = from_f<T>(df / (float)HW);                                            // == gap_bwd_kernel
     for (int p = 0; p < HW; ++p) d_out[((size_t)b * HW + p) * F + f] = g;
   }
-  (void)invHW;
 }
 
 // dW, db, loss from (ws, feat) -- the batch reductions of the head, off the critical path.  grid (ceil(F/64)), block 64.
 __global__ void head_grads_kernel(const float* __restrict__ feat, int B, int F, int ncls, const float* __restrict__ ws,
                                   float* __restrict__ loss, float* __restrict__ dW, float* __restrict__ db) {
+  pm_pdl_sync();
   const float inv = 1.f / ws[(size_t)B * (ncls + 1)];
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f < F) {

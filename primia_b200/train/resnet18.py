@@ -66,7 +66,7 @@ class ResNet18Engine:
         self._graph = None
         self.fuse_stats = True  # BN batch statistics accumulated in the conv epilogue (bf16 mode)
         self.fuse_bn_bwd = True  # BN backward as one launch with a grid barrier
-        self.fuse_head = True    # pool + Linear + CE + their gradients as one launch per step (batch reductions on the side stream)
+        self.fuse_head = os.environ.get("PRIMIA_FUSE_HEAD", "1") != "0"    # pool + Linear + CE + their gradients as one launch per step (batch reductions on the side stream)
         self.overlap_wgrad = mode == "bf16"
         # bf16 throughput mode: the stem's BN + ReLU + max-pool run as one pass (the 112x112 activation is never written) and
         # BN backward recomputes the ReLU decision from x instead of reading the stored activation where no residual is added
