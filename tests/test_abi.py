@@ -61,7 +61,7 @@ def test_every_kernel_launched_with_the_pdl_attribute_waits_on_its_predecessor()
         if var in names:
             names.discard(var)
             names.add(kernel)
-XX
+    names -= {"kernel", "void"}  # pm_launch itself
     assert len(names) >= 12, names
     for n in sorted(names):
         m = re.search(r"__global__[^;{]*?\b" + n + r"\s*\([^{;]*\)\s*\{", src, re.S)
