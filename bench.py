@@ -334,8 +334,12 @@ def linear_layers_block(steps=3):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     parties = [ring.Party("model_owner", dev), ring.Party("data_owner", dev)]
     prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", dev), seed=42)
+    from primia_b200 import _lib
+    from primia_b200.ring import resnet as _rr
+
     lin = SharedLinearLayers(parties, prov, 10, 16)
     eg = EncryptedLinearGraph(lin, lin.make_inputs(1), 1)
+    launches = eg.launches
     offl, onl = [], []
     for it in range(steps + 1):
         torch.cuda.synchronize()
@@ -360,9 +364,13 @@ def linear_layers_block(steps=3):
     hbm = 2 * 3 * tri_bytes / (lon * 1e-3) / 1e9
     return {"online_ms": lon, "offline_triple_gen_ms": sum(offl) / len(offl),
             "int64_gmac_per_s_per_party": 2 * INT64_MAC_PER_IMAGE / (lon * 1e-3) / 1e9,
-            "scope": "20 convs + fc Beaver protocol only (mask, open, combine on the int8 tensor cores, truncate), CUDA graph",
+            "scope": "20 convs + fc Beaver protocol only, CUDA graph; " + (
+                "online = mask the activation, open it into limb planes, 2-segment GEMM on the int8 tensor cores, truncate -- the weight "
+                "half (mask + open w, planes of a, b + eps, eps) runs in the offline phase" if _rr.HOIST_WEIGHT_SIDE else
+                "online = the whole protocol per layer (mask, open, planarise four operands, GEMM, truncate)"),
+            "online_launches": launches,
             "triple_bytes_per_party": tri_bytes,
-            "roofline": {"bound": "hbm", "kernel": "ring_i8::ring_gemm_i8_kernel + mask / planarize / open / truncate kernels (~330 launches)",
+            "roofline": {"bound": "hbm", "kernel": f"ring_i8::ring_gemm_i8_kernel + mask / open+planarize / truncate kernels ({launches} launches)",
                          "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm / pk["hbm_gbs"], "traffic": None,
                          "algorithmic": "per party: 226.7 MB of triples read + 206.9 MB of masked operands written and opened + outputs ~ 3 x "
                                         "226.7 MB; both parties on this GPU",

@@ -79,6 +79,17 @@ size_t pm_ring_tc_ws_bytes(int rows, int K, int N, int nseg);
 int pm_ring_tc_supported(int rows, int K, int N);
 int pm_ring_gemm2_tc_i64(const int64_t* A1, const int64_t* B1, const int64_t* A2, const int64_t* B2, const int64_t* Cinit, int rows,
                          int K, int N, void* ws, int64_t* C, pm_stream_t s);
+/* The same GEMM in pieces.  In spdz_mul (spdz.py:125-197) only delta = x - a depends on the image: the triple's a and b and the
+ * opened weight mask eps = w - b are known as soon as the triple exists, so their limb planes are built once in the OFFLINE
+ * phase (ring/functional.py prepare_weight_side) and the online phase of a layer is  mask -> open+planarise(delta) -> GEMM ->
+ * truncate.  pm_ring_planarize_rows_i64 with peer != NULL fuses the opening (spdz.py:162-163: delta = sum of the parties'
+ * masked shares; peer may be a peer-mapped pointer into the other party's GPU): planes of (A + peer) mod 2^64.
+ * planes: pm_ring_planes_bytes(n, K) bytes, n = rows (left operand) or N (right operand). */
+size_t pm_ring_planes_bytes(int n, int K);
+int pm_ring_planarize_rows_i64(const int64_t* A, const int64_t* peer, int rows, int K, void* planes, pm_stream_t s);
+int pm_ring_planarize_cols_i64(const int64_t* B, int K, int N, void* planes, pm_stream_t s);
+int pm_ring_gemm_planes_i64(const void* pa1, const void* pb1, const void* pa2, const void* pb2, const int64_t* Cinit, int rows, int K,
+                            int N, int64_t* C, pm_stream_t s);
 /* spdz_compute, op == "mul" with torch broadcasting of a [C]-vector against [P,C]:
  * mode 0: same shape n ; mode 1: left is [C], right is [P,C] ; mode 2: left is [P,C], right is [C]. */
 int pm_spdz_combine_mul_i64(int j, const int64_t* delta, const int64_t* eps, const int64_t* a, const int64_t* b,

@@ -125,7 +125,7 @@ def stream():
 # kernels launched per entry point when it is not exactly one (used for the gpu_launches claim in bench.py)
 KERNELS_PER_CALL = {
     "pm_conv_wgrad_f32": 2, "pm_linear_ce_f32": 2, "pm_stem_pool_bn_bwd_bf16": 2,
-    "pm_spdz_combine_matmul_i64": 1, "pm_bn_newton_p2p_i64": 2, "pm_dp_add_noise_f32": 2,
+    "pm_spdz_combine_matmul_i64": 1, "pm_ring_gemm2_tc_i64": 5, "pm_ring_gemm_planes_i64": 2, "pm_bn_newton_p2p_i64": 2, "pm_dp_add_noise_f32": 2,
 }
 launch_counter = 0
 

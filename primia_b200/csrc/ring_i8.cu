@@ -220,7 +220,10 @@ ring_gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
 
 // ---------------------------------------------------------------------------------------------- limb planes
 // x [R][K] int64 (row-major) -> planes [8][R][Kp] u8.  One thread = one row x 16 consecutive k (one 16-byte store per plane).
-__global__ void planarize_rows_kernel(const u64* __restrict__ x, int R, int K, int Kp, uint8_t* __restrict__ out) {
+// peer != NULL: the OPENING is fused -- the planes of (x + peer) mod 2^64, peer being the other party's masked share (possibly a
+// peer-mapped pointer into another GPU); the opened int64 operand is never materialised.
+__global__ void planarize_rows_kernel(const u64* __restrict__ x, const u64* __restrict__ peer, int R, int K, int Kp,
+                                      uint8_t* __restrict__ out) {
   const int kv = Kp / 16;
   const size_t total = (size_t)R * kv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -230,7 +233,8 @@ __global__ void planarize_rows_kernel(const u64* __restrict__ x, int R, int K, i
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int k = kc * 16 + e;
-      const u64 v = k < K ? x[r * K + k] : 0ull;
+      u64 v = k < K ? x[r * K + k] : 0ull;
+      if (peer != nullptr && k < K) v += peer[r * K + k];
 #pragma unroll
       for (int l = 0; l < 8; ++l) b[l][e] = (uint8_t)(v >> (8 * l));
     }
@@ -293,30 +297,40 @@ size_t pm_ring_tc_ws_bytes(int rows, int K, int N, int nseg) {
 
 int pm_ring_tc_supported(int rows, int K, int N) { return N % 32 == 0 && N >= 32 && K >= 1 && rows >= 1 && 2L * K <= 33000; }
 
-// C[rows,N] = Cinit + A1[rows,K] @ B1[K,N] (+ A2 @ B2) over Z_2^64 on the int8 tensor cores.  A2/B2 may be NULL.
-// ws: pm_ring_tc_ws_bytes(rows, K, N, nseg) bytes of scratch for the limb planes.
-int pm_ring_gemm2_tc_i64(const int64_t* A1, const int64_t* B1, const int64_t* A2, const int64_t* B2, const int64_t* Cinit, int rows,
-                         int K, int N, void* ws, int64_t* C, pm_stream_t s) {
+// ---- the limb-plane GEMM in pieces, so that operands which do not depend on the image (the triple's a and b, the opened
+// weight mask eps) are planarised ONCE in the offline phase and the online phase runs: open+planarise(delta) -> GEMM.
+size_t pm_ring_planes_bytes(int n, int K) { return (size_t)8 * (size_t)n * (((size_t)K + 127) / 128 * 128); }
+
+// planes [8][rows][Kp] of A (+ peer): left operand.  peer may be NULL.
+int pm_ring_planarize_rows_i64(const int64_t* A, const int64_t* peer, int rows, int K, void* planes, pm_stream_t s) {
   using namespace ri8;
-  PM_CHECK_ARG(A1 && B1 && C && ws && pm_ring_tc_supported(rows, K, N) && ((A2 == nullptr) == (B2 == nullptr)));
-  if (!load_driver()) return pm_set_err(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable");
-  const int nseg = A2 ? 2 : 1;
+  PM_CHECK_ARG(A && planes && rows >= 1 && K >= 1);
   const int Kp = (K + 127) / 128 * 128;
-  uint8_t* w = (uint8_t*)ws;
-  uint8_t* pa[2];
-  uint8_t* pb[2];
-  for (int g = 0; g < nseg; ++g) {
-    pa[g] = w; w += (size_t)8 * rows * Kp;
-    pb[g] = w; w += (size_t)8 * N * Kp;
-  }
-  const int64_t* As[2] = {A1, A2};
-  const int64_t* Bs[2] = {B1, B2};
-  for (int g = 0; g < nseg; ++g) {
-    const size_t tot = (size_t)rows * (Kp / 16);
-    planarize_rows_kernel<<<pm_grid(tot, 128, 1, 16), 128, 0, S(s)>>>((const u64*)As[g], rows, K, Kp, pa[g]);
-    dim3 gb((Kp + 31) / 32, (N + 31) / 32), bb(32, 8);
-    planarize_cols_kernel<<<gb, bb, 0, S(s)>>>((const u64*)Bs[g], K, N, Kp, pb[g]);
-  }
+  const size_t tot = (size_t)rows * (Kp / 16);
+  planarize_rows_kernel<<<pm_grid(tot, 128, 1, 16), 128, 0, S(s)>>>((const u64*)A, (const u64*)peer, rows, K, Kp, (uint8_t*)planes);
+  PM_LAUNCH_OK();
+}
+
+// planes [8][N][Kp] of B^T, B [K,N]: right operand.
+int pm_ring_planarize_cols_i64(const int64_t* B, int K, int N, void* planes, pm_stream_t s) {
+  using namespace ri8;
+  PM_CHECK_ARG(B && planes && N >= 1 && K >= 1);
+  const int Kp = (K + 127) / 128 * 128;
+  dim3 gb((Kp + 31) / 32, (N + 31) / 32), bb(32, 8);
+  planarize_cols_kernel<<<gb, bb, 0, S(s)>>>((const u64*)B, K, N, Kp, (uint8_t*)planes);
+  PM_LAUNCH_OK();
+}
+
+// C[rows,N] = Cinit + A1 @ B1 (+ A2 @ B2) from limb planes (pm_ring_planarize_*).  pa2/pb2 may be NULL.
+int pm_ring_gemm_planes_i64(const void* pa1, const void* pb1, const void* pa2, const void* pb2, const int64_t* Cinit, int rows, int K,
+                            int N, int64_t* C, pm_stream_t s) {
+  using namespace ri8;
+  PM_CHECK_ARG(pa1 && pb1 && C && pm_ring_tc_supported(rows, K, N) && ((pa2 == nullptr) == (pb2 == nullptr)));
+  if (!load_driver()) return pm_set_err(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable");
+  const int nseg = pa2 ? 2 : 1;
+  const int Kp = (K + 127) / 128 * 128;
+  const void* pa[2] = {pa1, pa2};
+  const void* pb[2] = {pb1, pb2};
   CUtensorMap tA[2], tB[2];
   for (int g = 0; g < 2; ++g) {
     const int h = g < nseg ? g : 0;
@@ -333,6 +347,26 @@ int pm_ring_gemm2_tc_i64(const int64_t* A1, const int64_t* B1, const int64_t* A2
   dim3 grid(tm, tn, splitK);
   ring_gemm_i8_kernel<<<grid, NTHREADS, SMEM_BYTES, S(s)>>>(tA[0], tB[0], tA[1], tB[1], nseg, rows, N, Kp, splitK, (const u64*)Cinit, (u64*)C);
   PM_LAUNCH_OK();
+}
+
+// C[rows,N] = Cinit + A1[rows,K] @ B1[K,N] (+ A2 @ B2) over Z_2^64 on the int8 tensor cores.  A2/B2 may be NULL.
+// ws: pm_ring_tc_ws_bytes(rows, K, N, nseg) bytes of scratch for the limb planes.
+int pm_ring_gemm2_tc_i64(const int64_t* A1, const int64_t* B1, const int64_t* A2, const int64_t* B2, const int64_t* Cinit, int rows,
+                         int K, int N, void* ws, int64_t* C, pm_stream_t s) {
+  PM_CHECK_ARG(A1 && B1 && C && ws && pm_ring_tc_supported(rows, K, N) && ((A2 == nullptr) == (B2 == nullptr)));
+  const int nseg = A2 ? 2 : 1;
+  uint8_t* w = (uint8_t*)ws;
+  uint8_t* pa[2] = {nullptr, nullptr};
+  uint8_t* pb[2] = {nullptr, nullptr};
+  const int64_t* As[2] = {A1, A2};
+  const int64_t* Bs[2] = {B1, B2};
+  for (int g = 0; g < nseg; ++g) {
+    pa[g] = w; w += pm_ring_planes_bytes(rows, K);
+    pb[g] = w; w += pm_ring_planes_bytes(N, K);
+    if (int rc = pm_ring_planarize_rows_i64(As[g], nullptr, rows, K, pa[g], s)) return rc;
+    if (int rc = pm_ring_planarize_cols_i64(Bs[g], K, N, pb[g], s)) return rc;
+  }
+  return pm_ring_gemm_planes_i64(pa[0], pb[0], pa[1], pb[1], Cinit, rows, K, N, C, s);
 }
 
 }  // extern "C"

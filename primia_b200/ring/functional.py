@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .spdz import EmptyCryptoPrimitiveStoreError, open_shares, spdz_compute
+from .spdz import EmptyCryptoPrimitiveStoreError, _key, open_planes, open_shares, spdz_compute
 from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
 
 
@@ -29,8 +29,37 @@ def _post_conv(bias, res, batch_size, nb_channels_out, nb_rows_out, nb_cols_out)
     return ops.trunc_post_conv(res, 1, bias, nb_rows_out, nb_cols_out)
 
 
+class WeightSide:
+    """Everything of one Beaver matmul that does NOT depend on the image, per party j: limb planes of b_j (+ eps on party 0),
+    of eps and of a_j.  Built by ``prepare_weight_side`` in the offline phase, consumed by ``conv2d(..., prepared=)``."""
+
+    __slots__ = ("shapes", "pb1", "pb2", "pa2")
+
+    def __init__(self, shapes, pb1, pb2, pa2):
+        self.shapes, self.pb1, self.pb2, self.pa2 = shapes, pb1, pb2, pa2
+
+
+def prepare_weight_side(weight: FixedPrecisionTensor, tri, batch: int, Ho: int, Wo: int):
+    """The weight half of spdz_mul for one convolution (spdz.py:22-45,162-163), hoisted out of the per-image path:
+    eps = open(w_j^T - b_j); party 0's right operand b_0 + eps; limb planes of those and of a_j.  ``tri``: the per-party triple
+    the layer is going to consume (peeked, not popped).  Returns None when the shape does not run on the tensor cores."""
+    w = weight.child
+    Co = w.shape[0]
+    K = w.child[0].numel() // Co
+    rows = batch * Ho * Wo
+    if not ops.tc_supported(rows, K, Co):
+        return None
+    parties = w.parties
+    e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
+    eps = open_shares(parties, e_sh)
+    pb1 = [ops.planarize_cols(ops.axpby(1, tri[0][1], 1, eps[0])), ops.planarize_cols(tri[1][1])]
+    pb2 = [ops.planarize_cols(eps[j]) for j in range(2)]
+    pa2 = [ops.planarize_rows(tri[j][0]) for j in range(2)]
+    return WeightSide(((batch, Ho * Wo, K), (K, Co)), pb1, pb2, pa2)
+
+
 def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None, stride=1, padding=0, dilation=1,
-           groups=1):
+           groups=1, prepared: WeightSide = None):
     """functional.py:204-308 + FPT.matmul truncation (precision.py:419-463), fused per party:
 
       delta_j = im2col(x_j) - a_j      (pm_spdz_mask_im2col_i64: no im2col tensor is materialised)
@@ -58,10 +87,21 @@ def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None,
                 raise
             provider.provide_primitives(parties=parties, **e.kwargs_)
     d_sh = [ops.mask_im2col(x.child[j], tri[j][0], kh, kw, stride, padding, dilation) for j in range(2)]
-    e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
-    delta = open_shares(parties, d_sh)
-    eps = open_shares(parties, e_sh)
-    z = [spdz_compute(p, j, delta[j], eps[j], "matmul") for j, p in enumerate(parties)]
+    if prepared is not None:
+        # online half only: delta is opened INTO its limb planes (never materialised), then one 2-segment GEMM per party
+        #   z_j = delta @ (b_j [+ eps]) + a_j @ eps + c_j
+        assert prepared.shapes == _key(shapes), (prepared.shapes, shapes)
+        pd = open_planes(parties, d_sh)
+        z = []
+        for j, p in enumerate(parties):
+            _a, _b, c = p.crypto_store.get_keys(op="matmul", shapes=shapes, remove=True)      # the pop of spdz_compute (spdz.py:84)
+            z.append(ops.gemm_planes(pd[j], prepared.pb1[j], prepared.pa2[j], prepared.pb2[j], c.reshape(B * M, N), B * M, K,
+                                     N).view(B, M, N))
+    else:
+        e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
+        delta = open_shares(parties, d_sh)
+        eps = open_shares(parties, e_sh)
+        z = [spdz_compute(p, j, delta[j], eps[j], "matmul") for j, p in enumerate(parties)]
     bsh = bias.child.child if bias is not None else [None, None]
     div = weight.base ** weight.precision_fractional
     out = [ops.trunc_post_conv(z[j], div, None, Ho, Wo) for j in range(2)]

@@ -152,6 +152,45 @@ def gemm2_tc(A1, B1, A2, B2, Cinit):
     return C
 
 
+def _planes(n, K, device):
+    from .._lib import lib
+
+    l = lib()
+    l.pm_ring_planes_bytes.restype = ctypes.c_size_t
+    return torch.empty(int(l.pm_ring_planes_bytes(int(n), int(K))), dtype=torch.uint8, device=device)
+
+
+def planarize_rows(A, peer=None):
+    """limb planes of the left operand A [rows,K] -- or of (A + peer) mod 2^64 when ``peer`` is given: the OPENING of a masked
+    share fused into the planarisation (``peer`` may be a peer-mapped tensor on another GPU)."""
+    A = _chk(A)
+    K = A.shape[-1]
+    rows = A.numel() // K
+    out = _planes(rows, K, A.device)
+    with torch.cuda.device(A.device):
+        call("pm_ring_planarize_rows_i64", ptr(A), ptr(_chk(peer)) if peer is not None else None, rows, K, ptr(out), stream())
+    return out
+
+
+def planarize_cols(Bm):
+    """limb planes of the right operand B [K,N] (stored transposed, K contiguous)"""
+    Bm = _chk(Bm)
+    K, N = Bm.shape
+    out = _planes(N, K, Bm.device)
+    with torch.cuda.device(Bm.device):
+        call("pm_ring_planarize_cols_i64", ptr(Bm), K, N, ptr(out), stream())
+    return out
+
+
+def gemm_planes(pa1, pb1, pa2, pb2, Cinit, rows, K, N):
+    """C = Cinit + A1@B1 (+ A2@B2) from limb planes built by planarize_rows / planarize_cols"""
+    C = torch.empty((rows, N), dtype=I64, device=pa1.device)
+    with torch.cuda.device(pa1.device):
+        call("pm_ring_gemm_planes_i64", ptr(pa1), ptr(pb1), ptr(pa2) if pa2 is not None else None,
+             ptr(pb2) if pb2 is not None else None, ptr(Cinit) if Cinit is not None else None, rows, K, N, ptr(C), stream())
+    return C
+
+
 def tc_supported(rows, K, N):
     from .._lib import lib
 

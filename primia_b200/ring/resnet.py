@@ -9,12 +9,18 @@ its online phase in a CUDA graph (single- or multi-GPU placement).  ``SharedLine
 forward."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import functional as F
 from . import ops
 from .spdz import Party, TripleProvider
 from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
+
+# PRIMIA_HOIST_WEIGHT_SIDE=0: the online graph runs the whole Beaver protocol per layer (mask and open the weights, planarise
+# all four operands) as the reference's spdz_mul does per call; 1: the image-independent half moves to the offline graph
+HOIST_WEIGHT_SIDE = os.environ.get("PRIMIA_HOIST_WEIGHT_SIDE", "1") != "0"
 
 # (name, Cin, H_in, Cout, k, stride, pad) for a 224x224 input -- torchlib/models.py:379-405,425-464
 RESNET18_CONVS = [("conv1", 3, 224, 64, 7, 2, 3)]
@@ -28,6 +34,24 @@ for _li, (_planes, _stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)]
         if _st != 1 or _c != _planes:
             RESNET18_CONVS.append((f"layer{_li}.{_bi}.downsample.0", _c, _h, _planes, 1, _st, 0))
         _c, _h = _planes, _ho
+
+
+def conv_geometry(input_size=224):
+    """RESNET18_CONVS for any input size: (name, Cin, H_in, Cout, k, stride, pad), walking the forward's own size arithmetic"""
+    h = (input_size + 2 * 3 - 7) // 2 + 1
+    out = [("conv1", 3, input_size, 64, 7, 2, 3)]
+    h = (h + 2 - 3) // 2 + 1                      # max-pool 3x3 s2 p1
+    c = 64
+    for li, (planes, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], start=1):
+        for bi in range(2):
+            st = stride if bi == 0 else 1
+            out.append((f"layer{li}.{bi}.conv1", c, h, planes, 3, st, 1))
+            ho = (h + 2 - 3) // st + 1
+            out.append((f"layer{li}.{bi}.conv2", planes, ho, planes, 3, 1, 1))
+            if st != 1 or c != planes:
+                out.append((f"layer{li}.{bi}.downsample.0", c, h, planes, 1, st, 0))
+            c, h = planes, ho
+    return out
 
 
 def triple_shapes(batch=1, num_classes=3):
@@ -77,11 +101,23 @@ class SharedLinearLayers:
             for _name, shapes in triple_shapes(batch, self.ncls):
                 self.provider.provide_primitives("matmul", shapes, self.parties, 1)
 
+    def prepare_weight_side(self, triples, batch=1):
+        """image-independent half of every layer from ``triples`` (per layer, per party), see EncryptedResNet18"""
+        ws = {}
+        for (name, C, H, Co, k, s, p), tri in zip(RESNET18_CONVS, triples):
+            Ho = (H + 2 * p - k) // s + 1
+            w = F.prepare_weight_side(self.weights[name], tri, batch, Ho, Ho)
+            if w is not None:
+                ws[name] = w
+        return ws
+
+    wside = {}
+
     def forward(self, xs):
         """online phase of all 21 linear layers; returns {name: FixedPrecisionTensor}."""
         out = {}
         for name, C, H, Co, k, s, p in RESNET18_CONVS:
-            out[name] = F.conv2d(xs[name], self.weights[name], None, s, p)
+            out[name] = F.conv2d(xs[name], self.weights[name], None, s, p, prepared=self.wside.get(name))
         out["fc"] = F.linear(xs["fc"], self.fc_w, self.fc_b)
         return out
 
@@ -106,10 +142,19 @@ class EncryptedLinearGraph:
             net.forward(xs)  # warm-up: loads kernels, sizes the caching allocator
         torch.cuda.current_stream().wait_stream(side)
         self._refill_store()
+        self.wside = net.prepare_weight_side(self.static, batch) if HOIST_WEIGHT_SIDE else {}
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = net.forward(xs)
+        from .. import _lib
+
+        net.wside = self.wside
+        l0 = _lib.launch_counter
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = net.forward(xs)
+        finally:
+            net.wside = {}
+        self.launches = _lib.launch_counter - l0     # kernels (and memsets) of one online replay
 
     def _refill_store(self):
         for (_name, shapes), per_party in zip(triple_shapes(self.batch, self.net.ncls), self.static):
@@ -124,6 +169,12 @@ class EncryptedLinearGraph:
             for j in range(len(parties)):
                 for dst, src in zip(per_party[j], fresh[j]):
                     dst.copy_(src, non_blocking=True)
+        if self.wside:    # ... and the image-independent half of every layer, into the planes the graph reads
+            fresh = self.net.prepare_weight_side(self.static, self.batch)
+            for name, st in self.wside.items():
+                for attr in ("pb1", "pb2", "pa2"):
+                    for dst, src in zip(getattr(st, attr), getattr(fresh[name], attr)):
+                        dst.copy_(src, non_blocking=True)
 
     def online(self):
         self.graph.replay()
@@ -144,6 +195,7 @@ class EncryptedResNet18:
         self.base, self.pf, self.input_size = base, precision_fractional, input_size
         self.taps = None
         self.rng = rng
+        self.wside = {}    # weight name -> functional.WeightSide (prepare_weight_side; empty = every layer runs the whole protocol)
 
     @classmethod
     def from_state_dict(cls, state_dict, parties, provider, base=10, precision_fractional=16, input_size=224, rng=None):
@@ -186,6 +238,32 @@ class EncryptedResNet18:
         inv = T.reciprocal_newton_batched([self.P[n + ".running_var"] for n in self.BN_ORDER])
         return dict(zip(self.BN_ORDER, inv))
 
+    def _conv(self, x, name, stride, pad):
+        return F.conv2d(x, self.P[name + ".weight"], None, stride, pad, prepared=self.wside.get(name))
+
+    def prepare_weight_side(self, batch: int = 1):
+        """Offline half of the 20 Beaver convolutions: for every layer, in forward order, peek the triple it is going to consume
+        and run everything that does not involve the image -- mask + open the weights, build the limb planes of b (+ eps), eps
+        and a (functional.prepare_weight_side).  The online forward of a layer is then mask -> open+planarise -> GEMM -> truncate.
+        Needs the stores filled for exactly one forward (``preprocess(1)``)."""
+        from .spdz import _key
+
+        self.wside = {}
+        seen = {}
+        pdev = self.provider.provider.device
+        for p in self.parties:   # the triples were copied from the provider's GPU on ITS stream
+            if p.device != pdev:
+                torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(pdev))
+        for name, C, Hin, Co, k, s, pd in conv_geometry(self.input_size):
+            Ho = (Hin + 2 * pd - k) // s + 1
+            shapes = ((batch, Ho * Ho, C * k * k), (C * k * k, Co))
+            i = seen.get(_key(shapes), 0)
+            seen[_key(shapes)] = i + 1
+            tri = [p.crypto_store._stacks["matmul"][_key(shapes)][i] for p in self.parties]
+            ws = F.prepare_weight_side(self.P[name + ".weight"], tri, batch, Ho, Ho)
+            if ws is not None:
+                self.wside[name] = ws
+
     def _bn(self, x, name):
         P = self.P
         return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"],
@@ -194,7 +272,7 @@ class EncryptedResNet18:
     def forward(self, x: FixedPrecisionTensor) -> FixedPrecisionTensor:
         P = self.P
         self._inv = self._newton_all()
-        x = self._tap("conv1", F.conv2d(x, P["conv1.weight"], None, 2, 3))
+        x = self._tap("conv1", self._conv(x, "conv1", 2, 3))
         x = self._tap("bn1", self._bn(x, "bn1"))
         x = self._tap("pool", F.max_pool2d(x, 3, 2, 1))       # model.relu <- model.pool (inference.py:289)
         x = self._tap("relu", F.relu(x))                       # model.pool <- model.relu
@@ -204,12 +282,12 @@ class EncryptedResNet18:
                 st = stride if bi == 0 else 1
                 pre = f"layer{li}.{bi}"
                 identity = x
-                out = F.conv2d(x, P[pre + ".conv1.weight"], None, st, 1)
+                out = self._conv(x, pre + ".conv1", st, 1)
                 out = F.relu(self._bn(out, pre + ".bn1"))
-                out = F.conv2d(out, P[pre + ".conv2.weight"], None, 1, 1)
+                out = self._conv(out, pre + ".conv2", 1, 1)
                 out = self._bn(out, pre + ".bn2")
                 if st != 1 or inplanes != planes:
-                    identity = self._bn(F.conv2d(x, P[pre + ".downsample.0.weight"], None, st, 0), pre + ".downsample.1")
+                    identity = self._bn(self._conv(x, pre + ".downsample.0", st, 0), pre + ".downsample.1")
                 out = out + identity
                 x = self._tap(pre, F.relu(out))
                 inplanes = planes
@@ -345,6 +423,8 @@ class EncryptedInferenceGraph:
             net.rng.bump_epoch()
             net.preprocess(1)
             net.rng.refresh_static()
+            if HOIST_WEIGHT_SIDE:
+                net.prepare_weight_side(example.shape[0])    # the image-independent half of every Beaver convolution
 
         self._off.capture(generate)
         self.bytes_per_image = net.provider.generated_bytes - b0
@@ -366,6 +446,7 @@ class EncryptedInferenceGraph:
         self.graph = self._on.graph
         self.kernels_in_graph = _lib.launch_counter - l0
         net.rng.mode = "live"
+        self.wside, net.wside = net.wside, {}      # the planes belong to the graphs; an eager net.forward runs the whole protocol
         for p in net.parties:
             p.crypto_store.clear()
 

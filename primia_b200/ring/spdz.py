@@ -301,6 +301,21 @@ def open_shares(parties, shares):
     return outs
 
 
+def open_planes(parties, shares):
+    """``open_shares`` for a value that is only ever used as the LEFT operand of the limb-plane ring GEMM: each party's kernel
+    adds the peer's masked share (peer-mapped pointer when it sits on another GPU) and writes the byte planes of the sum."""
+    outs = []
+    for j, p in enumerate(parties):
+        peer = shares[1 - j]
+        if peer.device != p.device:
+            torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(peer.device))
+            if not _ensure_peer(p.device, peer.device):
+                peer = peer.to(p.device)
+        outs.append(ops.planarize_rows(shares[j], peer))
+    release_after_peer_reads(parties)
+    return outs
+
+
 def release_after_peer_reads(parties):
     """After a symmetric exchange each GPU has just read the other's buffer through a peer pointer.  The caching allocator
     only orders a block's reuse on the OWNER's stream, so the owner's stream is made to wait for the reader's kernel: without

@@ -146,6 +146,19 @@ def _shared_conv_case(ring, g, B, C, H, Co, k, s, p, base, pf):
     out = ring.functional.conv2d(X, Wt, None, s, p)
     for j in range(2):
         assert torch.equal(out.child.child[j].cpu(), ref[j]), (C, H, Co, k, s, p, j)
+    # the same layer with its image-independent half hoisted (offline: mask + open the weights, limb planes of a, b + eps, eps;
+    # online: mask x, open INTO the planes, one 2-segment GEMM): same shares, bit for bit
+    gpu_tri = [tuple(cu(t) for t in tri[j]) for j in range(2)]
+    prep = ring.functional.prepare_weight_side(Wt, gpu_tri, B, Ho, Ho)
+    from primia_b200.ring import ops
+    assert (prep is not None) == bool(ops.tc_supported(B * M, K, N))
+    if prep is not None:
+        for j, pty in enumerate(parties):
+            pty.crypto_store.add_primitives("matmul", ((B, M, K), (K, N)), [gpu_tri[j]])
+        out2 = ring.functional.conv2d(X, Wt, None, s, p, prepared=prep)
+        assert all(pty.crypto_store.count("matmul", ((B, M, K), (K, N))) == 0 for pty in parties)   # popped like spdz_compute
+        for j in range(2):
+            assert torch.equal(out2.child.child[j].cpu(), ref[j]), ("hoisted", C, H, Co, k, s, p, j)
 
 
 @pytest.mark.parametrize("base,pf", [(10, 16), (10, 4)])

@@ -324,7 +324,8 @@ def test_maxpool_tie_breaking_matches_aten():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("P,C,masked,emit_g", [(3136, 512, True, False), (50000, 64, True, True), (777, 128, False, False)])
+@pytest.mark.parametrize("P,C,masked,emit_g", [(3136, 512, True, False), (50000, 64, True, True), (777, 128, False, False),
+                                               (12544, 256, True, True), (3136, 512, False, True)])
 def test_bn_backward_single_launch_matches_two_kernel_path(dtype, P, C, masked, emit_g):
     """pm_bn_bwd_fused_* (reduce -> grid barrier -> apply in one launch) == pm_bn_bwd_reduce_* + pm_bn_bwd_apply_*;
     run twice to exercise the self-resetting barrier state."""
