@@ -140,6 +140,13 @@ int pm_bn_newton_p2p_i64(int party, const pm_newton_p2p_job_t* jobs, int n_jobs,
                          void* inbox, void* peer_inbox, uint64_t* epoch, int max_channels, int* err, pm_stream_t s);
 /* avg pool k x k, stride k on one share: sum / (k*k) with trunc  functional.py:460-525 + additive_shared.py:720-729 */
 int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t* out, pm_stream_t s);
+/* One elementwise pass of a hoisted Beaver product with a per-channel operand on NCHW shares (nn/functional.py:44-75 batch_norm:
+ * x * (flat - mean), normalized * weight + bias).  With the operand that depends only on the model opened in the offline phase,
+ * spdz_compute (spdz.py:64-122) collapses to  z_j = s_j[c] * open(masked)[i] + d_j[i]  and the whole layer is three passes per party:
+ *   out[i] = T( sc[c] * (u[i] + peer[i]) + add[i] ) + cs * chan[c] + es * elem[i],  c = (i / HW) % C,
+ * T = C-style division by div (precision.py:146-160) when div > 1.  NULL operands drop out; cs, es in {-1, 0, +1}. */
+int pm_spdz_affine_i64(const int64_t* u, const int64_t* peer, const int64_t* sc, const int64_t* add, int64_t div, const int64_t* chan,
+                       int cs, const int64_t* elem, int es, int C, int HW, size_t n, int64_t* out, pm_stream_t s);
 /* batch_norm layout shuffles functional.py:52-55,70-73: NCHW [B,C,H,W] <-> [P=B*H*W, C] */
 int pm_nchw_to_pc_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);
 int pm_pc_to_nchw_i64(const int64_t* x, int B, int C, int HW, int64_t* out, pm_stream_t s);

@@ -108,6 +108,31 @@ __global__ void axpby_kernel(int64_t alpha, const int64_t* __restrict__ x, int64
   }
 }
 
+// ---- one elementwise pass of a HOISTED Beaver product with a per-channel operand, NCHW (ring/functional.py batch_norm):
+//   out[i] = T( sc[c] * (u[i] + peer[i]) + add[i] ) + cs * chan[c] + es * elem[i],   c = (i / HW) % C
+// with T = C-style division by `div` (div > 1) or the identity.  NULL operands drop out (sc -> 1).  `peer` is the other party's
+// masked share (the opening, spdz.py:162-163; possibly a peer-mapped pointer), everything else is local.  All arithmetic wraps
+// mod 2^64 exactly as the share-level torch ops of the reference do.
+__global__ void spdz_affine_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ peer, const int64_t* __restrict__ sc,
+                                   const int64_t* __restrict__ add, int64_t div, const int64_t* __restrict__ chan, int cs,
+                                   const int64_t* __restrict__ elem, int es, int C, int HW, size_t n, int64_t* __restrict__ out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int c = (int)((i / (size_t)HW) % (size_t)C);
+    u64 v = (u64)u[i];
+    if (peer) v += (u64)peer[i];
+    if (sc) v *= (u64)sc[c];
+    if (add) v += (u64)add[i];
+    int64_t t = (int64_t)v;
+    if (div > 1) t = t / div;
+    u64 r = (u64)t;
+    if (chan) r += (u64)(int64_t)cs * (u64)chan[c];
+    if (elem) r += (u64)(int64_t)es * (u64)elem[i];
+    out[i] = (int64_t)r;
+  }
+}
+
 __global__ void trunc_div_kernel(const int64_t* __restrict__ x, int64_t div, int64_t* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -722,6 +747,15 @@ int pm_avgpool_i64(const int64_t* x, int B, int C, int H, int W, int k, int64_t*
   PM_CHECK_ARG(x && out && k > 0 && H % k == 0 && W % k == 0);
   const size_t total = (size_t)B * C * (H / k) * (W / k);
   avgpool_kernel<<<pm_grid(total, 128), 128, 0, S(s)>>>(x, H, W, k, out, total);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_affine_i64(const int64_t* u, const int64_t* peer, const int64_t* sc, const int64_t* add, int64_t div, const int64_t* chan,
+                       int cs, const int64_t* elem, int es, int C, int HW, size_t n, int64_t* out, pm_stream_t s) {
+  PM_CHECK_ARG(u && out && div >= 1 && C >= 1 && HW >= 1 && n % ((size_t)C * HW) == 0 && (cs == 0 || chan) && (es == 0 || elem) &&
+               cs >= -1 && cs <= 1 && es >= -1 && es <= 1);
+  if (n == 0) return 0;
+  spdz_affine_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(u, peer, sc, add, div, cs ? chan : nullptr, cs, es ? elem : nullptr, es, C, HW, n, out);
   PM_LAUNCH_OK();
 }
 

@@ -30,19 +30,22 @@ def _post_conv(bias, res, batch_size, nb_channels_out, nb_rows_out, nb_cols_out)
 
 
 class WeightSide:
-    """Everything of one Beaver matmul that does NOT depend on the image, per party j: limb planes of b_j (+ eps on party 0),
-    of eps and of a_j.  Built by ``prepare_weight_side`` in the offline phase, consumed by ``conv2d(..., prepared=)``."""
+    """Everything of one Beaver matmul that does NOT depend on the image, per party j: the limb planes of the right operand
+    b_j (+ eps on party 0) and c'_j = a_j @ eps + c_j.  Built by ``prepare_weight_side`` in the offline phase, consumed by
+    ``conv2d(..., prepared=)``."""
 
-    __slots__ = ("shapes", "pb1", "pb2", "pa2")
+    __slots__ = ("shapes", "pb1", "cprime")
+    TENSORS = ("pb1", "cprime")
 
-    def __init__(self, shapes, pb1, pb2, pa2):
-        self.shapes, self.pb1, self.pb2, self.pa2 = shapes, pb1, pb2, pa2
+    def __init__(self, shapes, pb1, cprime):
+        self.shapes, self.pb1, self.cprime = shapes, pb1, cprime
 
 
 def prepare_weight_side(weight: FixedPrecisionTensor, tri, batch: int, Ho: int, Wo: int):
     """The weight half of spdz_mul for one convolution (spdz.py:22-45,162-163), hoisted out of the per-image path:
-    eps = open(w_j^T - b_j); party 0's right operand b_0 + eps; limb planes of those and of a_j.  ``tri``: the per-party triple
-    the layer is going to consume (peeked, not popped).  Returns None when the shape does not run on the tensor cores."""
+    eps = open(w_j^T - b_j); party 0's right operand b_0 + eps as limb planes; c'_j = a_j @ eps + c_j (one ring GEMM per party, so
+    that the online product is the single segment  z_j = delta @ (b_j [+ eps]) + c'_j).  ``tri``: the per-party triple the layer is
+    going to consume (peeked, not popped).  Returns None when the shape does not run on the tensor cores."""
     w = weight.child
     Co = w.shape[0]
     K = w.child[0].numel() // Co
@@ -53,9 +56,9 @@ def prepare_weight_side(weight: FixedPrecisionTensor, tri, batch: int, Ho: int, 
     e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
     eps = open_shares(parties, e_sh)
     pb1 = [ops.planarize_cols(ops.axpby(1, tri[0][1], 1, eps[0])), ops.planarize_cols(tri[1][1])]
-    pb2 = [ops.planarize_cols(eps[j]) for j in range(2)]
-    pa2 = [ops.planarize_rows(tri[j][0]) for j in range(2)]
-    return WeightSide(((batch, Ho * Wo, K), (K, Co)), pb1, pb2, pa2)
+    cprime = [ops.gemm_planes(ops.planarize_rows(tri[j][0]), ops.planarize_cols(eps[j]), None, None, tri[j][2].reshape(rows, Co),
+                              rows, K, Co) for j in range(2)]
+    return WeightSide(((batch, Ho * Wo, K), (K, Co)), pb1, cprime)
 
 
 def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None, stride=1, padding=0, dilation=1,
@@ -88,15 +91,14 @@ def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None,
             provider.provide_primitives(parties=parties, **e.kwargs_)
     d_sh = [ops.mask_im2col(x.child[j], tri[j][0], kh, kw, stride, padding, dilation) for j in range(2)]
     if prepared is not None:
-        # online half only: delta is opened INTO its limb planes (never materialised), then one 2-segment GEMM per party
-        #   z_j = delta @ (b_j [+ eps]) + a_j @ eps + c_j
+        # online half only: delta is opened INTO its limb planes (never materialised), then one GEMM per party
+        #   z_j = delta @ (b_j [+ eps]) + c'_j ,  c'_j = a_j @ eps + c_j from the offline phase
         assert prepared.shapes == _key(shapes), (prepared.shapes, shapes)
         pd = open_planes(parties, d_sh)
         z = []
         for j, p in enumerate(parties):
-            _a, _b, c = p.crypto_store.get_keys(op="matmul", shapes=shapes, remove=True)      # the pop of spdz_compute (spdz.py:84)
-            z.append(ops.gemm_planes(pd[j], prepared.pb1[j], prepared.pa2[j], prepared.pb2[j], c.reshape(B * M, N), B * M, K,
-                                     N).view(B, M, N))
+            p.crypto_store.get_keys(op="matmul", shapes=shapes, remove=True)      # the pop of spdz_compute (spdz.py:84)
+            z.append(ops.gemm_planes(pd[j], prepared.pb1[j], None, None, prepared.cprime[j], B * M, K, N).view(B, M, N))
     else:
         e_sh = [ops.mask_wt(w.child[j].reshape(Co, K), tri[j][1]) for j in range(2)]
         delta = open_shares(parties, d_sh)
@@ -109,6 +111,90 @@ def conv2d(input: FixedPrecisionTensor, weight: FixedPrecisionTensor, bias=None,
         out = [ops.axpby(1, out[j].permute(0, 2, 3, 1).contiguous(), 1, bsh[j]).permute(0, 3, 1, 2).contiguous()
                for j in range(2)]
     return FixedPrecisionTensor(x._new(out), input.base, input.precision_fractional)
+
+
+class BNSide:
+    """The image-independent half of one BatchNorm layer on shares, per party j (NCHW layout, see ``prepare_bn_side``)."""
+
+    __slots__ = ("keys", "s1", "d1", "b1", "s2", "d2", "a2")
+    TENSORS = ("s1", "d1", "b1", "s2", "d2", "a2")
+
+    def __init__(self, keys, **kw):
+        self.keys = keys
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def prepare_bn_side(inv_std: FixedPrecisionTensor, weight: FixedPrecisionTensor, tri1, tri2, B, C, H, W):
+    """batch_norm (functional.py:44-75) is two Beaver products with one operand that depends only on the model:
+
+      normalized = inv_std * (flat - mean)      triple 1 = (a1 [C], b1 [P,C], c1 [P,C])
+      result     = normalized * weight + bias   triple 2 = (a2 [P,C], b2 [C], c2 [P,C])
+
+    With delta1 = open(inv_std - a1) and eps2 = open(weight - b2) known offline, spdz_compute (spdz.py:64-122) collapses to
+      z1_j = s1_j[c] * eps1 + d1_j ,  s1_j = a1_j + [j=0] delta1 ,  d1_j = delta1 * b1_j + c1_j
+      z2_j = s2_j[c] * delta2 + d2_j ,  s2_j = b2_j + [j=0] eps2 ,  d2_j = a2_j * eps2 + c2_j
+    (exact in Z_2^64).  The [P,C] operands are stored NCHW so the online passes need no layout shuffle."""
+    parties = inv_std.child.parties
+    x, w = inv_std.child.child, weight.child.child
+    delta1 = open_shares(parties, [ops.mask(x[j], tri1[j][0]) for j in range(2)])
+    eps2 = open_shares(parties, [ops.mask(w[j], tri2[j][1]) for j in range(2)])
+    nchw = lambda t: ops.pc_to_nchw(t, B, C, H, W)
+    out = {k: [] for k in BNSide.TENSORS}
+    for j in range(2):
+        a1, b1, c1 = tri1[j]
+        a2, b2, c2 = tri2[j]
+        out["s1"].append(ops.axpby(1, a1, 1, delta1[j]) if j == 0 else a1)
+        out["s2"].append(ops.axpby(1, b2, 1, eps2[j]) if j == 0 else b2)
+        # combine_mul(1, delta, eps, a, b, c) = delta * b + a * eps + c with the [C] x [P,C] broadcasts
+        out["d1"].append(nchw(ops.combine_mul(1, delta1[j], torch.zeros_like(b1), torch.zeros_like(a1), b1, c1)))
+        out["d2"].append(nchw(ops.combine_mul(1, torch.zeros_like(a2), eps2[j], a2, torch.zeros_like(b2), c2)))
+        out["b1"].append(nchw(b1))
+        out["a2"].append(nchw(a2))
+    P = B * H * W
+    return BNSide((((C,), (P, C)), ((P, C), (C,))), **out)
+
+
+def _exchange(parties, shares):
+    """the event edges of ``open_shares`` for kernels that read the peer's masked share themselves: returns, per party, the
+    peer's tensor (peer-mapped pointer or a staged copy)"""
+    from .spdz import _ensure_peer
+
+    peers = []
+    for j, p in enumerate(parties):
+        peer = shares[1 - j]
+        if peer.device != p.device:
+            torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(peer.device))
+            if not _ensure_peer(p.device, peer.device):
+                peer = peer.to(p.device)
+        peers.append(peer)
+    return peers
+
+
+def batch_norm_prepared(input: FixedPrecisionTensor, running_mean, bias, side: BNSide):
+    """online half of batch_norm with ``side`` from the offline phase: three elementwise passes per party, NCHW throughout
+         eps1_j   = x_j - mean_j[c] - b1_j
+         delta2_j = trunc(s1_j[c] * open(eps1) + d1_j) - a2_j
+         out_j    = trunc(s2_j[c] * open(delta2) + d2_j) + bias_j[c]
+    -- the same shares as the op-by-op evaluation (tests/test_ring_gpu.py)."""
+    from .spdz import release_after_peer_reads
+
+    ast = input.child
+    parties = ast.parties
+    B, C, H, W = ast.shape
+    HW, D = H * W, input.base ** input.precision_fractional
+    mean, bs = running_mean.child.child, bias.child.child
+    for p in parties:                      # the two pops of spdz_compute (spdz.py:84)
+        for key in side.keys:
+            p.crypto_store.get_keys(op="mul", shapes=key, remove=True)
+    e1 = [ops.spdz_affine(ast.child[j], None, None, None, 1, mean[j], -1, side.b1[j], -1, C, HW) for j in range(2)]
+    pe = _exchange(parties, e1)
+    d2 = [ops.spdz_affine(e1[j], pe[j], side.s1[j], side.d1[j], D, None, 0, side.a2[j], -1, C, HW) for j in range(2)]
+    release_after_peer_reads(parties)
+    pd = _exchange(parties, d2)
+    out = [ops.spdz_affine(d2[j], pd[j], side.s2[j], side.d2[j], D, bs[j], 1, None, 0, C, HW) for j in range(2)]
+    release_after_peer_reads(parties)
+    return input._new(ast._new(out))
 
 
 def batch_norm(input: FixedPrecisionTensor, running_mean, running_var, weight, bias, training=False,

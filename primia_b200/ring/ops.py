@@ -292,6 +292,18 @@ def axpby(alpha: int, x, beta: int = 0, y=None):
     return out
 
 
+def spdz_affine(u, peer, sc, add, div: int, chan, cs: int, elem, es: int, C: int, HW: int):
+    """out[i] = T(sc[c] * (u[i] + peer[i]) + add[i]) + cs * chan[c] + es * elem[i] on NCHW shares, c = (i // HW) % C; T = C-style
+    division by ``div`` when div > 1.  None operands drop out.  One pass of a hoisted Beaver product (functional.batch_norm)."""
+    u = _chk(u)
+    out = torch.empty_like(u)
+    o = lambda t: ptr(_chk(t)) if t is not None else None
+    with torch.cuda.device(u.device):
+        call("pm_spdz_affine_i64", ptr(u), o(peer), o(sc), o(add), int(div), o(chan), int(cs), o(elem), int(es), int(C), int(HW),
+             u.numel(), ptr(out), stream())
+    return out
+
+
 def avgpool(x, k: int):
     x = _chk(x)
     B, C, H, W = x.shape

@@ -18,8 +18,9 @@ from . import ops
 from .spdz import Party, TripleProvider
 from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
 
-# PRIMIA_HOIST_WEIGHT_SIDE=0: the online graph runs the whole Beaver protocol per layer (mask and open the weights, planarise
-# all four operands) as the reference's spdz_mul does per call; 1: the image-independent half moves to the offline graph
+# PRIMIA_HOIST_WEIGHT_SIDE=0: the online graph runs the whole protocol per layer (mask and open the weights, planarise all four
+# operands, Newton iterations, op-by-op BatchNorm) as the reference does per call; 1: everything that depends only on the model
+# and the primitives moves to the offline graph (EncryptedResNet18.prepare_offline_side)
 HOIST_WEIGHT_SIDE = os.environ.get("PRIMIA_HOIST_WEIGHT_SIDE", "1") != "0"
 
 # (name, Cin, H_in, Cout, k, stride, pad) for a 224x224 input -- torchlib/models.py:379-405,425-464
@@ -172,7 +173,7 @@ class EncryptedLinearGraph:
         if self.wside:    # ... and the image-independent half of every layer, into the planes the graph reads
             fresh = self.net.prepare_weight_side(self.static, self.batch)
             for name, st in self.wside.items():
-                for attr in ("pb1", "pb2", "pa2"):
+                for attr in F.WeightSide.TENSORS:
                     for dst, src in zip(getattr(st, attr), getattr(fresh[name], attr)):
                         dst.copy_(src, non_blocking=True)
 
@@ -195,7 +196,10 @@ class EncryptedResNet18:
         self.base, self.pf, self.input_size = base, precision_fractional, input_size
         self.taps = None
         self.rng = rng
-        self.wside = {}    # weight name -> functional.WeightSide (prepare_weight_side; empty = every layer runs the whole protocol)
+        # image-independent halves prepared by the offline phase (prepare_offline_side); empty = every layer runs the whole protocol
+        self.wside = {}          # conv name -> functional.WeightSide
+        self.bnside = {}         # BatchNorm name -> functional.BNSide
+        self.hoisted_inv = None  # {BatchNorm name: inverse standard deviation} when the Newton iterations ran offline
 
     @classmethod
     def from_state_dict(cls, state_dict, parties, provider, base=10, precision_fractional=16, input_size=224, rng=None):
@@ -250,10 +254,6 @@ class EncryptedResNet18:
 
         self.wside = {}
         seen = {}
-        pdev = self.provider.provider.device
-        for p in self.parties:   # the triples were copied from the provider's GPU on ITS stream
-            if p.device != pdev:
-                torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(pdev))
         for name, C, Hin, Co, k, s, pd in conv_geometry(self.input_size):
             Ho = (Hin + 2 * pd - k) // s + 1
             shapes = ((batch, Ho * Ho, C * k * k), (C * k * k, Co))
@@ -264,14 +264,75 @@ class EncryptedResNet18:
             if ws is not None:
                 self.wside[name] = ws
 
+    NEWTON_ITERS = 80
+
+    def prepare_offline_side(self, batch: int = 1):
+        """Everything of one forward that depends on the model and the primitives but not on the image, run once per image in
+        the OFFLINE phase: the 80-step Newton inverse square roots of all BatchNorm layers, the weight half of the 20 Beaver
+        convolutions (prepare_weight_side) and the model-only operands of the 40 BatchNorm products (prepare_bn_side).  The stores
+        must hold the primitives of exactly one forward.  Nothing is consumed: the online forward still pops every primitive (and
+        advances the share RNG) where the op-by-op protocol would, so the two stay interchangeable primitive for primitive."""
+        from . import tensors as T
+
+        pdev = self.provider.provider.device
+        for p in self.parties:   # the primitives were copied from the provider's GPU on ITS stream
+            if p.device != pdev:
+                torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(pdev))
+        self.hoisted_inv, self.bnside = None, {}
+        if T.FUSE_NEWTON and self.rng is not None and self.rng.static:
+            snaps = [p.crypto_store.export_state() for p in self.parties]
+            mode, cur = self.rng.mode, self.rng.cursor
+            self.rng.mode, self.rng.cursor = "replay", 0       # the constants' sharings are the first entries of a forward
+            inv = self._newton_all()
+            self.rng.mode, self.rng.cursor = mode, cur
+            for p, st in zip(self.parties, snaps):
+                p.crypto_store.import_state(st)
+            self.hoisted_inv = inv
+        self.prepare_weight_side(batch)
+        if self.hoisted_inv is not None:
+            self.prepare_bn_side(batch)
+
+    def prepare_bn_side(self, batch: int = 1):
+        from .spdz import _key
+
+        geo = {name: (Co, (Hin + 2 * pd - k) // s + 1) for name, _C, Hin, Co, k, s, pd in conv_geometry(self.input_size)}
+        seen = {}
+        for bn in self.BN_ORDER:
+            conv = "conv1" if bn == "bn1" else bn.replace("downsample.1", "downsample.0").replace(".bn", ".conv")
+            C, H = geo[conv]
+            P = batch * H * H
+            tris = []
+            for key in (((C,), (P, C)), ((P, C), (C,))):
+                i = seen.get(_key(key), 0)
+                seen[_key(key)] = i + 1
+                tris.append([p.crypto_store._stacks["mul"][_key(key)][i] for p in self.parties])
+            self.bnside[bn] = F.prepare_bn_side(self.hoisted_inv[bn], self.P[bn + ".weight"], tris[0], tris[1], batch, C, H, H)
+
+    def _newton_bookkeeping(self):
+        """the pops and share-RNG draws of ``_newton_all`` without its arithmetic (the result came from the offline phase)"""
+        from .spdz import take_primitives
+
+        assert self.rng.mode == "replay"
+        for bn in self.BN_ORDER:
+            ast = self.P[bn + ".running_var"].child
+            n = ast.child[0].shape[0]
+            take_primitives("mul", ((n,), (n,)), 3 * (self.NEWTON_ITERS - 1), ast.parties, None)
+            self.rng.cursor += 1
+
     def _bn(self, x, name):
         P = self.P
+        if name in self.bnside:
+            return F.batch_norm_prepared(x, P[name + ".running_mean"], P[name + ".bias"], self.bnside[name])
         return F.batch_norm(x, P[name + ".running_mean"], P[name + ".running_var"], P[name + ".weight"], P[name + ".bias"],
                             inv_std=self._inv.get(name))
 
     def forward(self, x: FixedPrecisionTensor) -> FixedPrecisionTensor:
         P = self.P
-        self._inv = self._newton_all()
+        if self.hoisted_inv is not None:
+            self._newton_bookkeeping()
+            self._inv = self.hoisted_inv
+        else:
+            self._inv = self._newton_all()
         x = self._tap("conv1", self._conv(x, "conv1", 2, 3))
         x = self._tap("bn1", self._bn(x, "bn1"))
         x = self._tap("pool", F.max_pool2d(x, 3, 2, 1))       # model.relu <- model.pool (inference.py:289)
@@ -424,7 +485,7 @@ class EncryptedInferenceGraph:
             net.preprocess(1)
             net.rng.refresh_static()
             if HOIST_WEIGHT_SIDE:
-                net.prepare_weight_side(example.shape[0])    # the image-independent half of every Beaver convolution
+                net.prepare_offline_side(example.shape[0])   # Newton, the weight half of every Beaver convolution, BatchNorm operands
 
         self._off.capture(generate)
         self.bytes_per_image = net.provider.generated_bytes - b0
@@ -446,7 +507,9 @@ class EncryptedInferenceGraph:
         self.graph = self._on.graph
         self.kernels_in_graph = _lib.launch_counter - l0
         net.rng.mode = "live"
-        self.wside, net.wside = net.wside, {}      # the planes belong to the graphs; an eager net.forward runs the whole protocol
+        # the hoisted operands belong to the graphs; an eager net.forward runs the whole protocol op by op
+        self.wside, self.bnside, self.hoisted_inv = net.wside, net.bnside, net.hoisted_inv
+        net.wside, net.bnside, net.hoisted_inv = {}, {}, None
         for p in net.parties:
             p.crypto_store.clear()
 

@@ -367,9 +367,11 @@ def test_encrypted_inference_graph_replay_equals_eager_protocol(ring):
     net = ring.EncryptedResNet18.from_state_dict(model.state_dict(), parties, prov, base, pf, input_size=size)
     g = torch.Generator().manual_seed(9)
     eg = EncryptedInferenceGraph(net, torch.randn(1, 3, size, size, generator=g))
-    # the graphs run the hoisted protocol (weight half of all 20 convolutions in the offline graph); the eager forward below runs
+    # the graphs run the hoisted protocol (Newton, the weight half of all 20 convolutions and the model-only BatchNorm operands
+    # in the offline graph); the eager forward below runs
     # the whole protocol per layer, as the reference's spdz_mul does -- the shares must agree bit for bit
-    assert len(eg.wside) == 20 and net.wside == {}
+    assert len(eg.wside) == 20 and len(eg.bnside) == 20 and eg.hoisted_inv is not None
+    assert net.wside == {} and net.bnside == {} and net.hoisted_inv is None
     model.pool, model.relu = model.relu, model.pool
     prev = None
     for it in range(2):

@@ -273,6 +273,24 @@ def test_batch_norm_eval_newton_bit_exact(ring):
         T.FUSE_NEWTON = True
     for j in range(2):
         assert torch.equal(out2.child.child[j].cpu(), ref[j])
+    # the hoisted evaluation (offline: Newton, open(inv_std - a1), open(weight - b2), d1, d2 in NCHW; online: three elementwise
+    # passes per party) produces the same shares as the oracle's op-by-op protocol
+    for j, pty in enumerate(parties):
+        for it in range(1, iters):
+            for t in triples[it]:
+                pty.crypto_store.add_primitives("mul", ((C,), (C,)), [tuple(cu(u) for u in t[j])])
+    rng.s0 = list(c_s0)
+    inv = mk(v_sh).reciprocal(method="newton")
+    gt = lambda t: [tuple(cu(u) for u in t[j]) for j in range(2)]
+    t1, t2 = gt(tri_norm), gt(tri_aff)
+    side = ring.functional.prepare_bn_side(inv, mk(g_sh), t1, t2, B, C, H, W)
+    for j, pty in enumerate(parties):
+        pty.crypto_store.add_primitives("mul", ((C,), (P, C)), [t1[j]])
+        pty.crypto_store.add_primitives("mul", ((P, C), (C,)), [t2[j]])
+    out3 = ring.functional.batch_norm_prepared(mk(x_sh), mk(m_sh), mk(b_sh), side)
+    for j in range(2):
+        assert torch.equal(out3.child.child[j].cpu(), ref[j]), "hoisted batch_norm"
+    assert all(p.crypto_store.nbytes() == 0 for p in parties)
     # numerically sane at pf=4: decodes to the float batch norm (eps ignored) within fixed-point error
     got = R.decode(ref[0] + ref[1], base, pf)
     xf, mf, vf, gf, bf = (R.decode(t, base, pf) for t in (x, mean, var, gamma, beta))
