@@ -56,6 +56,13 @@ int pm_spdz_mask_i64(const int64_t* x, const int64_t* a, int64_t* delta, size_t 
 /* im2col-free fusion of _pre_conv + spdz_mask for the left operand: delta_j = im2col(x_j) - a_j */
 int pm_spdz_mask_im2col_i64(const int64_t* x, int B, int C, int H, int W, int kh, int kw, int stride, int pad,
                             int dil, const int64_t* a, int64_t* delta, pm_stream_t s);
+/* Elementwise Beaver product of two same-shape operands (AdditiveSharingTensor.mul -> spdz_mul, spdz.py:125-197; the ReLU and
+ * max-pool selects) in two launches per party: spdz_mask of both operands in one pass, then spdz_compute with the two openings
+ * fused -- delta = d_own + d_peer and eps = e_own + e_peer are formed in registers (peer pointers may be peer-mapped). */
+int pm_spdz_mask2_i64(const int64_t* x, const int64_t* a, const int64_t* y, const int64_t* b, int64_t* delta, int64_t* eps, size_t n,
+                      pm_stream_t s);
+int pm_spdz_combine_mul_open_i64(int j, const int64_t* d_own, const int64_t* d_peer, const int64_t* e_own, const int64_t* e_peer,
+                                 const int64_t* a, const int64_t* b, const int64_t* c, size_t n, int64_t* z, pm_stream_t s);
 /* right operand: weight_reshaped = w.reshape(Cout,-1).t() (functional.py:157) fused with spdz_mask:
  * eps_j[k,n] = w_j[n*K + k] - b_j[k*N + n] */
 int pm_spdz_mask_wt_i64(const int64_t* w, int N, int K, const int64_t* b, int64_t* eps, pm_stream_t s);
@@ -167,6 +174,11 @@ int pm_fss_dif_keygen(const uint64_t* alpha, const uint64_t* seeds, size_t n, si
  * [ (x_masked[i] mod 2^32) <= alpha[i] ]. */
 int pm_fss_dif_eval(int b, const int64_t* x_masked, const uint64_t* s0, const uint8_t* bits, const uint64_t* sigma_cw,
                     const uint64_t* s_cw, const int32_t* leaf, size_t n, size_t stride, int64_t* out, pm_stream_t s);
+/* the same evaluation with the opening of the masked difference fused (fss.py:158): x = (r_own + r_peer) mod 2^32 is formed in
+ * the kernel; r_peer may be a peer-mapped pointer into the other party's GPU */
+int pm_fss_dif_eval_open(int b, const int64_t* r_own, const int64_t* r_peer, const uint64_t* s0, const uint8_t* bits,
+                         const uint64_t* sigma_cw, const uint64_t* s_cw, const int32_t* leaf, size_t n, size_t stride, int64_t* out,
+                         pm_stream_t s);
 /* mask_builder  fss.py:189-204 : r_j = x1_j - x2_j + alpha_j ; x1 or x2 may be NULL (a public 0 operand) */
 int pm_fss_mask_i64(const int64_t* x1, const int64_t* x2, const int64_t* alpha_share, int64_t* r, size_t n, pm_stream_t s);
 /* opening of the masked difference  fss.py:158 : out = (local + peer) mod 2^32 ; `peer` may be peer-mapped (NVLink) */

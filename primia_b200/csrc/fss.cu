@@ -208,11 +208,12 @@ fss_dif_keygen_kernel(const uint64_t* __restrict__ alpha, const uint64_t* __rest
 
 // DIF.eval (fss.py:401-428): party b's int64 share of [x <= alpha] over the low 32 bits of x.
 __global__ void __launch_bounds__(128)
-fss_dif_eval_kernel(int b, const int64_t* __restrict__ x, const uint64_t* __restrict__ s0, const uint8_t* __restrict__ bits,
+fss_dif_eval_kernel(int b, const int64_t* __restrict__ x, const int64_t* __restrict__ peer /* != NULL: x + peer is opened here */,
+                    const uint64_t* __restrict__ s0, const uint8_t* __restrict__ bits,
                     const uint64_t* __restrict__ sigma_cw, const uint64_t* __restrict__ s_cw, const int32_t* __restrict__ leaf,
                     size_t n, size_t stride, int64_t* __restrict__ out) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t xv = (uint32_t)x[idx];
+    const uint32_t xv = (uint32_t)x[idx] + (peer ? (uint32_t)peer[idx] : 0u);   // the low 32 bits are all DIF reads
     uint64_t sa[1] = {s0[idx]}, sb[1] = {s0[stride + idx]};
     uint64_t t = (uint64_t)b;
     int64_t acc = 0;
@@ -331,7 +332,16 @@ extern "C" int pm_fss_dif_eval(int b, const int64_t* x_masked, const uint64_t* s
                                int64_t* out, pm_stream_t s) {
   if (n == 0) return PM_OK;
   PM_CHECK_ARG((b == 0 || b == 1) && x_masked && s0 && bits && sigma_cw && s_cw && leaf && out && stride >= n);
-  fss_dif_eval_kernel<<<pm_grid(n, 128, 1, 64), 128, 0, S(s)>>>(b, x_masked, s0, bits, sigma_cw, s_cw, leaf, n, stride, out);
+  fss_dif_eval_kernel<<<pm_grid(n, 128, 1, 64), 128, 0, S(s)>>>(b, x_masked, nullptr, s0, bits, sigma_cw, s_cw, leaf, n, stride, out);
+  PM_LAUNCH_OK();
+}
+
+extern "C" int pm_fss_dif_eval_open(int b, const int64_t* r_own, const int64_t* r_peer, const uint64_t* s0, const uint8_t* bits,
+                                    const uint64_t* sigma_cw, const uint64_t* s_cw, const int32_t* leaf, size_t n, size_t stride,
+                                    int64_t* out, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG((b == 0 || b == 1) && r_own && r_peer && s0 && bits && sigma_cw && s_cw && leaf && out && stride >= n);
+  fss_dif_eval_kernel<<<pm_grid(n, 128, 1, 64), 128, 0, S(s)>>>(b, r_own, r_peer, s0, bits, sigma_cw, s_cw, leaf, n, stride, out);
   PM_LAUNCH_OK();
 }
 

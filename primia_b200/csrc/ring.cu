@@ -402,6 +402,29 @@ __global__ void combine_mul_kernel(int j, const u64* __restrict__ delta, const u
   }
 }
 
+// spdz_mask of BOTH operands of an elementwise product in one pass (spdz.py:22-45): delta_j = x_j - a_j, eps_j = y_j - b_j
+__global__ void mask2_kernel(const u64* __restrict__ x, const u64* __restrict__ a, const u64* __restrict__ y, const u64* __restrict__ b,
+                             u64* __restrict__ d, u64* __restrict__ e, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { d[i] = x[i] - a[i]; e[i] = y[i] - b[i]; }
+}
+
+// spdz_compute for same-shape operands with the two openings fused (spdz.py:64-122,162-163): delta = d_own + d_peer,
+// eps = e_own + e_peer are formed in registers (the peer pointers may be peer-mapped), never stored
+__global__ void combine_mul_open_kernel(int j, const u64* __restrict__ d_own, const u64* __restrict__ d_peer,
+                                        const u64* __restrict__ e_own, const u64* __restrict__ e_peer, const u64* __restrict__ a,
+                                        const u64* __restrict__ b, const u64* __restrict__ c, size_t n, u64* __restrict__ z) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const u64 d = d_own[i] + d_peer[i], e = e_own[i] + e_peer[i];
+    u64 v = d * b[i] + a[i] * e + c[i];
+    if (j == 0) v += d * e;
+    z[i] = v;
+  }
+}
+
 // exact C-style (truncating) int64 division by a positive invariant divisor without the ~100-instruction emulated
 // 64-bit divide: two double-precision quotient estimates, each followed by an exact remainder in wrapping integer
 // arithmetic, then at most two unit corrections.  inv_d = 1.0 / d.
@@ -633,6 +656,23 @@ int pm_spdz_mask_i64(const int64_t* x, const int64_t* a, int64_t* delta, size_t 
   if (n == 0) return PM_OK;
   PM_CHECK_ARG(x && a && delta);
   sub_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(x, a, delta, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_mask2_i64(const int64_t* x, const int64_t* a, const int64_t* y, const int64_t* b, int64_t* delta, int64_t* eps, size_t n,
+                      pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG(x && a && y && b && delta && eps);
+  mask2_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>((const u64*)x, (const u64*)a, (const u64*)y, (const u64*)b, (u64*)delta, (u64*)eps, n);
+  PM_LAUNCH_OK();
+}
+
+int pm_spdz_combine_mul_open_i64(int j, const int64_t* d_own, const int64_t* d_peer, const int64_t* e_own, const int64_t* e_peer,
+                                 const int64_t* a, const int64_t* b, const int64_t* c, size_t n, int64_t* z, pm_stream_t s) {
+  if (n == 0) return PM_OK;
+  PM_CHECK_ARG((j == 0 || j == 1) && d_own && d_peer && e_own && e_peer && a && b && c && z);
+  combine_mul_open_kernel<<<pm_grid(n, 256), 256, 0, S(s)>>>(j, (const u64*)d_own, (const u64*)d_peer, (const u64*)e_own,
+                                                             (const u64*)e_peer, (const u64*)a, (const u64*)b, (const u64*)c, n, (u64*)z);
   PM_LAUNCH_OK();
 }
 

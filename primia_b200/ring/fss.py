@@ -107,6 +107,17 @@ def dif_eval(b: int, x_masked, win: FSSWindow):
     return out
 
 
+def dif_eval_open(b: int, r_own, r_peer, win: FSSWindow):
+    """DIF.eval on (r_own + r_peer) mod 2^32: the opening of the masked difference (fss.py:158) happens inside the kernel"""
+    x = r_own.contiguous()
+    assert x.numel() == win.n == r_peer.numel(), (x.shape, win.n)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        call("pm_fss_dif_eval_open", int(b), ptr(x), ptr(r_peer), _p(win.s0), _p(win.bits), _p(win.sigma_cw), _p(win.s_cw),
+             _p(win.leaf), win.n, win.stride, ptr(out), stream())
+    return out
+
+
 def mask_builder(x1, x2, alpha_share):
     """fss.py:189-204: x1 - x2 + alpha (either operand may be None = public 0)"""
     ref = x1 if x1 is not None else x2
@@ -177,6 +188,16 @@ def le(x1_shares, x2_shares, parties, provider=None):
         provider.provide_primitives(parties=parties, **e.kwargs_)
         return le(x1_shares, x2_shares, parties, provider)
     r = [mask_builder(x1_shares[j], x2_shares[j], wins[j].alpha) for j in range(2)]
+    from . import spdz as _spdz
+
+    if _spdz.FUSE_OPEN:
+        peers = _spdz.peer_views(parties, r)
+        out = []
+        for j, p in enumerate(parties):
+            win = p.crypto_store.get_keys(op=OP, n_instances=n, remove=True)
+            out.append(dif_eval_open(j, r[j], peers[j].contiguous(), win).view(ref[j].shape))
+        release_after_peer_reads(parties)
+        return out
     masked = []
     for j, p in enumerate(parties):
         peer = r[1 - j]

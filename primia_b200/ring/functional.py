@@ -155,29 +155,13 @@ def prepare_bn_side(inv_std: FixedPrecisionTensor, weight: FixedPrecisionTensor,
     return BNSide((((C,), (P, C)), ((P, C), (C,))), **out)
 
 
-def _exchange(parties, shares):
-    """the event edges of ``open_shares`` for kernels that read the peer's masked share themselves: returns, per party, the
-    peer's tensor (peer-mapped pointer or a staged copy)"""
-    from .spdz import _ensure_peer
-
-    peers = []
-    for j, p in enumerate(parties):
-        peer = shares[1 - j]
-        if peer.device != p.device:
-            torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(peer.device))
-            if not _ensure_peer(p.device, peer.device):
-                peer = peer.to(p.device)
-        peers.append(peer)
-    return peers
-
-
 def batch_norm_prepared(input: FixedPrecisionTensor, running_mean, bias, side: BNSide):
     """online half of batch_norm with ``side`` from the offline phase: three elementwise passes per party, NCHW throughout
          eps1_j   = x_j - mean_j[c] - b1_j
          delta2_j = trunc(s1_j[c] * open(eps1) + d1_j) - a2_j
          out_j    = trunc(s2_j[c] * open(delta2) + d2_j) + bias_j[c]
     -- the same shares as the op-by-op evaluation (tests/test_ring_gpu.py)."""
-    from .spdz import release_after_peer_reads
+    from .spdz import peer_views, release_after_peer_reads
 
     ast = input.child
     parties = ast.parties
@@ -188,10 +172,10 @@ def batch_norm_prepared(input: FixedPrecisionTensor, running_mean, bias, side: B
         for key in side.keys:
             p.crypto_store.get_keys(op="mul", shapes=key, remove=True)
     e1 = [ops.spdz_affine(ast.child[j], None, None, None, 1, mean[j], -1, side.b1[j], -1, C, HW) for j in range(2)]
-    pe = _exchange(parties, e1)
+    pe = peer_views(parties, e1)
     d2 = [ops.spdz_affine(e1[j], pe[j], side.s1[j], side.d1[j], D, None, 0, side.a2[j], -1, C, HW) for j in range(2)]
     release_after_peer_reads(parties)
-    pd = _exchange(parties, d2)
+    pd = peer_views(parties, d2)
     out = [ops.spdz_affine(d2[j], pd[j], side.s2[j], side.d2[j], D, bs[j], 1, None, 0, C, HW) for j in range(2)]
     release_after_peer_reads(parties)
     return input._new(ast._new(out))

@@ -101,6 +101,26 @@ def mask(x, a):
     return d
 
 
+def mask2(x, a, y, b):
+    """spdz_mask of both operands of a same-shape product in one pass: (x - a, y - b)"""
+    x, a, y, b = map(_chk, (x, a, y, b))
+    assert x.shape == a.shape == y.shape == b.shape, (x.shape, a.shape, y.shape, b.shape)
+    d, e = torch.empty_like(x), torch.empty_like(y)
+    with torch.cuda.device(x.device):
+        call("pm_spdz_mask2_i64", ptr(x), ptr(a), ptr(y), ptr(b), ptr(d), ptr(e), x.numel(), stream())
+    return d, e
+
+
+def combine_mul_open(j, d_own, d_peer, e_own, e_peer, a, b, c):
+    """spdz_compute (same-shape "mul") with both openings fused: delta = d_own + d_peer, eps = e_own + e_peer in registers"""
+    d_own, d_peer, e_own, e_peer, a, b, c = map(_chk, (d_own, d_peer, e_own, e_peer, a, b, c))
+    z = torch.empty_like(c)
+    with torch.cuda.device(d_own.device):
+        call("pm_spdz_combine_mul_open_i64", j, ptr(d_own), ptr(d_peer), ptr(e_own), ptr(e_peer), ptr(a), ptr(b), ptr(c),
+             c.numel(), ptr(z), stream())
+    return z
+
+
 def mask_im2col(x, a, kh, kw, stride, pad, dil=1):
     x, a = _chk(x), _chk(a)
     B, C, H, W = x.shape

@@ -17,6 +17,8 @@ from __future__ import annotations
 from collections import defaultdict
 from typing import Dict, List, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -336,8 +338,45 @@ def release_after_peer_reads(parties):
                 torch.cuda.current_stream(d).wait_event(evs[o])
 
 
+# PRIMIA_FUSE_OPEN=0: every opening is its own launch (mask, mask, open, open, combine -- the reference's message pattern one to
+# one); 1: same-shape products mask both operands in one pass and open them inside the combine kernel; DIF.eval opens its input
+FUSE_OPEN = os.environ.get("PRIMIA_FUSE_OPEN", "1") != "0"
+
+
+def peer_views(parties, shares):
+    """the event edges of ``open_shares`` for kernels that read the peer's masked share themselves: per party, the peer's
+    tensor (peer-mapped pointer, or a staged copy when no P2P mapping exists)"""
+    peers = []
+    for j, p in enumerate(parties):
+        peer = shares[1 - j]
+        if peer.device != p.device:
+            torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(peer.device))
+            if not _ensure_peer(p.device, peer.device):
+                peer = peer.to(p.device)
+        peers.append(peer)
+    return peers
+
+
 def spdz_mul(op: str, x_shares, y_shares, parties, provider: TripleProvider = None):
     """spdz.py:125-197.  x_shares / y_shares: per-party tensors. Returns per-party output shares."""
+    if FUSE_OPEN and op == "mul" and x_shares[0].shape == y_shares[0].shape:
+        shapes = (x_shares[0].shape, y_shares[0].shape)
+        try:
+            tri = [p.crypto_store.get_keys(op=op, shapes=shapes, n_instances=1, remove=False) for p in parties]
+        except EmptyCryptoPrimitiveStoreError as e:
+            if provider is None or any(p.crypto_store.force_preprocessing for p in parties):
+                raise
+            provider.provide_primitives(parties=parties, **e.kwargs_)
+            return spdz_mul(op, x_shares, y_shares, parties, provider)
+        masked = [ops.mask2(x_shares[j], tri[j][0], y_shares[j], tri[j][1]) for j in range(2)]
+        pd = peer_views(parties, [m[0] for m in masked])
+        pe = peer_views(parties, [m[1] for m in masked])
+        out = []
+        for j, p in enumerate(parties):
+            a, b, c = p.crypto_store.get_keys(op=op, shapes=shapes, n_instances=1, remove=True)
+            out.append(ops.combine_mul_open(j, masked[j][0], pd[j], masked[j][1], pe[j], a, b, c))
+        release_after_peer_reads(parties)
+        return out
     try:
         masked = [spdz_mask(p, x_shares[j], y_shares[j], op) for j, p in enumerate(parties)]
     except EmptyCryptoPrimitiveStoreError as e:

@@ -165,6 +165,11 @@ class AdditiveSharingTensor:
 
     def relu(self):
         """additive_shared.py:922-925"""
+        from . import fss, spdz
+
+        if spdz.FUSE_OPEN:
+            # zero = self - self is, share by share, exactly 0: mask_builder takes it as the public-0 operand (fss.py:189-204)
+            return self * self._new(fss.le([None, None], self.child, self.parties, self.provider))
         zero = self - self
         return self * (self >= zero)
 

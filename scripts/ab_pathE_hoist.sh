@@ -1,6 +1,6 @@
 #!/bin/bash
 # one B200: ring / FSS parity incl. the hoisted weight side, then the path E bench line hoisted vs not
-timeout 900 python -m pytest tests/test_ring_gpu.py tests/test_fss_gpu.py -m gpu -q -x 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_ring_gpu.py tests/test_fss_gpu.py tests/test_entrypoints_gpu.py -m gpu -q -x 2>&1 | tail -8
 for h in 1 0; do
   echo "== PRIMIA_HOIST_WEIGHT_SIDE=$h"
   PRIMIA_HOIST_WEIGHT_SIDE=$h timeout 400 python bench.py --path E --steps 3 --no-cpu 2>/dev/null | python -c "
