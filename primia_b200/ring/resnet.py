@@ -22,6 +22,7 @@ from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
 # operands, Newton iterations, op-by-op BatchNorm) as the reference does per call; 1: everything that depends only on the model
 # and the primitives moves to the offline graph (EncryptedResNet18.prepare_offline_side)
 HOIST_WEIGHT_SIDE = os.environ.get("PRIMIA_HOIST_WEIGHT_SIDE", "1") != "0"
+HOIST_PARTS = set(os.environ.get("PRIMIA_HOIST_PARTS", "newton,conv,bn").split(","))   # bisecting aid: which halves are hoisted
 
 # (name, Cin, H_in, Cout, k, stride, pad) for a 224x224 input -- torchlib/models.py:379-405,425-464
 RESNET18_CONVS = [("conv1", 3, 224, 64, 7, 2, 3)]
@@ -279,7 +280,8 @@ class EncryptedResNet18:
             if p.device != pdev:
                 torch.cuda.current_stream(p.device).wait_stream(torch.cuda.current_stream(pdev))
         self.hoisted_inv, self.bnside = None, {}
-        if T.FUSE_NEWTON and self.rng is not None and self.rng.static:
+        self.wside = {}
+        if "newton" in HOIST_PARTS and T.FUSE_NEWTON and self.rng is not None and self.rng.static:
             snaps = [p.crypto_store.export_state() for p in self.parties]
             mode, cur = self.rng.mode, self.rng.cursor
             self.rng.mode, self.rng.cursor = "replay", 0       # the constants' sharings are the first entries of a forward
@@ -288,8 +290,9 @@ class EncryptedResNet18:
             for p, st in zip(self.parties, snaps):
                 p.crypto_store.import_state(st)
             self.hoisted_inv = inv
-        self.prepare_weight_side(batch)
-        if self.hoisted_inv is not None:
+        if "conv" in HOIST_PARTS:
+            self.prepare_weight_side(batch)
+        if self.hoisted_inv is not None and "bn" in HOIST_PARTS:
             self.prepare_bn_side(batch)
 
     def prepare_bn_side(self, batch: int = 1):
@@ -389,7 +392,14 @@ class _MultiDeviceCapture:
     def __init__(self, devices):
         self.devices = list(devices)
         self.graph = torch.cuda.CUDAGraph()
-        self.pools = {d: torch.cuda.MemPool() for d in self.devices[1:]}
+        # a MemPool registers its reference with the allocator of the device that is CURRENT when it is constructed: built under
+        # another device, the pool's use count on `d` drops to zero when the capture ends and the next empty_cache() -- every
+        # torch.cuda.graph capture starts with one -- cudaFree()s the segments that hold only capture-time temporaries, which the
+        # graph still writes on replay (found as an illegal address in the second replay of the 3-GPU offline graph)
+        self.pools = {}
+        for d in self.devices[1:]:
+            with torch.cuda.device(d):
+                self.pools[d] = torch.cuda.MemPool()
         self.streams = {d: torch.cuda.Stream(d) for d in self.devices[1:]}
         # torch.cuda.graph's default capture stream is a process-wide singleton living on whichever device captured first:
         # a capture on another GPU must bring its own stream or nothing is recorded
