@@ -6,7 +6,7 @@ OUT=gpurun_out
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
     --log-file $OUT/r02_launches_raw.csv python scripts/prof_targets.py train > $OUT/r02_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"stem_pool_bn_bwd|bn_relu_maxpool|bn_bwd_bf16|bn_fwd_bf16|conv_halo|wgrad_halo|wgrad_tma|stem_kernel|conv_tma|dgrad_s2" \
-    --launch-skip 96 -c 96 -o /tmp/r02_full python scripts/prof_targets.py train > $OUT/r02_ncu2.log 2>&1
+    -k regex:"stem_pool_bn_bwd|stem_pool_reduce|head_fused|bn_relu_maxpool|bn_bwd_bf16|bn_fwd_bf16|conv_halo|wgrad_halo|wgrad_tma|stem_kernel|conv_tma|dgrad_s2" \
+    --launch-skip 98 -c 100 -o /tmp/r02_full python scripts/prof_targets.py train > $OUT/r02_ncu2.log 2>&1
 ncu -i /tmp/r02_full.ncu-rep --page raw --csv > $OUT/r02_full_raw.csv 2>>$OUT/r02_ncu2.log
 ls -la /tmp/r02_full.ncu-rep $OUT/r02_full_raw.csv
