@@ -188,7 +188,7 @@ def cpu_baseline_sample(seconds_cap=25.0):
     m = O.resnet18(seed=42)
     opt = O.make_optimizer(m)
     loss_fn = O.make_loss()
-    Bs = 16
+    Bs = 64   # the workload's own batch (C2: 64 images per hospital per step)
     g = torch.Generator().manual_seed(42)
     x, y = torch.randn(Bs, 3, 224, 224, generator=g), torch.randint(0, 3, (Bs,), generator=g)
     O.local_step(m, opt, loss_fn, x, y)  # warm-up
@@ -197,7 +197,7 @@ def cpu_baseline_sample(seconds_cap=25.0):
         O.local_step(m, opt, loss_fn, x, y)
         n += 1
         dt = time.perf_counter() - t0
-        if dt > seconds_cap or n >= 6:
+        if dt > seconds_cap or (n >= 8 and dt > 10.0) or n >= 40:   # ~10-25 s of CPU work
             break
     return {"value": Bs * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": f"{n} local steps of {Bs} images (fwd+bwd+Adam) with the torch-CPU fp32 oracle, {torch.get_num_threads()} threads"}
