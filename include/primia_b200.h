@@ -423,6 +423,32 @@ int pm_dp_add_noise_f32(float* g, size_t n, float stddev, uint64_t seed, uint64_
 /* g = (g + a * x) * post  (explicit noise tensor, tests) */
 int pm_dp_axpy_scale_f32(float* g, const float* x, float a, float post, size_t n, pm_stream_t s);
 
+/* ----- training-side image front end
+ * torchlib/dataloader.py:138-217 create_albu_transform, per image on the CPU in the reference: torchvision RandomAffine (PIL AFFINE,
+ * NEAREST, fill 0) -> albumentations Resize(inference_resolution) (cv::resize 8U INTER_LINEAR) -> RandomCrop(train_resolution) ->
+ * VerticalFlip / GaussNoise -> ToFloat(255) -> Normalize(mean, std).  One launch turns the raw uint8 images of a batch into the fp32
+ * NCHW batch; PIL's 16.16 and OpenCV's 11-bit fixed-point arithmetic are reproduced bit for bit (tests/test_oracle_augment.py pins the
+ * restatement to the libraries, tests/test_augment_gpu.py the kernel to the restatement).  The random parameters are drawn on the host.
+ *   src      packed uint8 images, HWC, sample b at src + samples[b].src_off
+ *   tables   int32; sample b's eight resize tables of R entries each at tables + samples[b].tab_off:
+ *            sx0 sx1 ax0 ax1 (columns) sy0 sy1 by0 by1 (rows) -- cv::resize's offsets and cvRound(fraction * 2048) coefficients
+ *   mean, rstd   HOST pointers, Cout floats each: Normalize's mean and reciprocal(std)
+ *   out      fp32 [B, Cout, T, T]; out_u8 (may be NULL): the uint8 image before ToFloat, same layout (tests) */
+typedef struct {
+  int64_t src_off;      /* byte offset of the image in src */
+  int32_t Hs, Ws, C;    /* source height, width, channels (1 or 3) */
+  int32_t tab_off;      /* int32 offset of the resize tables */
+  int32_t fix[6];       /* PIL affine_fixed coefficients: FIX(a) FIX(b) FIX(c + a/2 + b/2) FIX(d) FIX(e) FIX(f + d/2 + e/2) */
+  int32_t cy, cx;       /* RandomCrop offset inside the resized R x R image */
+  int32_t flip;         /* VerticalFlip */
+  int32_t area2;        /* source is exactly 2R x 2R: cv::resize uses the 2x2 box mean */
+  float noise_sigma;    /* GaussNoise on the uint8 image: 0 = off */
+  uint32_t reserved;
+  uint64_t noise_seed;
+} pm_aug_sample_t;
+int pm_augment_batch_u8_f32(const uint8_t* src, const pm_aug_sample_t* samples, const int32_t* tables, int B, int R, int T, int Cout,
+                            const float* mean, const float* rstd, float* out, uint8_t* out_u8, pm_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

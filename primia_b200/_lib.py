@@ -45,6 +45,15 @@ class NewtonP2PJob(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("v", "a", "b", "c", "k", "x")] + [("C", ctypes.c_int)]
 
 
+class AugSample(ctypes.Structure):
+    """pm_aug_sample_t"""
+
+    _fields_ = [("src_off", ctypes.c_int64), ("Hs", ctypes.c_int32), ("Ws", ctypes.c_int32), ("C", ctypes.c_int32),
+                ("tab_off", ctypes.c_int32), ("fix", ctypes.c_int32 * 6), ("cy", ctypes.c_int32), ("cx", ctypes.c_int32),
+                ("flip", ctypes.c_int32), ("area2", ctypes.c_int32), ("noise_sigma", ctypes.c_float), ("reserved", ctypes.c_uint32),
+                ("noise_seed", ctypes.c_uint64)]
+
+
 _SCALARS = {
     "int": ctypes.c_int,
     "size_t": ctypes.c_size_t,
