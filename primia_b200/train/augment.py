@@ -6,8 +6,9 @@ distributions of ``RandomAffine.get_params`` and albumentations' ``get_params`` 
 are produced on the hospital's GPU by ``pm_augment_batch_u8_f32`` (csrc/augment.cu), which reproduces PIL's and OpenCV's
 fixed-point arithmetic bit for bit (tests/test_augment_gpu.py, against oracle/augment_oracle.py which is pinned to the libraries).
 
-Transforms of the reference's list that are off in its shipped configs (CLAHE aside) -- RandomGamma, Blur, ElasticTransform,
-... (dataloader.py:159-198) -- are not built; asking for one raises."""
+Not built (asking for one raises): CLAHE -- which the shipped pneumonia configs switch on; on 3-channel images it runs on the L
+plane of an 8-bit RGB -> LAB -> RGB round trip (dataloader.py:150-156) -- and the optional transforms those configs leave off:
+RandomGamma, Blur, ElasticTransform, ... (dataloader.py:159-198)."""
 from __future__ import annotations
 
 import ctypes
