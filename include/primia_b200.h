@@ -448,6 +448,17 @@ typedef struct {
 } pm_aug_sample_t;
 int pm_augment_batch_u8_f32(const uint8_t* src, const pm_aug_sample_t* samples, const int32_t* tables, int B, int R, int T, int Cout,
                             const float* mean, const float* rstd, float* out, uint8_t* out_u8, pm_stream_t s);
+/* clahe = yes (dataloader.py:150-156: a.CLAHE(clip_limit=(1, 1), always_apply) after the crop, before the flip / noise group):
+ * cv::CLAHE_Impl (clahe.cpp) restated bit for bit for T divisible by `tiles`.  Three launches: pm_augment_batch_u8_f32 with
+ * Cout = 1, out = NULL and flip / noise cleared writes the uint8 crop [B,T,T]; pm_clahe_luts_u8 builds the per-tile tables
+ * luts [B, tiles*tiles, 256]; pm_augment_clahe_finish_f32 blends them per pixel and runs the tail of the pipeline.
+ * 3-channel models (albumentations: RGB -> LAB, CLAHE on L, LAB -> RGB) are served for GREY sources, the X-ray case: pre[256] =
+ * L of the grey pixel (v, v, v), post[256][3] = RGB of (L', 128, 128), both OpenCV's own 8-bit conversion tabulated
+ * (primia_b200/train/_lab_tables.py); pre / post NULL = single-channel model. */
+int pm_clahe_luts_u8(const uint8_t* img, const uint8_t* pre, int B, int T, int tiles, float clip_limit, uint8_t* luts, pm_stream_t s);
+int pm_augment_clahe_finish_f32(const uint8_t* img, const uint8_t* pre, const uint8_t* luts, const uint8_t* post,
+                                const pm_aug_sample_t* samples, int B, int T, int tiles, int Cout, const float* mean, const float* rstd,
+                                float* out, uint8_t* out_u8, pm_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,74 @@ def resize_linear_u8(src, R):
     return out.astype(np.uint8)
 
 
+def clahe_u8(src, clip_limit=1.0, tiles=8):
+    """cv2.createCLAHE(clipLimit, (tiles, tiles)).apply(src) for uint8 [H,W] with H, W divisible by ``tiles`` (clahe.cpp
+    CLAHE_CalcLut_Body + CLAHE_Interpolation_Body): per-tile histogram, clip at max(int(clip * area / 256), 1), excess spread
+    evenly (+1 every 256 // residual bins for the remainder), LUT = cvRound(cumsum * 255 / area) with float32 products, then
+    every pixel blends the four neighbouring tiles' LUTs bilinearly in float32 (separately rounded products) and cvRounds."""
+    H, W = src.shape
+    assert H % tiles == 0 and W % tiles == 0, "the reflect-padded case of CLAHE_Impl::apply is not restated"
+    th, tw = H // tiles, W // tiles
+    area = th * tw
+    lut_scale = np.float32(255.0) / np.float32(area)
+    clip = max(int(clip_limit * area / 256), 1) if clip_limit > 0 else 0
+    luts = np.zeros((tiles, tiles, 256), dtype=np.uint8)
+    for ty in range(tiles):
+        for tx in range(tiles):
+            h = np.bincount(src[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw].reshape(-1), minlength=256).astype(np.int64)
+            if clip > 0:
+                clipped = int(np.maximum(h - clip, 0).sum())
+                h = np.minimum(h, clip)
+                batch = clipped // 256
+                residual = clipped - batch * 256
+                h += batch
+                if residual:
+                    step = max(256 // residual, 1)
+                    i = 0
+                    while i < 256 and residual > 0:
+                        h[i] += 1
+                        i += step
+                        residual -= 1
+            luts[ty, tx] = np.clip(np.rint(np.cumsum(h).astype(np.float32) * lut_scale), 0, 255).astype(np.uint8)
+    f32 = np.float32
+
+    def axis(n, t):
+        pf = np.arange(n, dtype=np.float32) * (f32(1.0) / f32(t)) - f32(0.5)
+        p1 = np.floor(pf).astype(np.int64)
+        a = (pf - p1.astype(np.float32)).astype(np.float32)
+        return np.maximum(p1, 0), np.minimum(p1 + 1, tiles - 1), a, (f32(1.0) - a).astype(np.float32)
+
+    tx1, tx2, xa, xa1 = axis(W, tw)
+    ty1, ty2, ya, ya1 = axis(H, th)
+    v = src.astype(np.int64)
+    L = luts.astype(np.float32)
+    l11, l12 = L[ty1[:, None], tx1[None, :], v], L[ty1[:, None], tx2[None, :], v]
+    l21, l22 = L[ty2[:, None], tx1[None, :], v], L[ty2[:, None], tx2[None, :], v]
+    top = ((l11 * xa1[None, :]) + (l12 * xa[None, :])) * ya1[:, None]
+    bot = ((l21 * xa1[None, :]) + (l22 * xa[None, :])) * ya[:, None]
+    return np.clip(np.rint(top + bot), 0, 255).astype(np.uint8)
+
+
+def clahe_reference(img, clip_limit=1.0, tiles=8):
+    """albumentations.augmentations.functional.clahe (0.4.x) through OpenCV itself: grey images directly, 3-channel images on the
+    L plane of an 8-bit RGB -> LAB -> RGB round trip"""
+    import cv2
+
+    mat = cv2.createCLAHE(clipLimit=clip_limit, tileGridSize=(tiles, tiles))
+    if img.ndim == 2 or img.shape[2] == 1:
+        return mat.apply(img)
+    lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+    lab[:, :, 0] = mat.apply(lab[:, :, 0])
+    return cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+
+
+def clahe_grey_rgb(v, grey_to_l, l_to_rgb, clip_limit=1.0, tiles=8):
+    """the 3-channel recipe for a GREY image (R = G = B = v): L = grey_to_l[v], CLAHE, (r, g, b) = l_to_rgb[L'] -- the two
+    tables are OpenCV's own conversion tabulated on grey pixels (scripts/make_lab_tables.py)"""
+    lp = clahe_u8(np.asarray(grey_to_l, dtype=np.uint8)[v], clip_limit, tiles)
+    return np.asarray(l_to_rgb, dtype=np.uint8).reshape(256, 3)[lp]
+
+
 def to_float_normalize(u8, mean, std):
     """albumentations ToFloat(max_value=255) then Normalize(mean, std, max_pixel_value=1.0): float32 throughout,
     (x / 255 - mean) * reciprocal(std); HWC uint8 -> CHW float32 (AlbumentationsTorchTransform permutes, dataloader.py:50-51)"""
@@ -121,18 +189,22 @@ def to_float_normalize(u8, mean, std):
     return np.ascontiguousarray(x.transpose(2, 0, 1))
 
 
-def restated_pipeline(src, matrix, R, T, cy, cx, vflip, mean, std):
-    """deterministic part of create_albu_transform with explicit random parameters; src uint8 [H,W] or [H,W,C]"""
+def restated_pipeline(src, matrix, R, T, cy, cx, vflip, mean, std, clahe=False, rgb_tables=None):
+    """deterministic part of create_albu_transform with explicit random parameters; src uint8 [H,W] or [H,W,C].
+    clahe: dataloader.py:150-156 (after the crop, before the flip); rgb_tables = (grey_to_l, l_to_rgb) makes a grey source a
+    3-channel image first (the RGB loader) and runs the LAB recipe"""
     w = affine_nearest_fixed(src, matrix)
     r = resize_linear_u8(w, R)
     c = r[cy:cy + T, cx:cx + T]
+    if clahe:
+        c = clahe_grey_rgb(c, *rgb_tables) if rgb_tables is not None else clahe_u8(np.ascontiguousarray(c))
     if vflip:
         c = c[::-1]
     return c, to_float_normalize(c, mean, std)
 
 
 # ------------------------------------------------------------------------------------------------ the real libraries
-def reference_pipeline(src, angle, translate, scale, shear, R, T, cy, cx, vflip, mean, std):
+def reference_pipeline(src, angle, translate, scale, shear, R, T, cy, cx, vflip, mean, std, clahe=False):
     """the same steps through torchvision/PIL and OpenCV themselves"""
     import cv2
     import torchvision.transforms.functional as TF
@@ -143,6 +215,8 @@ def reference_pipeline(src, angle, translate, scale, shear, R, T, cy, cx, vflip,
     arr = np.array(img)
     arr = cv2.resize(arr, (R, R), interpolation=cv2.INTER_LINEAR)              # albumentations Resize
     arr = arr[cy:cy + T, cx:cx + T]                                            # RandomCrop with explicit offsets
+    if clahe:
+        arr = clahe_reference(np.ascontiguousarray(arr))                        # FromFloat(uint8) is the identity on uint8 input
     if vflip:
         arr = np.ascontiguousarray(arr[::-1, ...])                             # VerticalFlip = cv2.flip(img, 0)
     return arr, to_float_normalize(arr, mean, std)

@@ -6,9 +6,11 @@ distributions of ``RandomAffine.get_params`` and albumentations' ``get_params`` 
 are produced on the hospital's GPU by ``pm_augment_batch_u8_f32`` (csrc/augment.cu), which reproduces PIL's and OpenCV's
 fixed-point arithmetic bit for bit (tests/test_augment_gpu.py, against oracle/augment_oracle.py which is pinned to the libraries).
 
-Not built (asking for one raises): CLAHE -- which the shipped pneumonia configs switch on; on 3-channel images it runs on the L
-plane of an 8-bit RGB -> LAB -> RGB round trip (dataloader.py:150-156) -- and the optional transforms those configs leave off:
-RandomGamma, Blur, ElasticTransform, ... (dataloader.py:159-198)."""
+``clahe = yes`` (the shipped pneumonia configs; dataloader.py:150-156) is cv::CLAHE restated bit for bit: two more launches between
+the crop and the flip / noise / normalise tail.  albumentations runs it on the L plane of an 8-bit RGB -> LAB -> RGB round trip for
+3-channel images; that is served for GREY sources (X-rays through the RGB loader) with OpenCV's conversion tabulated on grey pixels
+(_lab_tables.py) -- a true colour source with clahe raises.  Not built (asking for one raises): the optional transforms the shipped
+configs leave off -- RandomGamma, Blur, ElasticTransform, ... (dataloader.py:159-198)."""
 from __future__ import annotations
 
 import ctypes
@@ -19,7 +21,7 @@ import torch
 
 from .._lib import AugSample, PrimiaError, call, ptr, stream
 
-UNSUPPORTED = ("clahe", "randomgamma", "randombrightness", "blur", "elastic", "optical_distortion", "grid_distortion", "grid_shuffle",
+UNSUPPORTED = ("randomgamma", "randombrightness", "blur", "elastic", "optical_distortion", "grid_distortion", "grid_shuffle",
                "hsv", "invert", "cutout", "shadow", "fog", "sun_flare", "solarize", "equalize", "grid_dropout")
 
 
@@ -86,6 +88,10 @@ class GpuAugment:
         self.rstd = np.reciprocal(np.ascontiguousarray(std[: self.cout]), dtype=np.float32)   # albumentations normalize()
         self.rng = np.random.default_rng(seed)
         self._tables = {}
+        self.clahe = bool(getattr(args, "clahe", False))
+        self._lab = None
+        if self.clahe and self.T % 8:
+            raise PrimiaError("clahe: train_resolution must be divisible by the 8 x 8 tile grid (the reflect-padded case of cv::CLAHE is not built)")
 
     # ---- random parameters (host)
     def sample_params(self, Hs: int, Ws: int) -> dict:
@@ -150,9 +156,35 @@ class GpuAugment:
             dbuf = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(self.device)
             out = torch.empty((B, self.cout, T, T), dtype=torch.float32, device=self.device)
             u8 = torch.empty((B, self.cout, T, T), dtype=torch.uint8, device=self.device) if return_u8 else None
-            call("pm_augment_batch_u8_f32", ptr(src), ptr(dbuf), ptr(tables), B, R, T, self.cout,
-                 self.mean.ctypes.data_as(ctypes.c_void_p), self.rstd.ctypes.data_as(ctypes.c_void_p), ptr(out),
-                 ptr(u8) if u8 is not None else None, stream())
+            mean_p, rstd_p = self.mean.ctypes.data_as(ctypes.c_void_p), self.rstd.ctypes.data_as(ctypes.c_void_p)
+            if not self.clahe:
+                call("pm_augment_batch_u8_f32", ptr(src), ptr(dbuf), ptr(tables), B, R, T, self.cout, mean_p, rstd_p, ptr(out),
+                     ptr(u8) if u8 is not None else None, stream())
+            else:
+                # crop (no flip, no noise) -> per-tile CLAHE tables -> blend + flip + noise + ToFloat + Normalize
+                if self.cout == 3 and any(d.C != 1 for d in descs):
+                    raise PrimiaError("clahe on a colour source needs the full 8-bit RGB <-> LAB conversion, which is not built; "
+                                      "grey sources (X-rays through the RGB loader) are")
+                plain = (AugSample * B)()
+                ctypes.memmove(plain, descs, ctypes.sizeof(descs))
+                for d in plain:
+                    d.flip, d.noise_sigma = 0, 0.0
+                pbuf = torch.frombuffer(bytearray(bytes(plain)), dtype=torch.uint8).to(self.device)
+                crop = torch.empty((B, T, T), dtype=torch.uint8, device=self.device)
+                call("pm_augment_batch_u8_f32", ptr(src), ptr(pbuf), ptr(tables), B, R, T, 1, mean_p, rstd_p, None, ptr(crop), stream())
+                pre = post = None
+                if self.cout == 3:
+                    if self._lab is None:
+                        from ._lab_tables import GREY_TO_L, L_TO_RGB
+
+                        self._lab = (torch.frombuffer(bytearray(GREY_TO_L), dtype=torch.uint8).to(self.device),
+                                     torch.frombuffer(bytearray(L_TO_RGB), dtype=torch.uint8).to(self.device))
+                    pre, post = self._lab
+                luts = torch.empty((B, 64, 256), dtype=torch.uint8, device=self.device)
+                o = lambda t: ptr(t) if t is not None else None
+                call("pm_clahe_luts_u8", ptr(crop), o(pre), B, T, 8, ctypes.c_float(1.0), ptr(luts), stream())   # clip_limit = (1, 1)
+                call("pm_augment_clahe_finish_f32", ptr(crop), o(pre), ptr(luts), o(post), ptr(dbuf), B, T, 8, self.cout, mean_p, rstd_p,
+                     ptr(out), ptr(u8) if u8 is not None else None, stream())
         return (out, u8) if return_u8 else out
 
     def __call__(self, images):

@@ -20,10 +20,16 @@ def _args(**kw):
     return types.SimpleNamespace(**d)
 
 
-def _oracle(im, p, R, T, cout):
+def _oracle(im, p, R, T, cout, clahe=False):
     H, W = im.shape[:2]
     m = A.inverse_affine_matrix([W * 0.5, H * 0.5], p["angle"], p["translate"], p["scale"], p["shear"])
-    u8, f = A.restated_pipeline(im, m, R, T, p["cy"], p["cx"], p["flip"], MEAN, STD)
+    if clahe and cout == 3:
+        from primia_b200.train import _lab_tables as tab
+
+        u8, f = A.restated_pipeline(im, m, R, T, p["cy"], p["cx"], p["flip"], MEAN, STD, clahe=True,
+                                    rgb_tables=(list(tab.GREY_TO_L), list(tab.L_TO_RGB)))
+        return np.ascontiguousarray(u8.transpose(2, 0, 1)), f
+    u8, f = A.restated_pipeline(im, m, R, T, p["cy"], p["cx"], p["flip"], MEAN, STD, clahe=clahe)
     if u8.ndim == 2:
         u8 = u8[:, :, None]
     u8 = np.ascontiguousarray(u8.transpose(2, 0, 1))
@@ -54,6 +60,31 @@ def test_batch_equals_oracle_bit_for_bit(pretrained):
         ref_u8, ref_f = _oracle(im, p, R, T, aug.cout)
         assert np.array_equal(u8[i].cpu().numpy(), ref_u8), f"image {i} {im.shape}: uint8 stage differs"
         assert np.array_equal(out[i].cpu().numpy(), ref_f), f"image {i}: float stage differs"
+
+
+@pytest.mark.parametrize("pretrained", [True, False])
+def test_clahe_batch_equals_oracle_bit_for_bit(pretrained):
+    """clahe = yes (the shipped pneumonia configs): cv::CLAHE between the crop and the flip, on the L plane of the LAB round trip
+    for the 3-channel model -- the oracle's restatement is pinned to OpenCV in tests/test_oracle_augment.py"""
+    from primia_b200._lib import PrimiaError
+    from primia_b200.train.augment import GpuAugment
+
+    rng = np.random.default_rng(15)
+    R, T = 512, 224
+    aug = GpuAugment(_args(pretrained=pretrained, noise_prob=0.0, clahe=True), MEAN, STD, DEV, seed=5)
+    images = [np.clip(rng.normal(110, 45, (H, W)), 0, 255).astype(np.uint8) for H, W in [(1024, 1024), (640, 480), (333, 901), (512, 512)]]
+    images.append(np.full((300, 300), 90, dtype=np.uint8))        # flat image: every tile's histogram is one clipped spike
+    params = [aug.sample_params(*im.shape[:2]) for im in images]
+    params[0]["flip"], params[1]["flip"] = True, False
+    out, u8 = aug.apply(images, params, return_u8=True)
+    torch.cuda.synchronize()
+    for i, (im, p) in enumerate(zip(images, params)):
+        ref_u8, ref_f = _oracle(im, p, R, T, aug.cout, clahe=True)
+        assert np.array_equal(u8[i].cpu().numpy(), ref_u8), f"image {i} {im.shape}: uint8 stage differs"
+        assert np.array_equal(out[i].cpu().numpy(), ref_f), f"image {i}: float stage differs"
+    if pretrained:
+        with pytest.raises(PrimiaError):
+            aug.apply([rng.integers(0, 256, (300, 300, 3), dtype=np.uint8)], [params[0]])
 
 
 def test_identity_parameters_reproduce_a_plain_resize_crop():

@@ -106,4 +106,57 @@ def test_host_side_of_the_gpu_front_end_builds_the_oracles_tables():
     assert abs(flips - 0.75 * 0.2) < 0.03 and abs(noisy - 0.75 * 0.5) < 0.04      # albu_prob gates the group, then each p
     assert all(p["noise_sigma"] <= 0.05 for p in ps)
     with pytest.raises(PrimiaError):
-        G.GpuAugment(types.SimpleNamespace(**dict(vars(args), clahe=True)), [0.5], [0.25], device="cpu")
+        G.GpuAugment(types.SimpleNamespace(**dict(vars(args), blur=True)), [0.5], [0.25], device="cpu")
+    with pytest.raises(PrimiaError):   # clahe needs the crop to tile 8 x 8
+        G.GpuAugment(types.SimpleNamespace(**dict(vars(args), clahe=True, train_resolution=225)), [0.5], [0.25], device="cpu")
+    assert G.GpuAugment(types.SimpleNamespace(**dict(vars(args), clahe=True)), [0.5], [0.25], device="cpu").clahe
+
+
+@pytest.mark.parametrize("T", [224, 256, 96, 512])
+def test_clahe_restatement_equals_opencv(T):
+    rng = np.random.default_rng(T)
+    yy, xx = np.mgrid[0:T, 0:T]
+    cases = [rng.integers(0, 256, (T, T), dtype=np.uint8), np.clip(rng.normal(120, 40, (T, T)), 0, 255).astype(np.uint8),
+             ((np.sin(xx / 17.0) * 60 + np.cos(yy / 23.0) * 50 + 128) + rng.normal(0, 6, (T, T))).clip(0, 255).astype(np.uint8),
+             np.full((T, T), 77, dtype=np.uint8), (xx % 256).astype(np.uint8)]
+    for src in cases:
+        assert np.array_equal(A.clahe_u8(src), cv2.createCLAHE(clipLimit=1.0, tileGridSize=(8, 8)).apply(src))
+
+
+def test_lab_tables_are_opencvs_conversion_on_grey_pixels_and_the_rgb_recipe_follows():
+    from primia_b200.train import _lab_tables as tab
+
+    v = np.arange(256, dtype=np.uint8)
+    lab = cv2.cvtColor(np.stack([v, v, v], -1)[None], cv2.COLOR_RGB2LAB)[0]
+    assert (lab[:, 1:] == 128).all() and bytes(lab[:, 0].tolist()) == tab.GREY_TO_L
+    rgb = cv2.cvtColor(np.stack([v, np.full(256, 128, np.uint8), np.full(256, 128, np.uint8)], -1)[None], cv2.COLOR_LAB2RGB)[0]
+    assert bytes(rgb.reshape(-1).tolist()) == tab.L_TO_RGB
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        g = np.clip(rng.normal(120, 50, (224, 224)), 0, 255).astype(np.uint8)
+        ref = A.clahe_reference(np.stack([g] * 3, -1))                     # albumentations' recipe through OpenCV
+        got = A.clahe_grey_rgb(g, list(tab.GREY_TO_L), list(tab.L_TO_RGB))
+        assert np.array_equal(ref, got)
+
+
+def test_pipeline_with_clahe_equals_the_libraries():
+    from primia_b200.train import _lab_tables as tab
+
+    rng = np.random.default_rng(10)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    for i in range(4):
+        H, W = int(rng.integers(300, 1100)), int(rng.integers(300, 1100))
+        g = np.clip(rng.normal(110, 45, (H, W)), 0, 255).astype(np.uint8)
+        R, T = 512, 224
+        angle, translate, scale, shear = _params(rng, W, H)
+        cy, cx, flip = int(rng.integers(0, R - T + 1)), int(rng.integers(0, R - T + 1)), bool(i % 2)
+        m = A.inverse_affine_matrix([W * 0.5, H * 0.5], angle, translate, scale, shear)
+        # single-channel model
+        ref_u8, ref_f = A.reference_pipeline(g, angle, translate, scale, shear, R, T, cy, cx, flip, mean, std, clahe=True)
+        got_u8, got_f = A.restated_pipeline(g, m, R, T, cy, cx, flip, mean, std, clahe=True)
+        assert np.array_equal(ref_u8, got_u8) and np.array_equal(ref_f, got_f)
+        # 3-channel model fed by the RGB loader (grey replicated)
+        ref_u8, ref_f = A.reference_pipeline(np.stack([g] * 3, -1), angle, translate, scale, shear, R, T, cy, cx, flip, mean, std, clahe=True)
+        got_u8, got_f = A.restated_pipeline(g, m, R, T, cy, cx, flip, mean, std, clahe=True,
+                                            rgb_tables=(list(tab.GREY_TO_L), list(tab.L_TO_RGB)))
+        assert np.array_equal(ref_u8, got_u8) and np.array_equal(ref_f, got_f)
