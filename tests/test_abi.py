@@ -71,3 +71,37 @@ def test_every_kernel_launched_with_the_pdl_attribute_waits_on_its_predecessor()
             depth += (src[i] == "{") - (src[i] == "}")
             i += 1
         assert "pm_pdl_sync" in src[m.end():i], f"{n} is launched with the PDL attribute but never waits"
+
+
+def test_ctypes_mirrors_have_the_layout_the_c_compiler_gives_the_header_structs(tmp_path):
+    """include/primia_b200.h is plain C: compile a probe with gcc that prints sizeof / offsetof of every struct a binding has to
+    mirror, and hold primia_b200/_lib.py's ctypes.Structure classes to it (a drifted field would silently corrupt descriptors)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from primia_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    pairs = {"pm_conv_t": _lib.ConvDesc, "pm_wcvt_t": _lib.WCvt, "pm_newton_job_t": _lib.NewtonJob,
+             "pm_newton_p2p_job_t": _lib.NewtonP2PJob, "pm_aug_sample_t": _lib.AugSample}
+    lines = []
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _t in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "primia_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)   # the header is valid C
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = pairs[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == want, (cname, field, value, want)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
