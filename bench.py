@@ -334,7 +334,6 @@ def linear_layers_block(steps=3):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     parties = [ring.Party("model_owner", dev), ring.Party("data_owner", dev)]
     prov = ring.spdz.TripleProvider(ring.Party("crypto_provider", dev), seed=42)
-    from primia_b200 import _lib
     from primia_b200.ring import resnet as _rr
 
     lin = SharedLinearLayers(parties, prov, 10, 16)

@@ -8,7 +8,7 @@ import torch
 
 from . import ops
 from .spdz import EmptyCryptoPrimitiveStoreError, _key, open_planes, open_shares, spdz_compute
-from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
+from .tensors import FixedPrecisionTensor
 
 
 def _pre_conv(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):

@@ -14,9 +14,8 @@ import os
 import torch
 
 from . import functional as F
-from . import ops
-from .spdz import Party, TripleProvider
-from .tensors import AdditiveSharingTensor, FixedPrecisionTensor
+from .spdz import TripleProvider
+from .tensors import FixedPrecisionTensor
 
 # PRIMIA_HOIST_WEIGHT_SIDE=0: the online graph runs the whole protocol per layer (mask and open the weights, planarise all four
 # operands, Newton iterations, op-by-op BatchNorm) as the reference does per call; 1: everything that depends only on the model

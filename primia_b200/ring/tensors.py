@@ -9,7 +9,7 @@ import os
 import torch
 
 from . import ops
-from .spdz import Party, TripleProvider, spdz_mul
+from .spdz import TripleProvider, spdz_mul
 
 
 class ShareRNG:
