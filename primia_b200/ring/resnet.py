@@ -446,10 +446,14 @@ class EncryptedInferenceGraph:
                    and sharings of the Newton constant -- IN PLACE: the generating launches (Philox, ring GEMM c = a@b, DIF
                    keygen) were captured once, their output tensors are the graph's own allocations, and a device-side epoch
                    added to every Philox offset (pm_epoch_bump is the graph's first node) makes each replay draw fresh
-                   randomness.  No host bookkeeping, no staging copy.
-      online(img)  share input -> forward on shares -> reconstruct -> decode: ~1.4 k launches of mostly tiny kernels that are
-                   launch-bound when issued eagerly from Python.  The crypto-store bookkeeping (peek / pop,
-                   primitives.py:52-102) ran on the host at capture time.
+                   randomness.  No host bookkeeping, no staging copy.  The same graph then runs everything of the forward that
+                   depends on the model and the primitives but not on the image (EncryptedResNet18.prepare_offline_side):
+                   the Newton inverse square roots, the weight half of every Beaver convolution, the model-only operands of
+                   the BatchNorm products.
+      online(img)  share input -> forward on shares -> reconstruct -> decode: 554 launches (1497 without the hoisting and the
+                   fused openings) of mostly tiny kernels that are launch-bound when issued eagerly from Python.  The
+                   crypto-store bookkeeping (peek / pop, primitives.py:52-102) ran on the host at capture time, primitive for
+                   primitive as the op-by-op protocol would.
 
     Placement: with the two share holders on different GPUs (model_owner cuda:0, data_owner cuda:1,
     crypto provider cuda:2) both graphs are multi-device graphs: every opening is a kernel on the consuming GPU that loads the
