@@ -10,8 +10,8 @@ GPU each when three are visible, inference.py:154-158), the images tagged and lo
 crypto_provider=..., protocol="fss", requires_grad=False)`` (:279-286), ``model.pool`` and ``model.relu`` swapped (:289), and per
 image ``data.fix_precision(..).share(..).get()`` -> ``model(data)`` -> ``.get().float_prec()`` -> argmax (:292-317).  Every
 arithmetic step is the primia_b200 C ABI (Beaver matmuls on the int8 tensor cores, 80-step Newton BatchNorm, FSS ReLU /
-max-pool).  ``--cuda_graph`` replays the online phase of each image as one captured CUDA graph (same shares, ~1.4 k launches
-fewer host round trips); ``--precision_fractional`` defaults to the reference's 16.
+max-pool).  ``--cuda_graph`` runs each image as two captured CUDA graphs -- offline (primitives, Newton, the model-only halves of
+every Beaver product) and online (554 launches in one replay instead of ~1.5 k host round trips); same shares either way; ``--precision_fractional`` defaults to the reference's 16.
 
 Image files / albumentations are out of scope: the data set is ``--num_images`` synthetic normalised
 224 x 224 x 3 tensors (``--data_dir`` is accepted and ignored).

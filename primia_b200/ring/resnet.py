@@ -124,7 +124,7 @@ class SharedLinearLayers:
 
 
 class EncryptedLinearGraph:
-    """The online phase of ``SharedLinearLayers.forward`` captured once in a CUDA graph (the ~330 launches of one encrypted
+    """The online phase of ``SharedLinearLayers.forward`` captured once in a CUDA graph (the ~214 launches of one encrypted
     image are latency-bound at batch 1).  The Beaver triples live in static buffers: the offline phase generates fresh
     triples (crypto provider, Philox + ring GEMM) and copies them into those buffers, the online phase is one graph replay.
     The crypto-store bookkeeping (peek in spdz_mask / pop in spdz_compute, primitives.py:52-102) runs at capture time."""
