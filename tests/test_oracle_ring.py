@@ -191,3 +191,51 @@ def test_full_encrypted_forward_oracle_tracks_plaintext_model():
     # protocol accounting: 20 convs + fc matmul triples, 20 BN layers x 239 elementwise triples, 17 ReLUs + 4 pool steps
     assert tape.n_consts == 20 * 80
     assert tape.n_triples == 21 + 20 * 239 + 17 + 4
+
+
+def test_hoisted_protocol_algebra_equals_the_reference_protocol():
+    """The offline / online split the CUDA path runs (ring/functional.py prepare_weight_side, prepare_bn_side) is the reference's
+    spdz_mul (spdz.py:125-197) with the terms regrouped -- exact in Z_2^64.  Written here on the oracle's plain int64 tensors:
+
+      conv:  z_j = delta @ (b_j + [j=0] eps) + (a_j @ eps + c_j)
+      bn 1:  z_j = (a1_j + [j=0] delta1)[c] * eps1 + (delta1[c] * b1_j + c1_j)          inv_std [C] x (flat - mean) [P,C]
+      bn 2:  z_j = delta2 * (b2_j + [j=0] eps2)[c] + (a2_j * eps2[c] + c2_j)            normalized [P,C] x weight [C]
+    """
+    g = torch.Generator().manual_seed(21)
+    rnd = lambda *s: torch.randint(-(2 ** 63), 2 ** 63 - 1, s, dtype=torch.int64, generator=g)
+    share = lambda q: R.share_from_random(q, rnd(*q.shape))
+
+    def triple(ls, rs, op):
+        a, b = rnd(*ls), rnd(*rs)
+        c = R.build_triple_c(a, b, op)
+        return list(zip(share(a), share(b), share(c)))
+
+    # ---- Beaver matmul with the weight side known in advance
+    M, K, N = 12, 20, 8
+    x, w = share(rnd(M, K)), share(rnd(K, N))
+    tri = triple((M, K), (K, N), "matmul")
+    ref = R.spdz_mul("matmul", x, w, tri)
+    eps = sum(w[j] - tri[j][1] for j in range(2))                                       # offline: open(w - b)
+    b_eff = [tri[0][1] + eps, tri[1][1]]
+    c_prime = [torch.matmul(tri[j][0], eps) + tri[j][2] for j in range(2)]              # offline: a @ eps + c
+    delta = sum(x[j] - tri[j][0] for j in range(2))                                     # online: open(x - a)
+    got = [torch.matmul(delta, b_eff[j]) + c_prime[j] for j in range(2)]
+    assert all(torch.equal(got[j], ref[j]) for j in range(2))
+    # ---- BatchNorm's two broadcast products
+    P, C = 10, 6
+    inv, centered, gamma = share(rnd(C)), share(rnd(P, C)), share(rnd(C))
+    t1, t2 = triple((C,), (P, C), "mul"), triple((P, C), (C,), "mul")
+    ref1 = R.spdz_mul("mul", inv, centered, t1)
+    delta1 = sum(inv[j] - t1[j][0] for j in range(2))                                   # offline
+    s1 = [t1[0][0] + delta1, t1[1][0]]
+    d1 = [delta1 * t1[j][1] + t1[j][2] for j in range(2)]
+    eps1 = sum(centered[j] - t1[j][1] for j in range(2))                                # online
+    got1 = [s1[j] * eps1 + d1[j] for j in range(2)]
+    assert all(torch.equal(got1[j], ref1[j]) for j in range(2))
+    ref2 = R.spdz_mul("mul", ref1, gamma, t2)
+    eps2 = sum(gamma[j] - t2[j][1] for j in range(2))                                   # offline
+    s2 = [t2[0][1] + eps2, t2[1][1]]
+    d2 = [t2[j][0] * eps2 + t2[j][2] for j in range(2)]
+    delta2 = sum(ref1[j] - t2[j][0] for j in range(2))                                  # online
+    got2 = [delta2 * s2[j] + d2[j] for j in range(2)]
+    assert all(torch.equal(got2[j], ref2[j]) for j in range(2))
