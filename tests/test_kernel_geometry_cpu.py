@@ -119,3 +119,32 @@ def test_stride2_dgrad_parity_classes():
                         src = dyp[:, :, off_h:off_h + Ho, off_w:off_w + Wo]  # dy[i + off_h, j + off_w]
                         dx[:, :, ca::2, cb::2] += torch.einsum("bkij,kc->bcij", src, w[:, :, r, s])
         assert torch.allclose(dx, x.grad, atol=1e-12)
+
+
+def test_encrypted_resnet_conv_geometry_walks_the_forwards_size_arithmetic():
+    """ring/resnet.py conv_geometry(size): the (name, Cin, H_in, Cout, k, stride, pad) list the offline phase uses to find each
+    layer's triple -- equal to the 224 table, and consistent with torch's own conv / pool output sizes at other input sizes"""
+    import torch
+
+    from primia_b200.ring.resnet import RESNET18_CONVS, conv_geometry, triple_shapes
+
+    assert conv_geometry(224) == RESNET18_CONVS and len(RESNET18_CONVS) == 20
+    assert [n for n, _ in triple_shapes()] == [c[0] for c in RESNET18_CONVS] + ["fc"]
+    for size in (32, 64, 96, 100, 224, 256):
+        geo = {name: (C, H, Co, k, s, p) for name, C, H, Co, k, s, p in conv_geometry(size)}
+        x = torch.zeros(1, 3, size, size)
+        x = torch.nn.functional.conv2d(x, torch.zeros(64, 3, 7, 7), stride=2, padding=3)
+        assert geo["conv1"][1] == size
+        x = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+        for li, planes in enumerate((64, 128, 256, 512), start=1):
+            for bi in range(2):
+                C, H, Co, k, s, p = geo[f"layer{li}.{bi}.conv1"]
+                assert (C, H, Co) == (x.shape[1], x.shape[2], planes)
+                y = torch.nn.functional.conv2d(x, torch.zeros(Co, C, k, k), stride=s, padding=p)
+                C2, H2, Co2, k2, s2, p2 = geo[f"layer{li}.{bi}.conv2"]
+                assert (C2, H2) == (y.shape[1], y.shape[2])
+                if f"layer{li}.{bi}.downsample.0" in geo:
+                    Cd, Hd, Cod, kd, sd, pd = geo[f"layer{li}.{bi}.downsample.0"]
+                    d = torch.nn.functional.conv2d(x, torch.zeros(Cod, Cd, kd, kd), stride=sd, padding=pd)
+                    assert d.shape == y.shape
+                x = torch.nn.functional.conv2d(y, torch.zeros(Co2, C2, k2, k2), stride=s2, padding=p2)
